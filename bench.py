@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- coordinate updates/sec of the CGGibbs hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one Gibbs iteration (all p coordinates) of every chain resident on a GPU.  The default
+workload is the one the metric is quoted on: binomial-logit, n=1e6, p=1000, laplace(0,1) prior,
+w=0.5, 8 chains per GPU (64 chains over 8 GPUs, chain-parallel, weak scaling, no collective).
+
+value   whole-job updates/s with X, y already resident in HBM (device timed, CUDA events on the
+        engine's stream, max over ranks)
+e2e     the same through the C ABI with HOST (pinned) buffers: upload X/y, init the chains, run
+        `e2e_iters` iterations, download the samples -- all inside the timed region
+roofline  algorithmic bytes of the sweep kernel / its CUDA-event duration vs MEASURED_PEAKS.json
+cpu_baseline  the oracle port (CPU restatement of the R algorithm, NOT R) on the host cores, bounded sample
+--impl reference  the same CPU port as its own arm (R is not installed in this image)
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: family, n, p, prior, chains per GPU, w, K, init scale of beta0 ~ prior
+    "cfg3": dict(family="binomial", n=1_000_000, p=1000, prior="laplace", chains=8, w=0.5, K=8, init_scale=1.0,
+                 desc="binomial-logit n=1e6 p=1000 laplace(0,1) w=0.5, 8 chains/GPU (BASELINE configs[2])"),
+    "cfg2": dict(family="binomial", n=100_000, p=100, prior="normal", chains=4, w=0.5, K=8, init_scale=1.0,
+                 desc="binomial-logit n=1e5 p=100 normal(0,1) w=0.5, 4 chains (BASELINE configs[1])"),
+    "cfg4": dict(family="poisson", n=1_000_000, p=500, prior="student_t", chains=8, w=0.5, K=8, init_scale=0.0,
+                 desc="poisson-log n=1e6 p=500 student_t(4) w=0.5 K=8, 8 chains/GPU (BASELINE configs[3])"),
+    "cfg5shard": dict(family="gaussian", n=6_250_000, p=200, prior="normal", chains=1, w=0.5, K=8, init_scale=1.0,
+                      desc="gaussian n=6.25e6 (one of 8 row shards of n=5e7) p=200, 1 chain (BASELINE configs[4], local part)"),
+    "tiny": dict(family="binomial", n=20_000, p=20, prior="laplace", chains=4, w=0.5, K=8, init_scale=1.0,
+                 desc="tiny smoke workload"),
+}
+PRIOR_KW = {"normal": dict(prior="normal", prior_mu=0.0, prior_sigma=1.0),
+            "laplace": dict(prior="laplace", prior_mu=0.0, prior_sigma=1.0),
+            "student_t": dict(prior="student_t", prior_mu=0.0, prior_sigma=1.0, prior_df=4.0)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int)
+    ap.add_argument("--p", type=int)
+    ap.add_argument("--chains", type=int)
+    ap.add_argument("--family")
+    ap.add_argument("--prior")
+    ap.add_argument("--w", type=float)
+    ap.add_argument("--K", type=int)
+    ap.add_argument("--tau", type=float, default=0.5)
+    ap.add_argument("--driver", default="persistent", choices=["persistent", "stepwise"])
+    ap.add_argument("--rows-per-cta-min", type=int, default=0)
+    ap.add_argument("--e2e-iters", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--seed", type=int, default=42)
+    a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    for k in ("n", "p", "chains", "family", "prior", "w", "K"):
+        if getattr(a, k) is not None:
+            wl[k] = getattr(a, k)
+    wl["name"] = a.workload
+    return a, wl
+
+
+def draw_beta0(wl, rng, C):
+    p = wl["p"]
+    if wl["prior"] == "normal":
+        b = rng.standard_normal((C, p))
+    elif wl["prior"] == "laplace":
+        b = rng.laplace(0.0, 1.0, (C, p))
+    else:
+        b = rng.standard_t(4.0, (C, p))
+    return b * wl["init_scale"]      # reference: init_beta ~ prior (R/mcmcglm.R:208); poisson starts at 0 (exp overflow)
+
+
+def make_data(wl, device, seed):
+    """Synthetic X (column 0 == 1, rest N(0,1)), beta* ~ N(0, 1/p), y ~ family -- generated on the device.
+    Layout: tensor [p, n] row-major == column-major n x p with ld = n, exactly an R matrix."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    n, p = wl["n"], wl["p"]
+    X = torch.empty((p, n), dtype=torch.float64, device=device)
+    for j0 in range(0, p, 64):   # chunked: randn in fp64 without a second 8 GB temporary
+        j1 = min(p, j0 + 64)
+        X[j0:j1].normal_(generator=g)
+    X[0].fill_(1.0)
+    bt = torch.randn(p, dtype=torch.float64, device=device, generator=g) / (p ** 0.5)
+    eta = torch.mv(X.t(), bt)
+    if wl["family"] == "gaussian":
+        y = eta + torch.randn(n, dtype=torch.float64, device=device, generator=g)
+    elif wl["family"] == "binomial":
+        y = (torch.rand(n, dtype=torch.float64, device=device, generator=g) < torch.sigmoid(eta)).to(torch.float64)
+    else:
+        y = torch.poisson(torch.exp(eta), generator=g)
+    return X, y
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (pynvml; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return None
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_port_run(wl, Xh, yh, beta0, eta0, seconds, threads=None, per_thread_updates=None):
+    """Times the oracle port (CPU restatement of the R algorithm -- NOT R) on the host cores.
+    One independent chain per thread, the way parallel::mclapply would spread chains; each chain performs
+    the first m coordinate updates of iteration 1 from its prior-drawn beta0.  Returns (updates/s, info)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    oracle.lib()
+    m = oracle.make_model(wl["family"], sd=1.0, **PRIOR_KW[wl["prior"]])
+    cores = threads or os.cpu_count() or 1
+    C = beta0.shape[0]
+
+    def one(t, nupd):
+        c = t % C
+        t0 = time.perf_counter()
+        out = oracle.run_chain(m, Xh, yh, beta0[c], w=wl["w"], n_iter=1, seed=1234, chain=1000 + t, max_updates=nupd,
+                               compute_mu=True, eta0=eta0[c])
+        return time.perf_counter() - t0, out["n_eval"], out["rc"]
+
+    if per_thread_updates is None:
+        t1, _, _ = one(0, 1)    # calibrate on one update
+        per_thread_updates = int(max(2, min(wl["p"], round(seconds / max(t1, 1e-4)))))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        res = list(ex.map(lambda t: one(t, per_thread_updates), range(cores)))
+    wall = time.perf_counter() - t0
+    total = cores * per_thread_updates
+    evals = sum(r[1] for r in res)
+    info = {"cores": cores, "updates": total, "wall_s": wall, "evals_per_update": evals / total,
+            "sample": f"first {per_thread_updates} coordinate updates of iteration 1 on each of {cores} independent "
+                      f"chains (one per host thread), beta0 ~ prior, same X/y as the GPU run"}
+    return total / wall, info
+
+
+def main():
+    a, wl = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    if a.impl == "reference" and rank != 0:
+        return 0
+    multi = world > 1 and a.impl == "ours"
+    if multi:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this engine has no CPU fallback"}))
+        return 1
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from mcmcglm_b200 import Engine
+
+    n, p, C = wl["n"], wl["p"], wl["chains"]
+    X, y = make_data(wl, dev, a.seed)            # identical data on every rank (replicated, like the reference's workers)
+    rng = np.random.default_rng(a.seed + 1000 * rank)
+    beta0 = draw_beta0(wl, rng, C)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    def new_engine():
+        return Engine(n, p, family=wl["family"], sd=1.0, w=wl["w"], n_chains=C, K=wl["K"], device=local,
+                      driver=a.driver, seed=a.seed, chain_offset=rank * C, spec_tau=a.tau,
+                      rows_per_cta_min=a.rows_per_cta_min, **PRIOR_KW[wl["prior"]])
+
+    # ---------------------------------------------------------------- reference arm (CPU port)
+    if a.impl == "reference":
+        Xh = X.cpu().numpy().T      # F-contiguous n x p view, no copy
+        yh = y.cpu().numpy()
+        eng = new_engine()
+        eng.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
+        eta0 = []
+        for c in range(C):
+            eng.init_chain(c, beta0[c])
+            eta0.append(eng.state(c)[1])     # init eta = X beta0 (a GEMV the timed CPU sample does not repeat)
+        eng.close()
+        del X
+        cores = os.cpu_count() or 1
+        t1 = time.perf_counter()
+        _, info0 = cpu_port_run(wl, Xh, yh, beta0, eta0, 0, per_thread_updates=1)
+        per = int(max(1, min(p, round(8.0 / max(time.perf_counter() - t1, 1e-3)))))
+        for _ in range(a.warmup):
+            cpu_port_run(wl, Xh, yh, beta0, eta0, 0, per_thread_updates=1)
+        t0 = time.perf_counter()
+        tot = 0
+        for _ in range(a.steps):
+            _, info = cpu_port_run(wl, Xh, yh, beta0, eta0, 0, per_thread_updates=per)
+            tot += info["updates"]
+        wall = time.perf_counter() - t0
+        v = tot / wall
+        line = {"impl": "reference", "metric": "coordinate updates/sec", "value": v, "unit": "updates/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "n": n, "p": p, "family": wl["family"], "prior": wl["prior"], "w": wl["w"]},
+                "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
+                                 "sample": info["sample"] + f"; per step. evals/update {info['evals_per_update']:.2f}. "
+                                 "R is not installed in this image: this is the C restatement of the R algorithm (oracle/oracle.c), not R"},
+                "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    eng = new_engine()
+    eng.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
+    for c in range(C):
+        eng.init_chain(c, beta0[c])
+    ctas, threads = eng.launch_shape()
+    ext = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    for _ in range(max(a.warmup, 0)):
+        eng.run(1, want_samples=False)
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {}
+    e0.record(ext)
+    for _ in range(a.steps):
+        _, st = eng.run(1, want_samples=False)
+        for k, v in st.items():
+            if isinstance(v, (int, float)):
+                agg[k] = agg.get(k, 0) + v
+    e1.record(ext)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if multi:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if multi:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    updates_per_rank = a.steps * C * p
+    value = world * updates_per_rank / (ms * 1e-3)
+    achieved = agg["algorithmic_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9
+
+    # ---------------------------------------------------------------- e2e (host buffers through the C ABI)
+    e2e = None
+    if not a.no_e2e:
+        Xp = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
+        yp = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        Xp.copy_(X)
+        yp.copy_(y)
+        eng.close()
+        torch.cuda.synchronize()
+        it = a.e2e_iters
+
+        def one_call():
+            e = new_engine()
+            e.set_data_ptr(Xp.data_ptr(), n, yp.data_ptr(), device=False, keepalive=(Xp, yp))   # H2D inside
+            for c in range(C):
+                e.init_chain(c, beta0[c])
+            S, _ = e.run(it, want_samples=True)                                                   # D2H inside
+            e.close()
+            return S
+
+        one_call()
+        if multi:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            S = one_call()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        if multi:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": world * a.e2e_steps * it * C * p / el, "unit": "updates/s",
+               "h2d_bytes_per_step": 8 * n * p + 8 * n + 8 * C * p, "d2h_bytes_per_step": 8 * C * it * p,
+               "step": f"one engine call: upload X,y from pinned host memory, init {C} chains, {it} Gibbs iterations, download samples",
+               "ms_per_step": 1e3 * el / a.e2e_steps, "finite": bool(np.isfinite(S).all())}
+        Xh, yh = Xp.numpy().T, yp.numpy()
+    else:
+        Xh = yh = None
+
+    # ---------------------------------------------------------------- cpu baseline (rank 0, N=1 only)
+    cpu = None
+    if not a.no_cpu and rank == 0 and world == 1:
+        if Xh is None:
+            Xh, yh = X.cpu().numpy().T, y.cpu().numpy()
+        e = new_engine()
+        e.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
+        eta0 = []
+        for c in range(C):
+            e.init_chain(c, beta0[c])
+            eta0.append(e.state(c)[1])
+        e.close()
+        v, info = cpu_port_run(wl, Xh, yh, beta0, eta0, a.cpu_seconds)
+        cpu = {"value": v, "unit": "updates/s", "cores": info["cores"], "kind": "port",
+               "sample": info["sample"] + f" ({info['wall_s']:.1f} s, {info['evals_per_update']:.2f} evals/update). "
+               "CPU restatement of the R algorithm (oracle/oracle.c), not R: R is not installed in this image"}
+
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl["name"])
+    except Exception:
+        pass
+    if rank == 0:
+        line = {"metric": "coordinate updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["desc"], "n": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
+                           "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver,
+                           "parallelism": f"chain-parallel x{world} (no collective)", "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
+                           "beta0": "prior draw x %g" % wl["init_scale"]},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(agg["launches"]),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if a.driver == "persistent" else "pass_kernel",
+                             "algorithmic_bytes_per_step": agg["algorithmic_bytes"] / a.steps, "kernel_ms_per_step": agg["sweep_ms"] / a.steps,
+                             "grid": [ctas, threads]},
+                "cpu_baseline": cpu,
+                "engine_stats": {"passes_per_update": agg["passes"] / max(agg["updates"], 1) * C,
+                                 "chain_passes_per_update": agg["chain_passes"] / max(agg["updates"], 1),
+                                 "cand_evals_per_update": agg["cand_evals"] / max(agg["updates"], 1),
+                                 "ref_evals_per_update": agg["ref_evals"] / max(agg["updates"], 1),
+                                 "row_evals_per_s": agg["cand_evals"] * n / (agg["sweep_ms"] * 1e-3)}}
+        print(json.dumps(line))
+    if multi:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,157 @@
+/*
+ * cggibbs.h -- C ABI of the B200-native CGGibbs engine (libcggibbs.so).
+ *
+ * This is the drop-in boundary for ONE path of mathiaslj/mcmcglm: the slice-within-Gibbs
+ * coordinate update (reference R/mcmcglm.R:226-274 and everything it calls).  The reference is pure
+ * R and has no FFI of its own; these entry points are what an R `.Call` shim (r/src/rshim.c), a
+ * ctypes binding (mcmcglm_b200/_lib.py) or any other host binds.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns CGG_OK (0) or a negative cgg_status; cgg_last_error() gives the
+ *     message of the calling thread's last failure.  Nothing here exits, aborts or prints.
+ *   - "host" pointers are ordinary CPU memory owned by the caller; the library copies in/out.
+ *     "device" pointers (only cgg_set_data_device) are CUDA device memory on cfg.device.
+ *   - matrices are column-major fp64 exactly as R stores them: X[i + j*ldx], ldx >= n.
+ *   - j is 0-based here; the R shim subtracts 1.
+ *   - a handle is not re-entrant; all calls block until their results are in the output buffers.
+ *   - there is NO CPU fallback: unsupported family/link/prior/sampler => CGG_E_UNSUPPORTED,
+ *     no usable CUDA device => CGG_E_CUDA.
+ */
+#ifndef CGGIBBS_H
+#define CGGIBBS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGG_ABI_VERSION 1
+#define CGG_KMAX 8 /* most candidates one chain can score in one pass over its rows */
+
+typedef enum cgg_status {
+    CGG_OK = 0,
+    CGG_E_ARG = -1,         /* bad argument (NULL, size, alignment, y outside the family's support) */
+    CGG_E_UNSUPPORTED = -2, /* family/link/prior/sampler outside the supported set: rejected */
+    CGG_E_CUDA = -3,        /* CUDA runtime failure, or no device */
+    CGG_E_NAN = -4,         /* log-potential evaluated to NaN where the reference would stop() */
+    CGG_E_STREAM = -5,      /* replay-uniform stream exhausted */
+    CGG_E_NOTERM = -6,      /* slice loop exceeded the pass guard (reference would spin forever) */
+    CGG_E_STATE = -7,       /* call sequence error (no data, chain not initialised, ...) */
+    CGG_E_COMM = -8         /* collective layer failure (row-sharded mode) */
+} cgg_status;
+
+/* family$family / family$link of the reference (R/family_data_processing.R:3-16).  Only the
+ * canonical pairs are implemented: gaussian+identity, binomial+logit, poisson+log. */
+enum { CGG_GAUSSIAN = 0, CGG_BINOMIAL = 1, CGG_POISSON = 2 };
+enum { CGG_LINK_IDENTITY = 0, CGG_LINK_LOGIT = 1, CGG_LINK_LOG = 2 };
+/* beta_prior: iid distributional::dist_normal / dist_laplace / dist_student_t (R/glm_utils.R:108-110) */
+enum { CGG_PRIOR_NORMAL = 0, CGG_PRIOR_LAPLACE = 1, CGG_PRIOR_STUDENT_T = 2 };
+/* how the sweep is driven on the device */
+enum {
+    CGG_DRIVER_PERSISTENT = 0, /* one cooperative kernel runs all sweeps; per-chain flags, no grid barrier */
+    CGG_DRIVER_STEPWISE = 1    /* one launch per pass; the last CTA to finish decides */
+};
+/* how rows are distributed */
+enum {
+    CGG_MODE_CHAINS = 0,      /* this handle holds all n rows; chains are independent (no collective) */
+    CGG_MODE_ROW_SHARDED = 1  /* this handle holds one row shard; per-pass sums are exchanged via the
+                                 exchange callback installed with cgg_set_exchange() */
+};
+
+typedef struct cgg_config {
+    int32_t abi_version; /* must be CGG_ABI_VERSION */
+    int32_t device;      /* CUDA device ordinal */
+    int64_t n;           /* rows held by this handle */
+    int64_t p;           /* columns of the model matrix (intercept included) */
+    int32_t family;      /* CGG_GAUSSIAN | CGG_BINOMIAL | CGG_POISSON */
+    int32_t link;        /* must be the family's canonical link */
+    double sd;           /* log_likelihood_extra_args$sd (R/mcmcglm.R:151); gaussian only */
+    int32_t prior;       /* CGG_PRIOR_* */
+    int32_t n_chains;    /* independent chains resident on this device (>= 1) */
+    double prior_mu, prior_sigma, prior_df;
+    double w;            /* qslice::slice_stepping_out `w` (> 0), R/mcmcglm.R:258-261 */
+    int64_t max_steps;   /* qslice `max`; < 0 means Inf (the default) */
+    int32_t K;           /* speculative candidates per chain per pass, 1..CGG_KMAX */
+    int32_t driver;      /* CGG_DRIVER_* */
+    int32_t mode;        /* CGG_MODE_* */
+    int32_t chain_offset;/* global index of this handle's chain 0 (selects the Philox substream) */
+    uint64_t seed;       /* Philox key */
+    double spec_tau;     /* speculate a candidate only if P(needed) >= spec_tau; <= 0 => always fill K */
+    int32_t rows_per_cta_min; /* 0 => default */
+    int32_t reserved;
+} cgg_config;
+
+typedef struct cgg_stats {
+    uint64_t updates;        /* coordinate updates completed (all chains) */
+    uint64_t passes;         /* (chain, pass) pairs, idle ones included */
+    uint64_t chain_passes;   /* (chain, pass) pairs that scored >= 1 candidate */
+    uint64_t commit_passes;  /* (chain, pass) pairs that applied a pending eta update */
+    uint64_t cand_evals;     /* candidates scored (speculative ones included) */
+    uint64_t ref_evals;      /* evaluations qslice would have made (its nEvaluations), f(x0) included */
+    uint64_t stepouts;       /* bracket expansions */
+    uint64_t shrinks;        /* shrink proposals consumed (accepted one included) */
+    uint64_t launches;       /* kernels launched by the last cgg_run */
+    double sweep_ms;         /* device time of the last cgg_run's sweep kernels (CUDA events) */
+    double algorithmic_bytes;/* 8n * (3*chain_passes + 2*commit_passes) of the last cgg_run */
+} cgg_stats;
+
+typedef struct cgg_handle cgg_handle;
+
+/* Row-sharded exchange hook: called on the host between the local pass and the decision with a
+ * DEVICE buffer of `count` doubles on `cuda_stream`; must sum it element-wise over all ranks in
+ * place with a result that is bit-identical on every rank (e.g. all-gather + fixed-order sum). */
+typedef int (*cgg_exchange_fn)(void *user, double *device_buf, int64_t count, void *cuda_stream);
+
+const char *cgg_last_error(void);
+int cgg_abi_version(void);
+
+/* Replaces the front half of mcmcglm() that builds state (R/mcmcglm.R:171-198). */
+int cgg_create(const cgg_config *cfg, cgg_handle **out);
+void cgg_destroy(cgg_handle *h);
+
+/* X = model.matrix, Y = model.response (R/mcmcglm.R:176-178).  Host buffers, copied to HBM. */
+int cgg_set_data(cgg_handle *h, const double *X_host, int64_t ldx, const double *y_host);
+/* Same, but X/y already live in device memory (adopted, not copied; caller keeps them alive;
+ * both 16-byte aligned, ldx even). */
+int cgg_set_data_device(cgg_handle *h, const double *X_dev, int64_t ldx, const double *y_dev);
+
+/* init_beta -> init_eta = X %*% init_beta (R/mcmcglm.R:200-216).  beta0 is drawn by the host
+ * (the R shim uses distributional::generate exactly as the reference does). */
+int cgg_init_chain(cgg_handle *h, int32_t chain, const double *beta0_host);
+
+/* log_potential_from_betaj(new_beta_j, j, current_beta, current_eta, Y, X, family, beta_prior,
+ * "update") of R/glm_utils.R:187-218 at K values of new_beta_j, against the chain's current
+ * beta/eta.  Parity gate 1. */
+int cgg_log_potential(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host,
+                      double *out_host);
+
+/* update_linear_predictor(new_beta_j, current_beta_j, current_eta, X_j) of R/glm_utils.R:126-132
+ * plus the commit of R/mcmcglm.R:264-268: beta[j] <- new_beta_j; eta <- eta + X_j * diff. */
+int cgg_update_eta(cgg_handle *h, int32_t chain, int64_t j, double new_beta_j);
+
+/* The (k, j) loop of R/mcmcglm.R:226-274 for n_iter further iterations of every chain.
+ *   replay_u  NULL => on-device Philox; else n_chains streams of n_u uniforms each
+ *             (replay_u[c*n_u + i]) consumed exactly as qslice's runif(1) calls would.
+ *   u_consumed  [n_chains] cumulative uniforms consumed per chain (nullable).
+ *   samples_out [n_chains][n_iter][p] row-major: beta after each iteration (nullable).
+ * May be called repeatedly; the chain state persists between calls. */
+int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, uint64_t n_u, uint64_t *u_consumed,
+            double *samples_out, cgg_stats *stats);
+
+/* Current beta[p] and (nullable) eta[n] of a chain, to host. */
+int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, double *eta_host);
+/* Carried log-potential at the chain's current point (what qslice's first f(x) would return). */
+int cgg_get_fx(cgg_handle *h, int32_t chain, double *fx);
+
+int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
+/* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
+void *cgg_stream(cgg_handle *h);
+/* Grid used by the sweep kernels: CTAs and threads per CTA (for launch accounting) */
+int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGGIBBS_H */

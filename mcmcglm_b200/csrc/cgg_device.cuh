@@ -1,0 +1,526 @@
+// cgg_device.cuh -- device-side data layout and the device routines every sweep kernel is made of:
+//   warp_pass_chain<FAMILY>() : one warp, one chain, one pass over the warp's row tiles: scores every
+//                               live candidate and applies a pending eta update (reference a4..a9 + a5)
+//   decide_chain()            : the qslice stepping-out / shrinkage state machine (reference a3) for one
+//                               chain, run by one warp once per pass, with exact speculative candidates
+// Workers are WARPS.  Worker w owns the 64-row tiles w, w+W, w+2W, ... for the whole run (at any moment
+// the grid touches one contiguous window of every operand); chains are independent, each with its own
+// arrival counter and version flag, so there is no grid-wide barrier anywhere.
+#pragma once
+#include "cgg_math.cuh"
+
+namespace cgg {
+
+constexpr int KMAX = CGG_KMAX;
+constexpr int THREADS = 512;   // one CTA per SM, 16 warp-workers each
+constexpr int NWARPS = THREADS / 32;
+constexpr int CMAX = 64;       // chains per device (shared-memory slots of the CTA-level reduction)
+constexpr int NU = 12;         // uniforms fetched per decision: 3 start draws + KMAX proposals (+1 spare)
+constexpr int RING_D = 4;      // tiles in flight per warp (cp.async ring depth)
+constexpr int RING_OPS = 4;    // eta, y, X_j, X_commit
+constexpr int TILE_ROWS = 64;  // 32 lanes x one 128-bit transfer per operand
+constexpr int RING_BYTES_PER_WARP = RING_D * RING_OPS * 32 * 16;
+
+enum Phase : int32_t { PH_START = 0, PH_STEPOUT = 1, PH_SHRINK = 2, PH_FLUSH = 3, PH_FINISHED = 4 };
+
+// What every worker needs to know about a chain for its coming pass.  12 x 8 bytes.
+struct __align__(16) Ctl {
+    int32_t j;          // column being sampled; -1: chain finished or failed, skip it for good
+    int32_t ncand;      // candidates to score (0..KMAX)
+    int32_t commit_j;   // column of a pending eta update to apply first (-1: none)
+    int32_t pad0;
+    double commit_delta;// new_beta_j - current_beta_j of that update (R/glm_utils.R:127)
+    double delta[KMAX]; // cand_k - beta_j
+    double pad1;
+};
+static_assert(sizeof(Ctl) == 96, "Ctl must be 12 doubles");
+constexpr int CTL_WORDS = sizeof(Ctl) / 8;
+
+// Per-chain synchronisation words, one 128-byte line each.
+struct __align__(128) ChainSync {
+    unsigned long long arrive;   // monotone: CTAs that finished a pass of this chain
+    unsigned long long version;  // passes decided so far (release/acquire flag)
+    unsigned long long pad[14];
+};
+
+// Exact accumulator of one candidate's log-likelihood: 128-bit two's-complement fixed point with 64
+// fractional bits, updated with integer atomics.  Integer addition is associative, so the total does not
+// depend on arrival order: sums are bit-reproducible without a serial reduction over per-CTA partials.
+struct __align__(128) Acc {  // one L2 line each, so different candidates hit different L2 slices
+    unsigned long long lo;
+    long long hi;
+    unsigned int flags;  // 1: a partial was -Inf, 2: NaN, 4: +Inf or out of range
+    unsigned int pad[27];
+};
+
+// Slice-sampler state of one chain; touched only by the deciding warp.
+struct __align__(16) ChainState {
+    double x0, fx0, ylev, L, R, Jb, Kb;
+    double prior_sum;   // sum_l log pi(beta_l) at the current beta
+    double prior_rest;  // prior_sum - log pi(beta_j)
+    double pexp;        // running estimate of P(a stepping-out expansion happens)
+    double cand[KMAX];
+    int32_t phase, status;
+    int32_t nL, nR, nS;
+    int32_t openL, openR;
+    int32_t sdrawn;     // shrink uniforms already consumed by rejected proposals of this update
+    int32_t npass;      // passes spent on this update (non-termination guard)
+    int32_t j;
+    int32_t pad[2];
+    int64_t iter;       // iterations completed in this run
+    uint64_t cursor;    // uniforms consumed before this update
+    uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
+};
+static_assert(sizeof(ChainState) % 16 == 0, "ChainState is copied with 128-bit accesses");
+
+struct Hdr {
+    unsigned int ticket;        // stepwise driver: CTAs finished in this launch
+    int32_t done;               // stepwise driver: every chain finished (or failed)
+    int32_t abort;              // a wait timed out
+    int32_t pad;
+};
+
+struct Dev {
+    const double *X; const double *y;
+    double *eta, *beta, *shat, *samples, *xbuf;
+    const double *replay;
+    Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
+    unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
+    int64_t n, p, ldx, lde, n_tiles, n_iter;
+    uint64_t n_u, seed;
+    int64_t max_steps;
+    double inv_sd, ll_const, w, tau;
+    PriorParams prior;
+    int32_t C, K, G, family, chain_offset, sharded;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// acquire-release fence at device scope (cheaper than __threadfence(), which is a sequentially consistent MEMBAR.SC)
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- asynchronous global -> shared staging (LDGSTS), L2-coherent (.cg bypasses L1) ---------------
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double2 lds2(uint32_t smem_addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_addr) : "memory");
+    return v;
+}
+
+// ---- exact accumulation ---------------------------------------------------------------------
+__device__ __forceinline__ void acc_add(Acc *a, double v) {
+    if (!(fabs(v) < 9.0e18)) {  // -Inf, NaN, +Inf or beyond the fixed-point range
+        atomicOr(&a->flags, (v != v) ? 2u : ((v < 0.0) ? 1u : 4u));
+        return;
+    }
+    const double fl = floor(v);
+    const long long hi = (long long)fl;
+    const unsigned long long lo = (unsigned long long)((v - fl) * 18446744073709551616.0);  // (v - fl) in [0,1)
+    long long carry = 0;
+    if (lo) {
+        const unsigned long long old = atomicAdd(&a->lo, lo);
+        carry = (old + lo < old) ? 1 : 0;
+    }
+    if (hi + carry) atomicAdd(reinterpret_cast<unsigned long long *>(&a->hi), (unsigned long long)(hi + carry));
+}
+
+// Read-and-clear by the single deciding lane (all adds of this pass are ordered before by the arrive counter).
+__device__ __forceinline__ double acc_take(Acc *a) {
+    const unsigned long long lo = __ldcg(&a->lo);
+    const long long hi = __ldcg(&a->hi);
+    const unsigned int fl = __ldcg(&a->flags);
+    a->lo = 0ULL; a->hi = 0LL; a->flags = 0u;
+    if (fl & 2u) return NAN;
+    if ((fl & 1u) && (fl & 4u)) return NAN;
+    if (fl & 1u) return -INFINITY;
+    if (fl & 4u) return INFINITY;
+    return (double)hi + (double)lo * 5.421010862427522e-20;  // 2^-64
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp, one chain, one pass over the warp's tiles T = wid, wid + W, ... (64 rows each, one 128-bit
+// transfer per lane per operand).  Algorithmic traffic: 8 B/row each of y, eta, X_j; a pending commit
+// adds X_commit (read) and eta (write).  Operand tiles are staged global -> shared with cp.async into a
+// RING_D-deep per-warp ring, so RING_D - 1 tiles are in flight while one is being scored; every lane
+// reads back only the 16-byte slots it copied itself, so no barrier of any kind is needed.
+template <int FAMILY>
+__device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int nc, int cj, double cdelta,
+                                                const double (&dl)[KMAX], long long wid, long long W, int lane,
+                                                uint32_t ring, double (&acc)[KMAX]) {
+    const double *xj = d.X + (int64_t)j * d.ldx;
+    const double *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
+    double *eta = d.eta + (int64_t)c * d.lde;
+    const int64_t n = d.n;
+    const uint32_t slot0 = ring + (uint32_t)lane * 16u;
+    auto issue = [&](long long T, int stage) {
+        const int64_t i = T * TILE_ROWS + 2 * lane;
+        if (T < d.n_tiles && i + 1 < n) {
+            const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
+            cp_async16(s, eta + i);
+            if (nc > 0) { cp_async16(s + 512u, d.y + i); cp_async16(s + 1024u, xj + i); }
+            if (cj >= 0) cp_async16(s + 1536u, xc + i);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < RING_D - 1; ++s) issue(wid + s * W, s);
+    int stage = 0;
+    for (long long T = wid; T < d.n_tiles; T += W) {
+        issue(T + (RING_D - 1) * W, (stage + RING_D - 1) & (RING_D - 1));
+        cp_async_wait<RING_D - 1>();
+        const int64_t i = T * TILE_ROWS + 2 * lane;
+        if (i + 1 < n) {
+            const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
+            double2 e = lds2(s);
+            if (cj >= 0) {
+                const double2 cv = lds2(s + 1536u);
+                e.x = eta_shift(e.x, cv.x, cdelta);
+                e.y = eta_shift(e.y, cv.y, cdelta);
+                *reinterpret_cast<double2 *>(eta + i) = e;
+            }
+            if (nc > 0) {
+                const double2 yv = lds2(s + 512u), xv = lds2(s + 1024u);
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k)
+                    if (k < nc) {
+                        acc[k] += row_term<FAMILY>(yv.x, eta_shift(e.x, xv.x, dl[k]), d.inv_sd);
+                        acc[k] += row_term<FAMILY>(yv.y, eta_shift(e.y, xv.y, dl[k]), d.inv_sd);
+                    }
+            }
+        }
+        stage = (stage + 1) & (RING_D - 1);
+    }
+    cp_async_wait<0>();
+    if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
+        const int64_t t = n - 1;
+        const long long Tl = t / TILE_ROWS;
+        if (Tl % W == wid && lane == (int)((t % TILE_ROWS) >> 1)) {
+            double e = __ldcg(eta + t);
+            if (cj >= 0) { e = eta_shift(e, __ldg(xc + t), cdelta); eta[t] = e; }
+            if (nc > 0) {
+                const double yy = __ldg(d.y + t), xx = __ldg(xj + t);
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k)
+                    if (k < nc) acc[k] += row_term<FAMILY>(yy, eta_shift(e, xx, dl[k]), d.inv_sd);
+            }
+        }
+    }
+}
+
+// A worker's whole contribution to one pass of chain c: read the control block, stream the rows and
+// return the warp's partial sums (identical in every lane).  Return value: -1 chain finished,
+// otherwise the number of candidates scored (0 when the pass was idle or commit-only); j_out = column.
+template <int FAMILY>
+__device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw /* the CTA's shared copy of ctl[c] */,
+                                           long long wid, long long W, int lane, uint32_t ring,
+                                           double (&acc)[KMAX], int &j_out) {
+    const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
+    const int j = (int)(w0 & 0xffffffffLL), nc = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
+    j_out = j;
+    if (j < 0) return -1;
+    if (nc == 0 && cj < 0) return 0;
+    const double cdelta = cw[2];
+    double dl[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) { dl[k] = cw[3 + k]; acc[k] = 0.0; }
+    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cdelta, dl, wid, W, lane, ring, acc);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < nc) acc[k] = warp_sum(acc[k]);
+    return nc;
+}
+
+// Shared memory of a sweep CTA: the warps' staging rings, per-chain slots of the non-blocking CTA-level
+// reduction and the CTA's cached view of the chains' version flags.
+struct CtaShared {                       // views into dynamic shared memory, sized by the chain count
+    double *part;                        // [C][NWARPS][KMAX] warp partial sums of the pass in flight
+    double *ctl;                         // [C][CTL_WORDS] the control block that goes with ver[c] (one L2 fetch per CTA)
+    unsigned long long *ver;             // [C] last version of chain c seen by this CTA
+    int *cnt;                            // [C] warps of this CTA that delivered their partials
+    int *lock;                           // [C] elected poller of the chain's version flag
+    uint32_t ring0;                      // shared-space address of warp 0's ring
+    __device__ __forceinline__ CtaShared(unsigned char *base, int C) {
+        ring0 = (uint32_t)__cvta_generic_to_shared(base);
+        part = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
+        ctl = part + (size_t)C * NWARPS * KMAX;
+        ver = reinterpret_cast<unsigned long long *>(ctl + (size_t)C * CTL_WORDS);
+        cnt = reinterpret_cast<int *>(ver + C);
+        lock = cnt + C;
+    }
+    static size_t bytes(int C) {
+        return (size_t)NWARPS * RING_BYTES_PER_WARP +
+               (size_t)C * (sizeof(double) * (NWARPS * KMAX + CTL_WORDS) + sizeof(unsigned long long) + 2 * sizeof(int));
+    }
+};
+
+// Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
+// has folded the CTA's NWARPS partials -- summed in warp order, so the value is reproducible -- into the
+// chain's exact accumulators; the other warps return at once and move on to their next chain.
+__device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers, const double (&acc)[KMAX]) {
+    int last = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < nc) sh.part[((size_t)c * NWARPS + warp) * KMAX + k] = acc[k];
+        __threadfence_block();
+        last = (atomicAdd_block(&sh.cnt[c], 1) == nworkers - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return false;
+    __threadfence_block();
+    if (lane < nc) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w)
+            if (w < nworkers) v += sh.part[((size_t)c * NWARPS + w) * KMAX + lane];
+        acc_add(d.acc + c * KMAX + lane, v);
+        fence_gpu();       // fences are per thread: each adding lane orders its atomics before the arrival
+    }
+    if (lane == 0) sh.cnt[c] = 0;
+    __syncwarp();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Uniform #i (0-based within the chain's stream): replayed (R's runif record) or Philox.
+__device__ __forceinline__ bool draw_uniform(const Dev &d, int c, uint64_t i, double &u) {
+    if (d.replay) {
+        if (i >= d.n_u) { u = 0.5; return false; }
+        u = __ldcg(d.replay + (uint64_t)c * d.n_u + i);
+    } else {
+        u = philox_uniform(d.seed, (uint32_t)(d.chain_offset + c), i);
+    }
+    return true;
+}
+
+__device__ __forceinline__ int base_draws(const Dev &d) { return d.max_steps > 0 ? 3 : 2; }
+
+// Lane-0 scalar code: fill the chain's next candidate list from its bracket state.  U[0..nU) are the
+// uniforms that follow the ones already consumed by rejected shrink proposals of this update.
+// Stepping-out candidates (L / R) and shrink proposals x_i = L + u_i (R - L) with the bracket update
+// `if (x_i < x0) L = x_i else R = x_i` are functions of (L, R, x0, u) only, never of f (SURVEY.md fact
+// 5a), so scoring several of them in one pass is exact: f only decides where the sequence stops, and
+// uniforms of unused proposals are simply not consumed.
+__device__ __forceinline__ void build_candidates(const Dev &d, ChainState &s, Ctl &ct, double shat, const double *U, int nU) {
+    int n = 0;
+    s.nL = s.nR = s.nS = 0;
+    double pneed = 1.0;  // P(the next speculative shrink proposal is needed)
+    if (s.phase == PH_STEPOUT) {
+        if (s.openL) { s.cand[n++] = s.L; s.nL = 1; }
+        if (s.openR) { s.cand[n++] = s.R; s.nR = 1; }
+        pneed = 1.0 - s.pexp;
+    }
+    double l = s.L, r = s.R;
+    for (int i = 0; n < d.K; ++i) {
+        if (d.tau > 0.0 && (i > 0 || s.phase == PH_STEPOUT) && pneed < d.tau) break;
+        if (i >= nU) {
+            if (i == 0 && s.phase == PH_SHRINK) s.status = CGG_E_STREAM;  // a needed draw is missing
+            break;
+        }
+        const double x = __dadd_rn(l, __dmul_rn(U[i], __dadd_rn(r, -l)));  // L + runif(1) * (R - L)
+        s.cand[n++] = x; s.nS++;
+        double pacc = (shat > 0.0) ? shat / (r - l) : 0.0;
+        pacc = pacc < 1.0 ? pacc : 1.0;
+        pneed *= (1.0 - pacc);
+        if (x < s.x0) l = x; else r = x;
+    }
+    if (s.phase == PH_STEPOUT && n == 0 && s.status == CGG_OK) s.status = CGG_E_STREAM;
+    ct.j = s.j; ct.ncand = (s.status == CGG_OK) ? n : 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) ct.delta[k] = (k < n) ? __dadd_rn(s.cand[k], -s.x0) : 0.0;
+    s.cand_evals += ct.ncand;
+    if (ct.ncand > 0) s.chain_passes++;
+}
+
+// Lane-0 scalar code: begin the update of coordinate s.j (qslice::slice_stepping_out up to the first
+// f(L) test; R/mcmcglm.R:258-261).  f(x0) is the carried log-potential.
+__device__ __forceinline__ void start_coordinate(const Dev &d, ChainState &s, double x0, const double *U, int nU) {
+    s.x0 = x0;
+    s.prior_rest = s.prior_sum - prior_logdens(d.prior, s.x0);
+    s.sdrawn = 0; s.npass = 0;
+    if (nU < base_draws(d)) { s.status = CGG_E_STREAM; return; }
+    s.ylev = __dadd_rn(log(U[0]), s.fx0);                // y <- log(runif(1)) + f(x)
+    s.L = __dadd_rn(s.x0, -__dmul_rn(U[1], d.w));        // L <- x - runif(1) * w
+    s.R = __dadd_rn(s.L, d.w);                           // R <- L + w
+    s.ref_evals += 1;                                    // qslice's f(x0)
+    if (d.max_steps < 0) { s.openL = s.openR = 1; s.Jb = s.Kb = 0.0; }
+    else if (d.max_steps > 0) {
+        s.Jb = floor(U[2] * (double)d.max_steps);        // J <- floor(runif(1) * max)
+        s.Kb = (double)d.max_steps - 1.0 - s.Jb;         // K <- max - 1 - J
+        s.openL = s.Jb > 0.0; s.openR = s.Kb > 0.0;
+    } else { s.openL = s.openR = 0; s.Jb = s.Kb = 0.0; }
+    s.phase = (s.openL || s.openR) ? PH_STEPOUT : PH_SHRINK;
+}
+
+// Lane-0 scalar code: consume the log-potentials F[0..ncand) of the pass that just finished.
+// Returns true when the update was accepted (s.j / s.iter advanced, s.phase = START or FLUSH);
+// x1_out / shat_out then hold the accepted value and the refreshed width estimate of that coordinate.
+__device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState &s, Ctl &ct, const double *F,
+                                                double shat_j, double &x1_out, double &shat_out) {
+    s.npass++;
+    if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
+    if (s.phase == PH_FLUSH) { s.phase = PH_FINISHED; ct.ncand = 0; return false; }
+    int idx = 0;
+    bool expanded = false;
+    if (s.phase == PH_STEPOUT) {
+        // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
+        for (int i = 0; i < s.nL && s.openL; ++i) {
+            const double f = F[idx + i];
+            s.ref_evals++;
+            if (f != f) { s.status = CGG_E_NAN; return false; }
+            if (s.ylev < f) {
+                s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true;
+                if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; }
+            } else s.openL = 0;
+        }
+        idx += s.nL;
+        for (int i = 0; i < s.nR && s.openR; ++i) {
+            const double f = F[idx + i];
+            s.ref_evals++;
+            if (f != f) { s.status = CGG_E_NAN; return false; }
+            if (s.ylev < f) {
+                s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true;
+                if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; }
+            } else s.openR = 0;
+        }
+        idx += s.nR;
+        s.pexp = 0.9 * s.pexp + (expanded ? 0.1 : 0.0);
+        if (s.openL || s.openR) return false; // keep stepping out next pass
+        s.phase = PH_SHRINK;
+        if (expanded) return false;           // speculative proposals assumed the old bracket
+    }
+    // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }
+    for (int i = 0; i < s.nS; ++i) {
+        const double f = F[idx + i], x1 = s.cand[idx + i];
+        s.ref_evals++; s.shrinks++;
+        if (f != f) { s.status = CGG_E_NAN; return false; }
+        if (s.ylev < f) {
+            const int64_t pj = (int64_t)c * d.p + s.j;
+            shat_out = (shat_j > 0.0) ? 0.75 * shat_j + 0.25 * (s.R - s.L) : (s.R - s.L);  // bracket width at acceptance
+            x1_out = x1;
+            d.shat[pj] = shat_out;
+            d.beta[pj] = x1;                                        // R/mcmcglm.R:264
+            ct.commit_j = s.j;                                      // eta update deferred to the next pass
+            ct.commit_delta = __dadd_rn(x1, -s.x0);
+            s.fx0 = f;
+            s.prior_sum = s.prior_rest + prior_logdens(d.prior, x1);
+            s.cursor += base_draws(d) + s.sdrawn + i + 1;
+            if (d.samples) d.samples[((int64_t)c * d.n_iter + s.iter) * d.p + s.j] = x1;  // :271
+            s.updates++;
+            s.j++;
+            if (s.j == d.p) { s.j = 0; s.iter++; }
+            s.phase = (s.iter >= d.n_iter) ? PH_FLUSH : PH_START;
+            return true;
+        }
+        if (x1 < s.x0) s.L = x1; else s.R = x1;
+    }
+    s.sdrawn += s.nS;
+    if (s.npass > 100000) s.status = CGG_E_NOTERM;
+    return false;
+}
+
+// One warp decides one chain after every worker's contribution to the pass is visible.
+// j_hint: the column of the pass just finished if the caller already knows it (>= 0), else -1.
+// from_xbuf: log-likelihood sums come from d.xbuf (already reduced across ranks, row-sharded mode).
+// Returns true when the chain is finished (or failed) after this decision.
+// The parameter block is taken by pointer -- the kernels pass the address of their __grid_constant__
+// parameter -- so this cold, register-hungry routine stays out of line and off the hot loop's registers.
+__device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_hint, bool from_xbuf) {
+    const Dev &d = *dp;
+    // ---- one batched round of loads: control block, state, accumulators, beta/shat of j and j+1
+    if (j_hint < 0) j_hint = __ldcg(&d.ctl[c].j);
+    const int jq = j_hint < 0 ? 0 : j_hint;              // column of the pass that just finished
+    const int jn = (jq + 1 == d.p) ? 0 : jq + 1;         // the column an acceptance moves on to
+    const double *bp = d.beta + (int64_t)c * d.p, *sp = d.shat + (int64_t)c * d.p;
+    const double beta_j = __ldcg(bp + jq), beta_n = __ldcg(bp + jn);
+    const double shat_j = __ldcg(sp + jq), shat_n = __ldcg(sp + jn);
+    Ctl ct = d.ctl[c];
+    ChainState s = d.cs[c];
+    if (s.phase == PH_FINISHED || s.status != CGG_OK) return true;
+    const int nc = ct.ncand;
+    // lane k: total log-likelihood of candidate k + its prior term
+    double f = 0.0;
+    if (lane < nc) {
+        const double ll = from_xbuf ? __ldcg(d.xbuf + c * KMAX + lane) : acc_take(d.acc + c * KMAX + lane) + d.ll_const;
+        f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));
+    }
+    double F[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) F[k] = __shfl_sync(0xffffffffu, f, k);
+    s.passes++;
+    double x0 = beta_j, shat = shat_j;     // values of the coordinate that is sampled next
+    if (lane == 0 && s.phase != PH_START) {
+        double x1 = 0.0, sh1 = 0.0;
+        if (process_results(d, c, s, ct, F, shat_j, x1, sh1)) {
+            if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }   // p == 1: same column again
+        }
+    }
+    const int phase = __shfl_sync(0xffffffffu, s.phase, 0);
+    const int status = __shfl_sync(0xffffffffu, s.status, 0);
+    const int j = __shfl_sync(0xffffffffu, s.j, 0);
+    __syncwarp();
+    if (status == CGG_OK && phase == PH_START && j == 0) {
+        // once per sweep: re-sum the prior over all p coordinates (quirk Q5) so the running value cannot drift
+        double v = 0.0;
+        for (int64_t l = lane; l < d.p; l += 32) v += prior_logdens(d.prior, __ldcg(bp + l));
+        v = warp_sum(v);
+        s.prior_sum = v;
+    }
+    if (status == CGG_OK && (phase == PH_START || phase == PH_SHRINK || phase == PH_STEPOUT)) {
+        // uniforms the next decision steps can need, fetched by the lanes in parallel
+        const uint64_t cursor = __shfl_sync(0xffffffffu, (unsigned long long)s.cursor, 0);
+        const int sdrawn = __shfl_sync(0xffffffffu, s.sdrawn, 0);
+        const uint64_t ustart = (phase == PH_START) ? cursor : cursor + base_draws(d) + sdrawn;
+        double u = 0.5;
+        const bool ok = (lane < NU) ? draw_uniform(d, c, ustart + lane, u) : true;
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        int nU = __ffs(~okmask) - 1;   // first lane whose draw was unavailable
+        if (nU < 0 || nU > NU) nU = NU;
+        double U[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) U[i] = __shfl_sync(0xffffffffu, u, i);
+        if (lane == 0) {
+            int off = 0;
+            if (phase == PH_START) { start_coordinate(d, s, x0, U, nU); off = base_draws(d); }
+            if (s.status == CGG_OK) build_candidates(d, s, ct, shat, U + off, nU - off > 0 ? nU - off : 0);
+        }
+    } else if (lane == 0) {
+        ct.ncand = 0;
+    }
+    bool fin = false;
+    if (lane == 0) {
+        if (s.status != CGG_OK) { ct.ncand = 0; ct.commit_j = -1; }
+        fin = (s.phase == PH_FINISHED) || (s.status != CGG_OK);
+        if (fin) ct.j = -1;
+        d.cs[c] = s;
+        d.ctl[c] = ct;
+    }
+    fin = __shfl_sync(0xffffffffu, (int)fin, 0);
+    fence_gpu();       // every lane: its accumulator clears must be visible before the version is released
+    __syncwarp();
+    return fin;
+}
+
+}  // namespace cgg

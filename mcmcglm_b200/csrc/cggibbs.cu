@@ -1,0 +1,798 @@
+// cggibbs.cu -- kernels and C ABI of libcggibbs.so (see include/cggibbs.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "cgg_device.cuh"
+
+using namespace cgg;
+
+// ============================================================================================
+// Kernels
+// ============================================================================================
+
+// K3 (persistent driver).  Launched cooperatively, one 16-warp CTA per SM, so that every warp of the grid
+// is resident.  Warps are specialised:
+//   worker warps  own a fixed set of 64-row tiles for the whole run and walk the chains round-robin.  A
+//                 chain's pass #r may start as soon as its decision #r is published (version >= r).  Workers
+//                 deliver their partial sums to their CTA without blocking; the last worker of a CTA folds
+//                 them into the chain's exact accumulators and arrives for the CTA.
+//   decider warps (the last warp of CTA c, one per chain) watch their chain's arrival counter and run the
+//                 chain's slice state machine the moment a pass is complete, then publish the next version.
+// There is no grid-wide barrier and no worker ever runs a decision: decisions of different chains proceed
+// concurrently on different SMs, and with >= 2 chains per device their latency is hidden behind the
+// streaming of the other chains.
+constexpr unsigned long long VERSION_FINISHED = 1ULL << 62;
+
+__device__ __forceinline__ bool wait_timed_out(const Dev &d, unsigned long long t0, int lane) {
+    if (__ldcg(&d.hdr->abort)) return true;
+    if (globaltimer_ns() - t0 > 4000000000ULL) {  // a peer never showed up: bail out, do not hang the GPU
+        if (lane == 0) { d.hdr->abort = 1; fence_gpu(); }
+        return true;
+    }
+    return false;
+}
+
+__device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int stride, int lane) {
+    const Dev &d = *dp;
+    const unsigned long long t_start = globaltimer_ns();
+    unsigned long long t0 = t_start;
+    unsigned idle = 0;
+    for (;;) {
+        bool all_fin = true, progressed = false;
+        for (int c = first_chain; c < d.C; c += stride) {
+            unsigned long long v = 0, a = 0;
+            if (lane == 0) { v = __ldcg(&d.sync[c].version); if (v < VERSION_FINISHED) a = ld_acquire_u64(&d.sync[c].arrive); }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= VERSION_FINISHED) continue;
+            all_fin = false;
+            a = __shfl_sync(0xffffffffu, a, 0);
+            if (a < (v + 1) * (unsigned long long)d.G) continue;   // pass #v still has CTAs streaming
+            fence_gpu();
+            const bool fin = decide_chain(dp, c, lane, -1, false);
+            if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
+            progressed = true;
+        }
+        if (all_fin) break;
+        if (progressed) { idle = 0; t0 = globaltimer_ns(); }
+        else {
+            __nanosleep(40);
+            if ((++idle & 255u) == 0 && wait_timed_out(d, t0, lane)) break;
+        }
+    }
+}
+
+template <int FAMILY>
+__global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __grid_constant__ Dev d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared sh(smem_raw, d.C);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < d.C; i += THREADS) { sh.ver[i] = 0ULL; sh.cnt[i] = 0; sh.lock[i] = 0; }
+    for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
+    __syncthreads();
+    // decider warps: the last warp of the first ND CTAs
+    const int ND = d.C < d.G ? d.C : d.G;
+    const bool decider_cta = (int)blockIdx.x < ND;
+    if (decider_cta && warp == NWARPS - 1) { decider_loop(&d, (int)blockIdx.x, ND, lane); return; }
+    const int nworkers = NWARPS - (decider_cta ? 1 : 0);
+    const long long wid = (long long)blockIdx.x * NWARPS + warp - ((int)blockIdx.x < ND ? (int)blockIdx.x : ND);
+    const long long W = (long long)d.G * NWARPS - ND;
+    const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
+    double acc[KMAX];
+    long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0;
+    const bool prof = d.prof != nullptr;
+    for (unsigned long long round = 0;; ++round) {
+        bool any = false;
+        for (int c = 0; c < d.C; ++c) {
+            // ---- wait until decision #round of chain c is published (usually it already is).  One warp at a
+            // time polls the flag for the whole CTA and, when it has advanced, fetches the chain's control
+            // block with one coalesced request into shared memory; the other warps only watch shared memory.
+            long long tA = prof ? clock64() : 0;
+            {
+                volatile unsigned long long *sv = &sh.ver[c];
+                if (*sv < round) {
+                    ++n_slow;
+                    const unsigned long long t0 = globaltimer_ns();
+                    unsigned spins = 0;
+                    for (;;) {
+                        int got = 0;
+                        if (lane == 0) got = (atomicCAS_block(&sh.lock[c], 0, 1) == 0);
+                        got = __shfl_sync(0xffffffffu, got, 0);
+                        if (got) {
+                            unsigned long long v = 0;
+                            if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
+                            v = __shfl_sync(0xffffffffu, v, 0);
+                            if (v >= round && v > *sv) {
+                                if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
+                                __syncwarp();
+                                if (lane == 0) { __threadfence_block(); *sv = v; }
+                            }
+                            if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
+                        }
+                        if (*sv >= round) break;
+                        __nanosleep(64);
+                        if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) return;
+                    }
+                }
+                __syncwarp();
+            }
+            long long tB = prof ? clock64() : 0;
+            t_wait += tB - tA;
+            // ---- stream this warp's rows for chain c
+            int j = -1;
+            const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, acc, j);
+            if (nc < 0) continue;
+            any = true;
+            long long tC = prof ? clock64() : 0;
+            t_rows += tC - tB;
+            // ---- CTA-level then grid-level arrival
+            if (cta_deliver(d, sh, c, nc, warp, lane, nworkers, acc) && lane == 0) {
+                fence_gpu();
+                atomicAdd(&d.sync[c].arrive, 1ULL);
+            }
+            if (prof) t_arrive += clock64() - tC;
+        }
+        if (!any) break;
+    }
+    if (prof && lane == 0) {
+        atomicAdd(d.prof + 0, (unsigned long long)t_wait); atomicAdd(d.prof + 1, (unsigned long long)t_rows);
+        atomicAdd(d.prof + 2, (unsigned long long)t_arrive); atomicAdd(d.prof + 5, (unsigned long long)n_slow);
+        atomicAdd(d.prof + 6, 1ULL);
+    }
+}
+
+// Stepwise driver: one pass of every chain per launch; the last CTA to finish decides.
+// mode 0: run the state machines.  mode 1 (row-sharded / operator): only fold the exact accumulators
+// into d.xbuf (+ ll_const) for the exchange / the caller.
+template <int FAMILY>
+__global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant__ Dev d, int mode) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaShared sh(smem_raw, d.C);
+    __shared__ int s_flag;
+    if (d.hdr->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < d.C; i += THREADS) sh.cnt[i] = 0;
+    for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
+    __syncthreads();
+    const long long wid = (long long)blockIdx.x * NWARPS + warp, W = (long long)d.G * NWARPS;
+    const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
+    double acc[KMAX];
+    for (int c = 0; c < d.C; ++c) {
+        int j;
+        const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, acc, j);
+        if (nc > 0) cta_deliver(d, sh, c, nc, warp, lane, NWARPS, acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(&d.hdr->ticket, 1u);
+        s_flag = (t == (unsigned)d.G - 1);
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    for (int c = warp; c < d.C; c += NWARPS) {
+        if (mode == 0) decide_chain(&d, c, lane, -1, false);
+        else {
+            const int nc = d.ctl[c].ncand;
+            if (lane < nc) d.xbuf[c * KMAX + lane] = acc_take(d.acc + c * KMAX + lane) + d.ll_const;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int done = 1;
+        for (int c = 0; c < d.C; ++c) done &= (d.ctl[c].j < 0);
+        if (mode == 0 && done) d.hdr->done = 1;
+        d.hdr->ticket = 0;
+    }
+}
+
+// Row-sharded mode: the state machines alone, after the exchange made d.xbuf global sums.
+__global__ void __launch_bounds__(THREADS, 1) decide_kernel(const __grid_constant__ Dev d) {
+    if (d.hdr->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < d.C; c += NWARPS) decide_chain(&d, c, lane, -1, true);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int done = 1;
+        for (int c = 0; c < d.C; ++c) done &= (d.ctl[c].j < 0);
+        if (done) d.hdr->done = 1;
+    }
+}
+
+// cgg_log_potential tail: out[k] = ll_k + sum_{l != j} log pi(beta_l) + log pi(cand_k)
+__global__ void finalize_eval_kernel(Dev d, int c, int j, int K, const double *cand, double *out, double *prior_sum_out) {
+    const int lane = threadIdx.x;
+    double v = 0.0, vall = 0.0;
+    for (int64_t l = lane; l < d.p; l += 32) {
+        const double t = prior_logdens(d.prior, d.beta[(int64_t)c * d.p + l]);
+        vall += t;
+        if (l != j) v += t;
+    }
+    v = warp_sum(v);
+    vall = warp_sum(vall);
+    if (lane < K) out[lane] = d.xbuf[c * KMAX + lane] + (v + prior_logdens(d.prior, cand[lane]));
+    if (lane == 0 && prior_sum_out) *prior_sum_out = vall;
+}
+
+// K4: eta = X %*% beta (R/mcmcglm.R:215).  Column-ordered accumulation with separate multiply and
+// add so the result is bit-identical to oracle.c:orc_init_eta.
+__global__ void __launch_bounds__(THREADS) init_eta_kernel(Dev d, int c) {
+    const double *beta = d.beta + (int64_t)c * d.p;
+    double *eta = d.eta + (int64_t)c * d.lde;
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * THREADS + threadIdx.x); i < d.n; i += 2LL * gridDim.x * THREADS) {
+        if (i + 1 < d.n) {
+            double2 a = make_double2(0.0, 0.0);
+            for (int64_t l = 0; l < d.p; ++l) {
+                const double2 x = ld_stream2(d.X + l * d.ldx + i);
+                const double bl = beta[l];
+                a.x = __dadd_rn(a.x, __dmul_rn(x.x, bl));
+                a.y = __dadd_rn(a.y, __dmul_rn(x.y, bl));
+            }
+            *reinterpret_cast<double2 *>(eta + i) = a;
+        } else {
+            double a = 0.0;
+            for (int64_t l = 0; l < d.p; ++l) a = __dadd_rn(a, __dmul_rn(d.X[l * d.ldx + i], beta[l]));
+            eta[i] = a;
+        }
+    }
+}
+
+// K2 stand-alone: eta <- eta + X_j * diff (R/glm_utils.R:126-132)
+__global__ void __launch_bounds__(THREADS) axpy_eta_kernel(Dev d, int c, int64_t j, double diff) {
+    const double *xj = d.X + j * d.ldx;
+    double *eta = d.eta + (int64_t)c * d.lde;
+    for (int64_t i = 2 * ((int64_t)blockIdx.x * THREADS + threadIdx.x); i < d.n; i += 2LL * gridDim.x * THREADS) {
+        if (i + 1 < d.n) {
+            double2 e = *reinterpret_cast<double2 *>(eta + i);
+            const double2 x = ld_stream2(xj + i);
+            e.x = eta_shift(e.x, x.x, diff);
+            e.y = eta_shift(e.y, x.y, diff);
+            *reinterpret_cast<double2 *>(eta + i) = e;
+        } else {
+            eta[i] = eta_shift(eta[i], xj[i], diff);
+        }
+    }
+}
+
+// One-time scan of y: support check per family, and sum lgamma(y + 1) for poisson.
+__global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial, int *bad) {
+    __shared__ double s_red[NWARPS];
+    double acc = 0.0;
+    int nbad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * THREADS) {
+        const double y = d.y[i];
+        if (d.family == CGG_GAUSSIAN) nbad += !isfinite(y);
+        else if (d.family == CGG_BINOMIAL) nbad += !(y == 0.0 || y == 1.0);
+        else {
+            const bool ok = isfinite(y) && y >= 0.0 && y == floor(y);
+            nbad += !ok;
+            if (ok) acc += lgamma(y + 1.0);
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    if (nbad) atomicAdd(bad, nbad);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < NWARPS) ? s_red[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+
+// ============================================================================================
+// Host side
+// ============================================================================================
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(CGG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct cgg_handle {
+    cgg_config cfg;
+    Dev d;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *X_owned = nullptr, *y_owned = nullptr;
+    double *replay_dev = nullptr; uint64_t replay_cap = 0;
+    double *samples_dev = nullptr; size_t samples_cap = 0;
+    double *scratch_dev = nullptr;  // KMAX cand + KMAX out + 1
+    size_t smem = 0;
+    unsigned long long *prof_dev = nullptr;
+    Hdr *hdr_pinned = nullptr;
+    bool has_data = false;
+    std::vector<char> chain_init, fx_valid;
+    int num_sms = 0, max_grid = 0;
+    cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
+    double local_ll_const = 0.0;
+};
+
+extern "C" const char *cgg_last_error(void) { return g_err.c_str(); }
+extern "C" int cgg_abi_version(void) { return CGG_ABI_VERSION; }
+
+static void *kernel_ptr(int family, int which) {
+    switch (family * 2 + which) {
+    case CGG_GAUSSIAN * 2 + 0: return (void *)sweep_persistent_kernel<CGG_GAUSSIAN>;
+    case CGG_GAUSSIAN * 2 + 1: return (void *)pass_kernel<CGG_GAUSSIAN>;
+    case CGG_BINOMIAL * 2 + 0: return (void *)sweep_persistent_kernel<CGG_BINOMIAL>;
+    case CGG_BINOMIAL * 2 + 1: return (void *)pass_kernel<CGG_BINOMIAL>;
+    case CGG_POISSON * 2 + 0: return (void *)sweep_persistent_kernel<CGG_POISSON>;
+    default: return (void *)pass_kernel<CGG_POISSON>;
+    }
+}
+
+static int launch_pass(cgg_handle *h, int mode) {
+    Dev d = h->d;
+    void *args[] = {&d, &mode};
+    CK(cudaLaunchKernel(kernel_ptr(h->cfg.family, 1), dim3(h->d.G), dim3(THREADS), args, h->smem, h->stream));
+    return CGG_OK;
+}
+
+extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
+    if (!cfg || !out) return fail(CGG_E_ARG, "cgg_create: NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != CGG_ABI_VERSION) return fail(CGG_E_ARG, "cgg_create: abi_version %d != %d", cfg->abi_version, CGG_ABI_VERSION);
+    if (cfg->n <= 0 || cfg->p <= 0) return fail(CGG_E_ARG, "cgg_create: n and p must be positive");
+    if (cfg->n_chains < 1 || cfg->n_chains > CMAX) return fail(CGG_E_ARG, "cgg_create: n_chains must be in 1..%d", CMAX);
+    if (cfg->K < 1 || cfg->K > CGG_KMAX) return fail(CGG_E_ARG, "cgg_create: K must be in 1..%d", CGG_KMAX);
+    if (!(cfg->w > 0.0) || !std::isfinite(cfg->w)) return fail(CGG_E_ARG, "cgg_create: slice width w must be positive and finite");
+    const bool fam_ok = (cfg->family == CGG_GAUSSIAN && cfg->link == CGG_LINK_IDENTITY) ||
+                        (cfg->family == CGG_BINOMIAL && cfg->link == CGG_LINK_LOGIT) ||
+                        (cfg->family == CGG_POISSON && cfg->link == CGG_LINK_LOG);
+    if (!fam_ok) return fail(CGG_E_UNSUPPORTED, "cgg_create: unsupported family/link pair (%d, %d); supported: gaussian/identity, binomial/logit, poisson/log", cfg->family, cfg->link);
+    if (cfg->prior < CGG_PRIOR_NORMAL || cfg->prior > CGG_PRIOR_STUDENT_T) return fail(CGG_E_UNSUPPORTED, "cgg_create: unsupported prior %d; supported: normal, laplace, student_t", cfg->prior);
+    if (!(cfg->prior_sigma > 0.0)) return fail(CGG_E_ARG, "cgg_create: prior scale must be positive");
+    if (cfg->prior == CGG_PRIOR_STUDENT_T && !(cfg->prior_df > 0.0)) return fail(CGG_E_ARG, "cgg_create: student-t df must be positive");
+    if (cfg->family == CGG_GAUSSIAN && !(cfg->sd > 0.0)) return fail(CGG_E_ARG, "cgg_create: gaussian sd must be positive");
+    if (cfg->driver != CGG_DRIVER_PERSISTENT && cfg->driver != CGG_DRIVER_STEPWISE) return fail(CGG_E_ARG, "cgg_create: unknown driver");
+    if (cfg->mode != CGG_MODE_CHAINS && cfg->mode != CGG_MODE_ROW_SHARDED) return fail(CGG_E_ARG, "cgg_create: unknown mode");
+    if (cfg->mode == CGG_MODE_ROW_SHARDED && cfg->driver != CGG_DRIVER_STEPWISE) return fail(CGG_E_ARG, "cgg_create: row-sharded mode requires the stepwise driver");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(CGG_E_CUDA, "cgg_create: no CUDA device available (this engine has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(CGG_E_ARG, "cgg_create: device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+
+    cgg_handle *h = new cgg_handle();
+    h->cfg = *cfg;
+    memset(&h->d, 0, sizeof(Dev));
+    Dev &d = h->d;
+    const int C = cfg->n_chains;
+    d.n = cfg->n; d.p = cfg->p; d.C = C; d.K = cfg->K; d.family = cfg->family;
+    d.inv_sd = 1.0 / (cfg->family == CGG_GAUSSIAN ? cfg->sd : 1.0);
+    d.w = cfg->w; d.max_steps = cfg->max_steps < 0 ? -1 : cfg->max_steps;
+    d.seed = cfg->seed; d.chain_offset = cfg->chain_offset; d.tau = cfg->spec_tau;
+    d.sharded = cfg->mode == CGG_MODE_ROW_SHARDED;
+    d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
+    d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
+    if (cfg->prior == CGG_PRIOR_NORMAL) d.prior.c0 = -(kLnSqrt2Pi + log(cfg->prior_sigma));
+    else if (cfg->prior == CGG_PRIOR_LAPLACE) d.prior.c0 = -log(2.0 * cfg->prior_sigma);
+    else d.prior.c0 = lgamma(0.5 * (cfg->prior_df + 1.0)) - lgamma(0.5 * cfg->prior_df) - 0.5 * log(cfg->prior_df * M_PI) - log(cfg->prior_sigma);
+
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    h->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    h->smem = CtaShared::bytes(C);
+    CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_ptr(cfg->family, 0), THREADS, h->smem));
+    if (occ < 1) { delete h; return fail(CGG_E_CUDA, "cgg_create: sweep kernel does not fit on an SM"); }
+    if (occ > 1) occ = 1;
+    h->max_grid = occ * h->num_sms;
+    // Workers are warps owning 64-row tiles w, w + W, ...; use fewer CTAs when there are not enough tiles
+    // to give every warp at least `tmin` of them (rows_per_cta_min / (64 * NWARPS), default 1).
+    d.n_tiles = (d.n + TILE_ROWS - 1) / TILE_ROWS;
+    int64_t tmin = cfg->rows_per_cta_min > 0 ? cfg->rows_per_cta_min / (TILE_ROWS * NWARPS) : 1;
+    if (tmin < 1) tmin = 1;
+    int64_t G = (d.n_tiles + NWARPS * tmin - 1) / (NWARPS * tmin);
+    if (G > h->max_grid) G = h->max_grid;
+    if (G < 1) G = 1;
+    d.G = (int)G;
+    d.lde = (d.n + 31) / 32 * 32;
+
+    auto A = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes); };
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = A((void **)&d.eta, sizeof(double) * (size_t)C * d.lde);
+    if (e == cudaSuccess) e = A((void **)&d.beta, sizeof(double) * (size_t)C * d.p);
+    if (e == cudaSuccess) e = A((void **)&d.shat, sizeof(double) * (size_t)C * d.p);
+    if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * KMAX);
+    if (e == cudaSuccess) e = A((void **)&d.sync, sizeof(ChainSync) * (size_t)C);
+    if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * KMAX);
+    if (e == cudaSuccess) e = A((void **)&d.ctl, sizeof(Ctl) * (size_t)C);
+    if (e == cudaSuccess) e = A((void **)&d.cs, sizeof(ChainState) * (size_t)C);
+    if (e == cudaSuccess) e = A((void **)&d.hdr, sizeof(Hdr));
+    if (e == cudaSuccess) e = A((void **)&h->scratch_dev, sizeof(double) * (2 * KMAX + 2));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->hdr_pinned, sizeof(Hdr));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) {
+        int rc = fail(CGG_E_CUDA, "cgg_create: allocation failed: %s", cudaGetErrorString(e));
+        cgg_destroy(h);
+        return rc;
+    }
+    cudaMemsetAsync(d.eta, 0, sizeof(double) * (size_t)C * d.lde, h->stream);
+    cudaMemsetAsync(d.cs, 0, sizeof(ChainState) * (size_t)C, h->stream);
+    cudaMemsetAsync(d.ctl, 0, sizeof(Ctl) * (size_t)C, h->stream);
+    cudaMemsetAsync(d.hdr, 0, sizeof(Hdr), h->stream);
+    cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * KMAX, h->stream);
+    cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream);
+    std::vector<double> neg((size_t)C * d.p, -1.0);
+    cudaMemcpyAsync(d.shat, neg.data(), sizeof(double) * neg.size(), cudaMemcpyHostToDevice, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    h->chain_init.assign(C, 0);
+    h->fx_valid.assign(C, 0);
+    *out = h;
+    return CGG_OK;
+}
+
+extern "C" void cgg_destroy(cgg_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    Dev &d = h->d;
+    cudaFree(d.eta); cudaFree(d.beta); cudaFree(d.shat); cudaFree(d.acc); cudaFree(d.sync); cudaFree(d.xbuf);
+    cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr);
+    cudaFree(h->scratch_dev); cudaFree(h->prof_dev); cudaFree(h->X_owned); cudaFree(h->y_owned);
+    cudaFree(h->replay_dev); cudaFree(h->samples_dev);
+    if (h->hdr_pinned) cudaFreeHost(h->hdr_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int finish_set_data(cgg_handle *h) {
+    Dev &d = h->d;
+    // y support check + lgamma sum: partials summed on the host in CTA order
+    const int G = 256;
+    double *part = nullptr; int *bad = nullptr;
+    CK(cudaMalloc((void **)&part, sizeof(double) * G));
+    CK(cudaMalloc((void **)&bad, sizeof(int)));
+    CK(cudaMemsetAsync(bad, 0, sizeof(int), h->stream));
+    scan_y_kernel<<<G, THREADS, 0, h->stream>>>(d, part, bad);
+    std::vector<double> hp(G);
+    int hbad = 0;
+    cudaError_t e1 = cudaMemcpyAsync(hp.data(), part, sizeof(double) * G, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->stream);
+    cudaFree(part); cudaFree(bad);
+    CK(e1); CK(e2); CK(e3);
+    if (hbad) return fail(CGG_E_ARG, "cgg_set_data: %d response value(s) outside the family's support (binomial needs 0/1, poisson non-negative integers, all finite)", hbad);
+    long double s = 0.0L;
+    for (int i = 0; i < G; ++i) s += hp[i];
+    if (d.family == CGG_GAUSSIAN) d.ll_const = -(double)d.n * (kLnSqrt2Pi + log(h->cfg.sd));
+    else if (d.family == CGG_POISSON) d.ll_const = -(double)s;
+    else d.ll_const = 0.0;
+    h->has_data = true;
+    std::fill(h->chain_init.begin(), h->chain_init.end(), 0);
+    std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);
+    return CGG_OK;
+}
+
+extern "C" int cgg_set_data(cgg_handle *h, const double *X_host, int64_t ldx, const double *y_host) {
+    if (!h || !X_host || !y_host) return fail(CGG_E_ARG, "cgg_set_data: NULL argument");
+    Dev &d = h->d;
+    if (ldx < d.n) return fail(CGG_E_ARG, "cgg_set_data: ldx (%lld) < n (%lld)", (long long)ldx, (long long)d.n);
+    CK(cudaSetDevice(h->cfg.device));
+    const int64_t ldd = (d.n + 31) / 32 * 32;
+    if (!h->X_owned) CK(cudaMalloc((void **)&h->X_owned, sizeof(double) * (size_t)ldd * d.p));
+    if (!h->y_owned) CK(cudaMalloc((void **)&h->y_owned, sizeof(double) * (size_t)ldd));
+    CK(cudaMemcpy2DAsync(h->X_owned, sizeof(double) * ldd, X_host, sizeof(double) * ldx, sizeof(double) * d.n, d.p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->y_owned, y_host, sizeof(double) * d.n, cudaMemcpyHostToDevice, h->stream));
+    d.X = h->X_owned; d.y = h->y_owned; d.ldx = ldd;
+    return finish_set_data(h);
+}
+
+extern "C" int cgg_set_data_device(cgg_handle *h, const double *X_dev, int64_t ldx, const double *y_dev) {
+    if (!h || !X_dev || !y_dev) return fail(CGG_E_ARG, "cgg_set_data_device: NULL argument");
+    Dev &d = h->d;
+    if (ldx < d.n || (ldx & 1)) return fail(CGG_E_ARG, "cgg_set_data_device: ldx must be even and >= n");
+    if (((uintptr_t)X_dev & 15) || ((uintptr_t)y_dev & 15)) return fail(CGG_E_ARG, "cgg_set_data_device: X and y must be 16-byte aligned");
+    CK(cudaSetDevice(h->cfg.device));
+    d.X = X_dev; d.y = y_dev; d.ldx = ldx;
+    return finish_set_data(h);
+}
+
+static int check_chain(cgg_handle *h, int32_t chain, const char *who, bool need_init) {
+    if (!h) return fail(CGG_E_ARG, "%s: NULL handle", who);
+    if (!h->has_data) return fail(CGG_E_STATE, "%s: call cgg_set_data first", who);
+    if (chain < 0 || chain >= h->d.C) return fail(CGG_E_ARG, "%s: chain %d out of range", who, chain);
+    if (need_init && !h->chain_init[chain]) return fail(CGG_E_STATE, "%s: chain %d not initialised (cgg_init_chain)", who, chain);
+    return CGG_OK;
+}
+
+extern "C" int cgg_init_chain(cgg_handle *h, int32_t chain, const double *beta0_host) {
+    int rc = check_chain(h, chain, "cgg_init_chain", false);
+    if (rc) return rc;
+    if (!beta0_host) return fail(CGG_E_ARG, "cgg_init_chain: NULL beta0");
+    Dev &d = h->d;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(d.beta + (int64_t)chain * d.p, beta0_host, sizeof(double) * d.p, cudaMemcpyHostToDevice, h->stream));
+    int grid = (int)std::min<int64_t>((d.n / 2 + THREADS - 1) / THREADS + 1, 8 * h->num_sms);
+    init_eta_kernel<<<grid, THREADS, 0, h->stream>>>(d, chain);
+    CK(cudaGetLastError());
+    ChainState cs;
+    memset(&cs, 0, sizeof cs);
+    cs.phase = PH_START;
+    CK(cudaMemcpyAsync(d.cs + chain, &cs, sizeof cs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->chain_init[chain] = 1;
+    h->fx_valid[chain] = 0;
+    return CGG_OK;
+}
+
+// Scores up to KMAX candidates of column j of one chain against its current state (no state change).
+static int eval_chunk(cgg_handle *h, int32_t chain, int64_t j, int K, const double *cand, double *out, double *prior_sum) {
+    Dev &d = h->d;
+    std::vector<double> beta_j(1);
+    CK(cudaMemcpyAsync(beta_j.data(), d.beta + (int64_t)chain * d.p + j, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<Ctl> ctl(d.C);
+    memset(ctl.data(), 0, sizeof(Ctl) * d.C);
+    for (int c = 0; c < d.C; ++c) ctl[c].commit_j = -1;
+    ctl[chain].j = (int32_t)j; ctl[chain].ncand = K;
+    for (int k = 0; k < K; ++k) ctl[chain].delta[k] = cand[k] - beta_j[0];  // diff_beta, R/glm_utils.R:127
+    std::vector<Ctl> saved(d.C);
+    CK(cudaMemcpyAsync(saved.data(), d.ctl, sizeof(Ctl) * d.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(d.ctl, ctl.data(), sizeof(Ctl) * d.C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->scratch_dev, cand, sizeof(double) * K, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(&d.hdr->done, 0, sizeof(int32_t), h->stream));
+    int rc = launch_pass(h, 1);
+    if (rc) return rc;
+    if (h->d.sharded) {
+        if (!h->xfn) return fail(CGG_E_STATE, "row-sharded handle has no exchange function (cgg_set_exchange)");
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->xfn(h->xuser, d.xbuf, (int64_t)d.C * KMAX, (void *)h->stream) != 0) return fail(CGG_E_COMM, "exchange callback failed");
+    }
+    finalize_eval_kernel<<<1, 32, 0, h->stream>>>(d, chain, (int)j, K, h->scratch_dev, h->scratch_dev + KMAX, h->scratch_dev + 2 * KMAX);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->scratch_dev + KMAX, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+    if (prior_sum) CK(cudaMemcpyAsync(prior_sum, h->scratch_dev + 2 * KMAX, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(d.ctl, saved.data(), sizeof(Ctl) * d.C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CGG_OK;
+}
+
+extern "C" int cgg_log_potential(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host, double *out_host) {
+    int rc = check_chain(h, chain, "cgg_log_potential", true);
+    if (rc) return rc;
+    if (j < 0 || j >= h->d.p) return fail(CGG_E_ARG, "cgg_log_potential: j out of range");
+    if (K < 0 || (K > 0 && (!cand_host || !out_host))) return fail(CGG_E_ARG, "cgg_log_potential: bad candidate buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int k0 = 0; k0 < K; k0 += KMAX) {
+        const int kk = std::min(KMAX, K - k0);
+        rc = eval_chunk(h, chain, j, kk, cand_host + k0, out_host + k0, nullptr);
+        if (rc) return rc;
+    }
+    return CGG_OK;
+}
+
+// f at the chain's current point (the value qslice's first f(x) would return) + prior sum
+static int ensure_fx(cgg_handle *h, int32_t chain) {
+    if (h->fx_valid[chain]) return CGG_OK;
+    Dev &d = h->d;
+    double b0 = 0.0, fx = 0.0, ps = 0.0;
+    CK(cudaMemcpyAsync(&b0, d.beta + (int64_t)chain * d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = eval_chunk(h, chain, 0, 1, &b0, &fx, &ps);
+    if (rc) return rc;
+    if (fx != fx) return fail(CGG_E_NAN, "log-potential at the starting point of chain %d is NaN", chain);
+    ChainState cs;
+    CK(cudaMemcpyAsync(&cs, d.cs + chain, sizeof cs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cs.fx0 = fx; cs.prior_sum = ps;
+    CK(cudaMemcpyAsync(d.cs + chain, &cs, sizeof cs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fx_valid[chain] = 1;
+    return CGG_OK;
+}
+
+extern "C" int cgg_get_fx(cgg_handle *h, int32_t chain, double *fx) {
+    int rc = check_chain(h, chain, "cgg_get_fx", true);
+    if (rc) return rc;
+    if (!fx) return fail(CGG_E_ARG, "cgg_get_fx: NULL output");
+    CK(cudaSetDevice(h->cfg.device));
+    rc = ensure_fx(h, chain);
+    if (rc) return rc;
+    ChainState cs;
+    CK(cudaMemcpy(&cs, h->d.cs + chain, sizeof cs, cudaMemcpyDeviceToHost));
+    *fx = cs.fx0;
+    return CGG_OK;
+}
+
+extern "C" int cgg_update_eta(cgg_handle *h, int32_t chain, int64_t j, double new_beta_j) {
+    int rc = check_chain(h, chain, "cgg_update_eta", true);
+    if (rc) return rc;
+    Dev &d = h->d;
+    if (j < 0 || j >= d.p) return fail(CGG_E_ARG, "cgg_update_eta: j out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    double cur = 0.0;
+    CK(cudaMemcpyAsync(&cur, d.beta + (int64_t)chain * d.p + j, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const double diff = new_beta_j - cur;
+    int grid = (int)std::min<int64_t>((d.n / 2 + THREADS - 1) / THREADS + 1, 8 * h->num_sms);
+    axpy_eta_kernel<<<grid, THREADS, 0, h->stream>>>(d, chain, j, diff);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(d.beta + (int64_t)chain * d.p + j, &new_beta_j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fx_valid[chain] = 0;
+    return CGG_OK;
+}
+
+extern "C" int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, double *eta_host) {
+    int rc = check_chain(h, chain, "cgg_get_state", true);
+    if (rc) return rc;
+    Dev &d = h->d;
+    CK(cudaSetDevice(h->cfg.device));
+    if (beta_host) CK(cudaMemcpyAsync(beta_host, d.beta + (int64_t)chain * d.p, sizeof(double) * d.p, cudaMemcpyDeviceToHost, h->stream));
+    if (eta_host) CK(cudaMemcpyAsync(eta_host, d.eta + (int64_t)chain * d.lde, sizeof(double) * d.n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CGG_OK;
+}
+
+extern "C" int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user) {
+    if (!h) return fail(CGG_E_ARG, "cgg_set_exchange: NULL handle");
+    h->xfn = fn; h->xuser = user;
+    return CGG_OK;
+}
+
+extern "C" void *cgg_stream(cgg_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads) {
+    if (!h) return fail(CGG_E_ARG, "cgg_launch_shape: NULL handle");
+    if (ctas) *ctas = h->d.G;
+    if (threads) *threads = THREADS;
+    return CGG_OK;
+}
+
+extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, uint64_t n_u, uint64_t *u_consumed,
+                       double *samples_out, cgg_stats *stats) {
+    if (!h) return fail(CGG_E_ARG, "cgg_run: NULL handle");
+    if (!h->has_data) return fail(CGG_E_STATE, "cgg_run: call cgg_set_data first");
+    if (n_iter < 0) return fail(CGG_E_ARG, "cgg_run: n_iter must be >= 0");
+    Dev &d = h->d;
+    const int C = d.C;
+    for (int c = 0; c < C; ++c)
+        if (!h->chain_init[c]) return fail(CGG_E_STATE, "cgg_run: chain %d not initialised (cgg_init_chain)", c);
+    if (d.sharded && !h->xfn) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange function");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int c = 0; c < C; ++c) {
+        int rc = ensure_fx(h, c);
+        if (rc) return rc;
+    }
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_iter == 0) return CGG_OK;
+
+    // replay stream
+    if (replay_u) {
+        const uint64_t need = (uint64_t)C * n_u;
+        if (need > h->replay_cap) {
+            cudaFree(h->replay_dev); h->replay_dev = nullptr; h->replay_cap = 0;
+            CK(cudaMalloc((void **)&h->replay_dev, sizeof(double) * (need ? need : 1)));
+            h->replay_cap = need;
+        }
+        CK(cudaMemcpyAsync(h->replay_dev, replay_u, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
+        d.replay = h->replay_dev; d.n_u = n_u;
+    } else { d.replay = nullptr; d.n_u = 0; }
+    // sample store
+    const size_t ns = (size_t)C * n_iter * d.p;
+    if (ns > h->samples_cap) {
+        cudaFree(h->samples_dev); h->samples_dev = nullptr; h->samples_cap = 0;
+        CK(cudaMalloc((void **)&h->samples_dev, sizeof(double) * ns));
+        h->samples_cap = ns;
+    }
+    d.samples = h->samples_dev;
+
+    // per-run reset of the chain machines (cursor persists across runs; counters restart)
+    std::vector<ChainState> cs(C);
+    CK(cudaMemcpyAsync(cs.data(), d.cs, sizeof(ChainState) * C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<Ctl> ctl(C);
+    memset(ctl.data(), 0, sizeof(Ctl) * C);
+    for (int c = 0; c < C; ++c) {
+        cs[c].phase = PH_START; cs[c].status = CGG_OK; cs[c].iter = 0; cs[c].j = 0;
+        cs[c].updates = cs[c].chain_passes = cs[c].commit_passes = cs[c].cand_evals = 0;
+        cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = 0;
+        ctl[c].commit_j = -1;
+    }
+    Hdr hdr;
+    memset(&hdr, 0, sizeof hdr);
+    d.n_iter = n_iter;
+    CK(cudaMemcpyAsync(d.cs, cs.data(), sizeof(ChainState) * C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.ctl, ctl.data(), sizeof(Ctl) * C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * KMAX, h->stream));
+    CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
+    const bool want_prof = getenv("CGG_PROFILE") != nullptr;
+    if (want_prof) {
+        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 64));
+        CK(cudaMemsetAsync(h->prof_dev, 0, 64, h->stream));
+    }
+    d.prof = want_prof ? h->prof_dev : nullptr;
+
+    uint64_t launches = 0;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (h->cfg.driver == CGG_DRIVER_PERSISTENT) {
+        Dev dd = d;
+        void *args[] = {&dd};
+        CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G), dim3(THREADS), args, h->smem, h->stream));
+        launches = 1;
+    } else {
+        const int batch = d.sharded ? 1 : 32;
+        for (;;) {
+            for (int i = 0; i < batch; ++i) {
+                int rc = launch_pass(h, d.sharded ? 1 : 0);
+                if (rc) return rc;
+                ++launches;
+                if (d.sharded) {
+                    if (h->xfn(h->xuser, d.xbuf, (int64_t)C * KMAX, (void *)h->stream) != 0) return fail(CGG_E_COMM, "cgg_run: exchange callback failed");
+                    decide_kernel<<<1, THREADS, 0, h->stream>>>(d);
+                    ++launches;
+                }
+            }
+            CK(cudaMemcpyAsync(h->hdr_pinned, d.hdr, sizeof(Hdr), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (h->hdr_pinned->done) break;
+        }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT) {
+        unsigned long long pr[8];
+        CK(cudaMemcpy(pr, h->prof_dev, 64, cudaMemcpyDeviceToHost));
+        const double nw = pr[6] ? (double)pr[6] : 1.0;
+        fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g arrive %.3g | slow-waits/worker %.1f workers %llu\n",
+                ms, pr[0] / nw, pr[1] / nw, pr[2] / nw, pr[5] / nw, pr[6]);
+    }
+
+    CK(cudaMemcpy(&hdr, d.hdr, sizeof hdr, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cs.data(), d.cs, sizeof(ChainState) * C, cudaMemcpyDeviceToHost));
+    if (samples_out) CK(cudaMemcpy(samples_out, d.samples, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    cgg_stats st;
+    memset(&st, 0, sizeof st);
+    int bad = CGG_OK, bad_chain = -1;
+    for (int c = 0; c < C; ++c) {
+        st.updates += cs[c].updates; st.chain_passes += cs[c].chain_passes; st.commit_passes += cs[c].commit_passes;
+        st.cand_evals += cs[c].cand_evals; st.ref_evals += cs[c].ref_evals; st.stepouts += cs[c].stepouts; st.shrinks += cs[c].shrinks;
+        st.passes += cs[c].passes;
+        if (u_consumed) u_consumed[c] = cs[c].cursor;
+        if (cs[c].status != CGG_OK && bad == CGG_OK) { bad = cs[c].status; bad_chain = c; }
+    }
+    st.launches = launches; st.sweep_ms = ms;
+    st.algorithmic_bytes = 8.0 * (double)d.n * (3.0 * (double)st.chain_passes + 2.0 * (double)st.commit_passes);
+    if (stats) *stats = st;
+    if (hdr.abort) return fail(CGG_E_CUDA, "cgg_run: a chain wait timed out (a worker never arrived)");
+    if (bad != CGG_OK) {
+        const char *why = bad == CGG_E_NAN ? "log-potential is NaN (the reference would stop with 'missing value where TRUE/FALSE needed')"
+                        : bad == CGG_E_STREAM ? "replay-uniform stream exhausted"
+                        : bad == CGG_E_NOTERM ? "slice loop did not terminate" : "device-side failure";
+        return fail(bad, "cgg_run: chain %d: %s", bad_chain, why);
+    }
+    return CGG_OK;
+}

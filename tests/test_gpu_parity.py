@@ -1,0 +1,182 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Gates from the north star:
+G1  same (beta, eta, j, candidates) => |f_gpu - f_oracle| <= 1e-12 |f_oracle|
+G2  replayed uniforms               => every sample within 1e-9, identical uniform consumption
+"""
+import json
+import os
+import numpy as np
+import pytest
+import oracle
+from helpers import synth, PRIOR_CASES
+from mcmcglm_b200 import Engine, CggError, _lib
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL_G1 = 1e-12
+ATOL_G2 = 1e-9
+
+
+def _engine(family, prior, X, **kw):
+    n, p = X.shape
+    return Engine(n, p, family=family, sd=kw.pop("sd", 1.0), **PRIOR_CASES[prior], **kw)
+
+
+@pytest.mark.parametrize("family", ["gaussian", "binomial", "poisson"])
+@pytest.mark.parametrize("prior", ["normal", "laplace", "student_t"])
+@pytest.mark.parametrize("n", [1001, 100000])
+def test_g1_log_potential(family, prior, n):
+    p = 7
+    X, y, bt = synth(family, n, p, seed=n % 97)
+    rng = np.random.default_rng(3)
+    beta = bt + 0.2 * rng.standard_normal(p)
+    m = oracle.make_model(family, sd=1.3, **PRIOR_CASES[prior])
+    with _engine(family, prior, X, sd=1.3) as e:
+        e.set_data(X, y)
+        e.init_chain(0, beta)
+        b_gpu, eta_gpu = e.state(0)
+        eta = oracle.init_eta(X, beta)
+        assert np.array_equal(b_gpu, beta)
+        assert np.array_equal(eta_gpu, eta)          # K4 is bit-identical to the oracle's GEMV
+        for j in (0, 3, p - 1):
+            cands = beta[j] + np.array([0.0, -0.4, 0.4, 1e-3, -1e-3, 0.05, -0.05, 0.2, 0.11, -0.3, 0.01])
+            got = e.log_potential(0, j, cands)       # 11 candidates: two chunks of <= KMAX
+            ref = oracle.log_potential(m, X, y, beta, eta, j, cands)
+            assert np.all(np.abs(got - ref) <= RTOL_G1 * np.abs(ref)), (got - ref) / ref
+        assert abs(e.fx(0) - oracle.log_potential(m, X, y, beta, eta, 0, [beta[0]])[0]) <= RTOL_G1 * abs(e.fx(0))
+
+
+def test_update_eta_bit_exact():
+    X, y, bt = synth("poisson", 5003, 4, seed=5)
+    with _engine("poisson", "normal", X) as e:
+        e.set_data(X, y)
+        e.init_chain(0, bt)
+        eta = oracle.init_eta(X, bt)
+        for j, nb in [(1, 0.3), (3, -0.2), (1, 0.1)]:
+            beta, _ = e.state(0, want_eta=False)
+            eta = oracle.update_linear_predictor(nb, beta[j], eta, X[:, j])
+            e.update_eta(0, j, nb)
+        beta, eta_gpu = e.state(0)
+        assert np.array_equal(eta_gpu, eta) and beta[1] == 0.1 and beta[3] == -0.2
+
+
+@pytest.mark.parametrize("driver", ["persistent", "stepwise"])
+@pytest.mark.parametrize("K,tau", [(1, 0.0), (8, 0.0), (8, 0.5), (3, 0.3)])
+def test_g2_readme_golden_replay(driver, K, tau):
+    """The reference's README run (seed 42) replayed on the GPU from R's recorded runif stream."""
+    z = np.load(os.path.join(G, "readme_gaussian.npz"))
+    with open(os.path.join(G, "readme_gaussian.json")) as f:
+        readme = json.load(f)
+    X, y = z["X"], z["y"]
+    with Engine(1000, 3, family="gaussian", sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0, w=0.5,
+                K=K, spec_tau=tau, driver=driver) as e:
+        e.set_data(X, y)
+        e.init_chain(0, z["beta0"])
+        S, st = e.run(500, replay_u=z["uniforms"])
+    S = np.vstack([z["beta0"], S[0]])
+    assert np.max(np.abs(S - z["samples"])) <= ATOL_G2
+    assert st["uniforms_used"][0] == int(z["uniforms_used"])
+    assert st["ref_evals"] == int(z["n_eval"]) and st["stepouts"] == int(z["n_stepout"]) and st["shrinks"] == int(z["n_shrink"])
+    assert st["updates"] == 1500
+    # and, independently of the oracle, the numbers the reference printed (README.md:79-80, :114-120)
+    for row, prow in zip(S[:6], readme["head_samples"]):
+        assert np.allclose(row, prow, rtol=2e-7, atol=1e-9)
+    coef = S[102:].mean(0)                    # burnin == FALSE rows (quirks Q1/Q3)
+    assert np.allclose(coef, list(readme["coef"].values()), rtol=1e-6)
+
+
+@pytest.mark.parametrize("family,prior,w,max_steps", [
+    ("binomial", "laplace", 0.5, -1), ("poisson", "student_t", 0.5, -1), ("gaussian", "normal", 0.05, -1),
+    ("binomial", "normal", 0.02, 5), ("poisson", "laplace", 0.01, 3), ("gaussian", "student_t", 0.3, 0)])
+@pytest.mark.parametrize("driver", ["persistent", "stepwise"])
+def test_g2_replay_and_philox_vs_oracle(family, prior, w, max_steps, driver):
+    n, p, C, iters = 3001, 5, 3, 40
+    X, y, bt = synth(family, n, p, seed=21)
+    m = oracle.make_model(family, sd=1.0, **PRIOR_CASES[prior])
+    rng = np.random.default_rng(8)
+    beta0 = 0.5 * rng.standard_normal((C, p))
+    U = rng.random((C, 40000))
+    for mode in ("replay", "philox"):
+        with _engine(family, prior, X, w=w, max_steps=max_steps, n_chains=C, K=6, spec_tau=0.4, driver=driver,
+                     seed=77, chain_offset=10) as e:
+            e.set_data(X, y)
+            for c in range(C):
+                e.init_chain(c, beta0[c])
+            S, st = e.run(iters, replay_u=U if mode == "replay" else None)
+            for c in range(C):
+                ref = oracle.run_chain(m, X, y, beta0[c], w=w, n_iter=iters, max_steps=max_steps,
+                                       replay_u=U[c] if mode == "replay" else None, seed=77, chain=10 + c)
+                assert ref["rc"] == 0
+                assert np.max(np.abs(S[c] - ref["samples"])) <= ATOL_G2, (mode, c)
+                assert st["uniforms_used"][c] == ref["uniforms_used"]
+                beta, eta = e.state(c)
+                assert np.max(np.abs(eta - ref["eta"])) <= 1e-9 and np.max(np.abs(beta - ref["beta"])) <= ATOL_G2
+
+
+def test_chunked_runs_continue_the_chain():
+    X, y, bt = synth("binomial", 2000, 4, seed=2)
+    m = oracle.make_model("binomial", **PRIOR_CASES["normal"])
+    ref = oracle.run_chain(m, X, y, np.zeros(4), w=0.3, n_iter=30, seed=5, chain=0)
+    with _engine("binomial", "normal", X, w=0.3, seed=5) as e:
+        e.set_data(X, y)
+        e.init_chain(0, np.zeros(4))
+        parts = [e.run(k)[0][0] for k in (7, 13, 10)]
+    assert np.max(np.abs(np.vstack(parts) - ref["samples"])) <= ATOL_G2
+
+
+def test_large_n_roundtrip_properties():
+    """Size-independent checks at a BASELINE-sized column (n = 1e6): the committed eta always equals
+    X beta recomputed from scratch, and f(x0) carried by the sweep equals a fresh evaluation."""
+    n, p = 1_000_000, 6
+    X, y, bt = synth("binomial", n, p, seed=9)
+    with _engine("binomial", "laplace", X, w=0.5, n_chains=2, K=8) as e:
+        e.set_data(X, y)
+        e.init_chain(0, np.zeros(p))
+        e.init_chain(1, 0.1 * np.ones(p))
+        S, st = e.run(3)
+        for c in range(2):
+            beta, eta = e.state(c)
+            assert np.array_equal(beta, S[c, -1])
+            assert np.max(np.abs(eta - X @ beta)) < 1e-11
+            carried = e.fx(c)
+            fresh = e.log_potential(c, 0, [beta[0]])[0]
+            assert abs(carried - fresh) <= 1e-12 * abs(fresh)
+    assert st["updates"] == 2 * 3 * p
+
+
+def test_errors():
+    X, y, _ = synth("binomial", 100, 2, seed=1)
+    with _engine("binomial", "normal", X) as e:
+        with pytest.raises(CggError) as ei:
+            e.run(1)
+        assert ei.value.code == _lib.E_STATE
+        ybad = y.copy(); ybad[3] = 2.0
+        with pytest.raises(CggError) as ei:
+            e.set_data(X, ybad)
+        assert ei.value.code == _lib.E_ARG
+        e.set_data(X, y)
+        with pytest.raises(CggError) as ei:
+            e.run(1)
+        assert ei.value.code == _lib.E_STATE      # chain not initialised
+        e.init_chain(0, np.zeros(2))
+        with pytest.raises(CggError) as ei:
+            e.run(5, replay_u=np.full(7, 0.5))
+        assert ei.value.code == _lib.E_STREAM
+        e.init_chain(0, np.array([np.nan, 0.0]))
+        with pytest.raises(CggError) as ei:
+            e.run(1)
+        assert ei.value.code == _lib.E_NAN
+
+
+def test_neg_inf_is_outside_the_slice_not_an_error():
+    # poisson: huge candidate => exp overflow => log-potential -Inf => "y < -Inf" is FALSE (R semantics)
+    X, y, _ = synth("poisson", 500, 2, seed=1)
+    m = oracle.make_model("poisson", **PRIOR_CASES["normal"])
+    with _engine("poisson", "normal", X, w=2000.0, seed=3) as e:
+        e.set_data(X, y)
+        e.init_chain(0, np.zeros(2))
+        f = e.log_potential(0, 1, [1500.0, -1500.0, 0.01])
+        fr = oracle.log_potential(m, X, y, np.zeros(2), np.zeros(500), 1, [1500.0, -1500.0, 0.01])
+        assert f[0] == -np.inf and fr[0] == -np.inf and f[1] == fr[1] and np.isfinite(f[2])
+        S, _ = e.run(5)
+    ref = oracle.run_chain(m, X, y, np.zeros(2), w=2000.0, n_iter=5, seed=3, chain=0)
+    assert np.max(np.abs(S[0] - ref["samples"])) <= ATOL_G2

@@ -1,0 +1,69 @@
+// fp64_probe.cu -- measures what bounds the per-row math of the CGGibbs pass on this GPU:
+// DFMA issue rate and the cost of the three families' row terms, against a plain streaming read.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fp64_probe tools/fp64_probe.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../mcmcglm_b200/csrc/cgg_math.cuh"
+using namespace cgg;
+
+__global__ void k_dfma(double *out, int iters) {
+    double a = threadIdx.x * 1e-9, b = 1.0000001, c = 1e-7, d = a + 1, e = a + 2, f = a + 3;
+    for (int i = 0; i < iters; ++i) { a = fma(a, b, c); d = fma(d, b, c); e = fma(e, b, c); f = fma(f, b, c); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a + d + e + f;
+}
+template <int FAM>
+__global__ void k_term(double *out, int iters) {
+    double y = (threadIdx.x & 1), eta = 0.001 * threadIdx.x - 0.1, acc = 0.0, x = 1.0 + 1e-3 * blockIdx.x;
+    for (int i = 0; i < iters; ++i) {
+        acc += row_term<FAM>(y, eta_shift(eta, x, 1e-4 * i), 1.0);
+        acc += row_term<FAM>(y, eta_shift(-eta, x, 1e-4 * i), 1.0);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void k_exp(double *out, int iters) {
+    double eta = 0.001 * threadIdx.x - 0.1, acc = 0.0;
+    for (int i = 0; i < iters; ++i) { acc += exp(eta + 1e-4 * i); acc += exp(-eta - 1e-4 * i); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void k_log1p(double *out, int iters) {
+    double t = 0.001 * threadIdx.x + 0.01, acc = 0.0;
+    for (int i = 0; i < iters; ++i) { acc += log1p(t + 1e-6 * i); acc += log1p(0.5 * t + 1e-6 * i); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void k_read(const double2 *in, double *out, size_t n2) {
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+        double2 v = ld_stream2(reinterpret_cast<const double *>(in + i));
+        acc += v.x + v.y;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <typename F>
+static float timeit(F f) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    f(); cudaDeviceSynchronize();
+    cudaEventRecord(a); f(); cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); return ms;
+}
+int main() {
+    cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+    const int G = pr.multiProcessorCount * 8, T = 256, iters = 4096;
+    double *out; cudaMalloc(&out, sizeof(double) * G * T);
+    const double thr = (double)G * T;
+    float ms = timeit([&] { k_dfma<<<G, T>>>(out, iters); });
+    printf("{\"gpu\": \"%s\", \"sms\": %d,\n \"dfma_per_s\": %.4g,\n", pr.name, pr.multiProcessorCount, thr * iters * 4 / (ms * 1e-3));
+    ms = timeit([&] { k_exp<<<G, T>>>(out, iters); });
+    printf(" \"exp_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_log1p<<<G, T>>>(out, iters); });
+    printf(" \"log1p_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_term<CGG_GAUSSIAN><<<G, T>>>(out, iters); });
+    printf(" \"term_gaussian_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_term<CGG_BINOMIAL><<<G, T>>>(out, iters); });
+    printf(" \"term_binomial_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_term<CGG_POISSON><<<G, T>>>(out, iters); });
+    printf(" \"term_poisson_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    size_t bytes = 4ull << 30; double2 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
+    ms = timeit([&] { k_read<<<pr.multiProcessorCount * 16, T>>>(buf, out, bytes / 16); });
+    printf(" \"stream_read_GBps\": %.4g}\n", bytes / (ms * 1e-3) / 1e9);
+    return 0;
+}
