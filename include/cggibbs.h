@@ -145,6 +145,12 @@ int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, double *eta_h
 /* Carried log-potential at the chain's current point (what qslice's first f(x) would return). */
 int cgg_get_fx(cgg_handle *h, int32_t chain, double *fx);
 
+/* Diagnostic: out[i] = the per-row log-density term the kernels accumulate for (y_i, eta_i), i.e.
+ * log_density(family, linkinv(eta_i), y_i) of R/glm_utils.R:24-57 minus the terms that do not depend on
+ * beta (gaussian: -log(sqrt(2 pi) sd); poisson: -lgamma(y + 1)).  Used by the accuracy tests. */
+int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double *y_host, const double *eta_host,
+                        double sd, double *out_host);
+
 int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
 /* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void *cgg_stream(cgg_handle *h);

@@ -18,7 +18,7 @@ MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 # every symbol include/cggibbs.h declares
 EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cgg_set_data",
            "cgg_set_data_device", "cgg_init_chain", "cgg_log_potential", "cgg_update_eta", "cgg_run",
-           "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape"]
+           "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms"]
 
 
 class Config(C.Structure):
@@ -76,6 +76,7 @@ def load():
     L.cgg_get_state.argtypes = [vp, i32, dp, dp]
     L.cgg_get_fx.argtypes = [vp, i32, dp]
     L.cgg_set_exchange.argtypes = [vp, EXCHANGE_FN, vp]
+    L.cgg_debug_row_terms.argtypes = [i32, i32, i64, dp, dp, C.c_double, dp]
     L.cgg_stream.argtypes = [vp]
     L.cgg_stream.restype = vp
     L.cgg_launch_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]

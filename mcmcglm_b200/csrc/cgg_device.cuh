@@ -14,7 +14,7 @@ namespace cgg {
 constexpr int KMAX = CGG_KMAX;
 constexpr int THREADS = 512;   // one CTA per SM, 16 warp-workers each
 constexpr int NWARPS = THREADS / 32;
-constexpr int CMAX = 64;       // chains per device (shared-memory slots of the CTA-level reduction)
+constexpr int CMAX = 32;       // chains per device (shared-memory slots of the CTA-level reduction)
 constexpr int NU = 12;         // uniforms fetched per decision: 3 start draws + KMAX proposals (+1 spare)
 constexpr int RING_D = 4;      // tiles in flight per warp (cp.async ring depth)
 constexpr int RING_OPS = 4;    // eta, y, X_j, X_commit
@@ -165,10 +165,12 @@ __device__ __forceinline__ double acc_take(Acc *a) {
 // adds X_commit (read) and eta (write).  Operand tiles are staged global -> shared with cp.async into a
 // RING_D-deep per-warp ring, so RING_D - 1 tiles are in flight while one is being scored; every lane
 // reads back only the 16-byte slots it copied itself, so no barrier of any kind is needed.
+// The candidate loop is a run-time loop (trip count nc is warp-uniform) with the per-lane running sums in
+// shared memory: sacc[k * 32 + lane].  s_dl[k] = cand_k - beta_j comes from the CTA's shared control block.
 template <int FAMILY>
 __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int nc, int cj, double cdelta,
-                                                const double (&dl)[KMAX], long long wid, long long W, int lane,
-                                                uint32_t ring, double (&acc)[KMAX]) {
+                                                const double *s_dl, long long wid, long long W, int lane,
+                                                uint32_t ring, const double2 *tab, double *sacc) {
     const double *xj = d.X + (int64_t)j * d.ldx;
     const double *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
     double *eta = d.eta + (int64_t)c * d.lde;
@@ -186,6 +188,7 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
     };
 #pragma unroll
     for (int s = 0; s < RING_D - 1; ++s) issue(wid + s * W, s);
+    for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] = 0.0;
     int stage = 0;
     for (long long T = wid; T < d.n_tiles; T += W) {
         issue(T + (RING_D - 1) * W, (stage + RING_D - 1) & (RING_D - 1));
@@ -201,13 +204,9 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
                 *reinterpret_cast<double2 *>(eta + i) = e;
             }
             if (nc > 0) {
-                const double2 yv = lds2(s + 512u), xv = lds2(s + 1024u);
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k)
-                    if (k < nc) {
-                        acc[k] += row_term<FAMILY>(yv.x, eta_shift(e.x, xv.x, dl[k]), d.inv_sd);
-                        acc[k] += row_term<FAMILY>(yv.y, eta_shift(e.y, xv.y, dl[k]), d.inv_sd);
-                    }
+                const RowPair<FAMILY> rp(lds2(s + 512u), e, lds2(s + 1024u));
+#pragma unroll 1
+                for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
             }
         }
         stage = (stage + 1) & (RING_D - 1);
@@ -219,12 +218,8 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
         if (Tl % W == wid && lane == (int)((t % TILE_ROWS) >> 1)) {
             double e = __ldcg(eta + t);
             if (cj >= 0) { e = eta_shift(e, __ldg(xc + t), cdelta); eta[t] = e; }
-            if (nc > 0) {
-                const double yy = __ldg(d.y + t), xx = __ldg(xj + t);
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k)
-                    if (k < nc) acc[k] += row_term<FAMILY>(yy, eta_shift(e, xx, dl[k]), d.inv_sd);
-            }
+            const double yy = __ldg(d.y + t), xx = __ldg(xj + t);
+            for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += row_term<FAMILY>(yy, eta_shift(e, xx, s_dl[k]), d.inv_sd, tab);
         }
     }
 }
@@ -234,21 +229,16 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
 // otherwise the number of candidates scored (0 when the pass was idle or commit-only); j_out = column.
 template <int FAMILY>
 __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw /* the CTA's shared copy of ctl[c] */,
-                                           long long wid, long long W, int lane, uint32_t ring,
-                                           double (&acc)[KMAX], int &j_out) {
+                                           long long wid, long long W, int lane, uint32_t ring, const double2 *tab,
+                                           double *sacc, double (&acc)[KMAX], int &j_out) {
     const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
     const int j = (int)(w0 & 0xffffffffLL), nc = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
     j_out = j;
     if (j < 0) return -1;
     if (nc == 0 && cj < 0) return 0;
-    const double cdelta = cw[2];
-    double dl[KMAX];
+    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cw[2], cw + 3, wid, W, lane, ring, tab, sacc);
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) { dl[k] = cw[3 + k]; acc[k] = 0.0; }
-    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cdelta, dl, wid, W, lane, ring, acc);
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-        if (k < nc) acc[k] = warp_sum(acc[k]);
+    for (int k = 0; k < KMAX; ++k) acc[k] = (k < nc) ? warp_sum(sacc[k * 32 + lane]) : 0.0;
     return nc;
 }
 
@@ -260,17 +250,19 @@ struct CtaShared {                       // views into dynamic shared memory, si
     unsigned long long *ver;             // [C] last version of chain c seen by this CTA
     int *cnt;                            // [C] warps of this CTA that delivered their partials
     int *lock;                           // [C] elected poller of the chain's version flag
+    double *sacc;                        // [NWARPS][KMAX][32] per-lane running sums of the chain pass in flight
     uint32_t ring0;                      // shared-space address of warp 0's ring
     __device__ __forceinline__ CtaShared(unsigned char *base, int C) {
         ring0 = (uint32_t)__cvta_generic_to_shared(base);
-        part = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
+        sacc = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
+        part = sacc + NWARPS * KMAX * 32;
         ctl = part + (size_t)C * NWARPS * KMAX;
         ver = reinterpret_cast<unsigned long long *>(ctl + (size_t)C * CTL_WORDS);
         cnt = reinterpret_cast<int *>(ver + C);
         lock = cnt + C;
     }
     static size_t bytes(int C) {
-        return (size_t)NWARPS * RING_BYTES_PER_WARP +
+        return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * NWARPS * KMAX * 32 +
                (size_t)C * (sizeof(double) * (NWARPS * KMAX + CTL_WORDS) + sizeof(unsigned long long) + 2 * sizeof(int));
     }
 };

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/cggibbs.h"
+#include "cgg_math_tables.cuh"
 
 namespace cgg {
 
@@ -18,42 +19,127 @@ __device__ __forceinline__ double eta_shift(double eta, double x, double diff) {
     return __dadd_rn(eta, __dmul_rn(x, diff));
 }
 
-// One row's log-density up to a per-dataset constant (added once per sum by ll_finish):
-//   gaussian  dnorm(y, eta, sd, log=TRUE)            -> -0.5 z^2            (R/glm_utils.R:40-42)
-//   binomial  dbinom(y, 1, logit_linkinv(eta), TRUE) -> -softplus(+-eta)    (R/glm_utils.R:45-47)
-//   poisson   dpois(y, pmax(exp(eta), eps), TRUE)    -> y log(mu) - mu      (R/glm_utils.R:50-52)
+// Fused softplus(s) = max(s, 0) + log1p(exp(-|s|)) for two independent arguments at once (the two rows a
+// lane owns in a tile), written 2-wide so that the two dependency chains interleave.  ~40 fp64 operations
+// per argument (libdevice exp + log1p cost ~85), <= ~1 ulp:
+//   exp(-|s|) : k = rint(-|s| log2 e), r = -|s| - k ln2 (two-step Cody-Waite), degree-11 polynomial, exponent add
+//   log1p(t)  : c = rint(32 t)/32, v = (t - c)/(1 + c) via a 33-entry {1/(1+c), log(1+c)} table in shared
+//               memory, log1p(t) = log(1+c) + v + v^2 q(v) with |v| <= 1/64
+// stats' logit_linkinv clamps exp(eta) to [DBL_EPSILON, 1/DBL_EPSILON] when |eta| > 30, which is the same as
+// evaluating at |s| = 36.04...: applied here to a = |s|.  Coefficients and table: cgg_math_tables.cuh
+// (tools/gen_math_tables.py, checked against mpmath).  NaN propagates; the table index is clamped so a NaN
+// can never index out of bounds.
+__device__ __forceinline__ double poly_exp(double r) {
+    static_assert(EXP_DEG == 11, "layout below assumes degree 11");
+    // two interleaved half-degree Horner chains in r^2 (depth 7 instead of 11)
+    const double r2 = r * r;
+    double pe = EXP_C[10], po = EXP_C[11];
+    pe = fma(pe, r2, EXP_C[8]); po = fma(po, r2, EXP_C[9]);
+    pe = fma(pe, r2, EXP_C[6]); po = fma(po, r2, EXP_C[7]);
+    pe = fma(pe, r2, EXP_C[4]); po = fma(po, r2, EXP_C[5]);
+    pe = fma(pe, r2, EXP_C[2]); po = fma(po, r2, EXP_C[3]);
+    pe = fma(pe, r2, EXP_C[0]); po = fma(po, r2, EXP_C[1]);
+    return fma(po, r, pe);
+}
+__device__ __forceinline__ double poly_l1p_q(double v, double v2) {
+    static_assert(L1P_QDEG == 6, "layout below assumes degree 6");
+    double qe = L1P_Q[6], qo = L1P_Q[5];
+    qe = fma(qe, v2, L1P_Q[4]); qo = fma(qo, v2, L1P_Q[3]);
+    qe = fma(qe, v2, L1P_Q[2]); qo = fma(qo, v2, L1P_Q[1]);
+    qe = fma(qe, v2, L1P_Q[0]);
+    return fma(qo, v, qe);
+}
+__device__ __forceinline__ void softplus2(double s0, double s1, const double2 *tab, double &o0, double &o1) {
+    const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer
+    double a0 = fabs(s0), a1 = fabs(s1);
+    a0 = (a0 > 30.0) ? kLogitClampEta : a0;
+    a1 = (a1 > 30.0) ? kLogitClampEta : a1;
+    const double kd0 = fma(-a0, 1.4426950408889634, SHIFT), kd1 = fma(-a1, 1.4426950408889634, SHIFT);
+    const double kf0 = kd0 - SHIFT, kf1 = kd1 - SHIFT;
+    double r0 = fma(kf0, -6.93147180369123816490e-01, -a0), r1 = fma(kf1, -6.93147180369123816490e-01, -a1);
+    r0 = fma(kf0, -1.90821492927058770002e-10, r0); r1 = fma(kf1, -1.90821492927058770002e-10, r1);
+    const double p0 = poly_exp(r0), p1 = poly_exp(r1);
+    const double t0 = __hiloint2double(__double2hiint(p0) + (__double2loint(kd0) << 20), __double2loint(p0));   // p * 2^k, k in [-52, 0]
+    const double t1 = __hiloint2double(__double2hiint(p1) + (__double2loint(kd1) << 20), __double2loint(p1));
+    const double md0 = fma(t0, (double)L1P_N, SHIFT), md1 = fma(t1, (double)L1P_N, SHIFT);
+    int m0 = __double2loint(md0), m1 = __double2loint(md1);
+    m0 = min(max(m0, 0), L1P_N); m1 = min(max(m1, 0), L1P_N);
+    const double2 tb0 = tab[m0], tb1 = tab[m1];
+    const double v0 = fma(md0 - SHIFT, -1.0 / L1P_N, t0) * tb0.x, v1 = fma(md1 - SHIFT, -1.0 / L1P_N, t1) * tb1.x;
+    const double w0 = v0 * v0, w1 = v1 * v1;
+    const double q0 = poly_l1p_q(v0, w0), q1 = poly_l1p_q(v1, w1);
+    const double l0 = tb0.y + fma(w0, q0, v0), l1 = tb1.y + fma(w1, q1, v1);
+    o0 = ((s0 > 0.0) ? a0 : 0.0) + l0;
+    o1 = ((s1 > 0.0) ? a1 : 0.0) + l1;
+}
+
+// The two rows (i, i+1) a lane owns in a tile, with everything that does not depend on the candidate
+// hoisted out of the candidate loop.  term(delta) returns the sum of the two rows' log-density terms up to
+// a per-dataset constant (added once per sum, ll_const):
+//   gaussian  dnorm(y, eta', sd, log=TRUE)            -> -0.5 z^2            (R/glm_utils.R:40-42)
+//   binomial  dbinom(y, 1, logit_linkinv(eta'), TRUE) -> -softplus(+-eta')   (R/glm_utils.R:45-47)
+//   poisson   dpois(y, pmax(exp(eta'), eps), TRUE)    -> y log(mu) - mu      (R/glm_utils.R:50-52)
+// with eta' = eta + X_j * delta formed as two roundings (eta_shift).
+template <int FAMILY> struct RowPair;
+
+template <> struct RowPair<CGG_GAUSSIAN> {
+    double y0, y1, e0, e1, x0, x1;
+    __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) : y0(y.x), y1(y.y), e0(e.x), e1(e.y), x0(x.x), x1(x.y) {}
+    __device__ __forceinline__ double term(double dk, double inv_sd, const double2 *) const {
+        const double z0 = (y0 - eta_shift(e0, x0, dk)) * inv_sd, z1 = (y1 - eta_shift(e1, x1, dk)) * inv_sd;
+        return -0.5 * fma(z0, z0, z1 * z1);
+    }
+};
+
+// dbinom_raw returns log(p) (y = 1) or log(1 - p) (y = 0) = -softplus(s), s = eta' for y = 0, -eta' for
+// y = 1.  Multiplying by +-1 is exact, so s = (+-eta) + (+-x) * delta has the very same two roundings as
+// +-(eta + x * delta): the sign is applied once per row instead of once per candidate.
+template <> struct RowPair<CGG_BINOMIAL> {
+    double e0, e1, x0, x1;
+    __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) {
+        const double g0 = (y.x > 0.5) ? -1.0 : 1.0, g1 = (y.y > 0.5) ? -1.0 : 1.0;
+        e0 = e.x * g0; e1 = e.y * g1; x0 = x.x * g0; x1 = x.y * g1;
+    }
+    __device__ __forceinline__ double term(double dk, double, const double2 *tab) const {
+        double o0, o1;
+        softplus2(eta_shift(e0, x0, dk), eta_shift(e1, x1, dk), tab, o0, o1);
+        return -(o0 + o1);
+    }
+};
+
+// mu = pmax(exp(eta'), eps); dpois_raw(y, mu) = y log(mu) - mu - lgamma(y + 1).  The lgamma term does not
+// depend on beta and is added once per sum.  exp overflow gives -Inf as in R (!R_FINITE(lambda) -> R_D__0).
+template <> struct RowPair<CGG_POISSON> {
+    double y0, y1, e0, e1, x0, x1;
+    __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) : y0(y.x), y1(y.y), e0(e.x), e1(e.y), x0(x.x), x1(x.y) {}
+    __device__ __forceinline__ double term(double dk, double, const double2 *) const {
+        double l0 = eta_shift(e0, x0, dk), l1 = eta_shift(e1, x1, dk);
+        l0 = (l0 < kLogEps) ? kLogEps : l0; l1 = (l1 < kLogEps) ? kLogEps : l1;
+        const double m0 = exp(l0), m1 = exp(l1);
+        const double v0 = (m0 > 1.7976931348623157e308) ? -INFINITY : fma(y0, l0, -m0);
+        const double v1 = (m1 > 1.7976931348623157e308) ? -INFINITY : fma(y1, l1, -m1);
+        return v0 + v1;
+    }
+};
+
+// Single-row form (odd last row of a matrix, diagnostics): the pair with a neutral second row removed.
 template <int FAMILY>
-__device__ __forceinline__ double row_term(double y, double eta, double inv_sd);
-
-template <>
-__device__ __forceinline__ double row_term<CGG_GAUSSIAN>(double y, double eta, double inv_sd) {
-    double z = (y - eta) * inv_sd;
-    return -0.5 * z * z;
-}
-
-// stats' logit_linkinv clamps exp(eta) to [DBL_EPSILON, 1/DBL_EPSILON] when |eta| > 30, which is the
-// same as evaluating at eta = -+36.04...; dbinom_raw then returns log(p) (y = 1) or log(1 - p)
-// (y = 0).  Both equal -log(1 + exp(-+eta)), evaluated here without forming p or 1 - p:
-//   -softplus(s) = -(max(s, 0) + log1p(exp(-|s|))),  s = eta for y = 0, -eta for y = 1.
-// NaN propagates (comparisons with NaN are false, exp/log1p keep it).
-template <>
-__device__ __forceinline__ double row_term<CGG_BINOMIAL>(double y, double eta, double) {
-    double s = (y > 0.5) ? -eta : eta;
-    s = (s > 30.0) ? kLogitClampEta : ((s < -30.0) ? -kLogitClampEta : s);
-    double t = exp(-fabs(s));
-    double r = log1p(t);
-    return -((s > 0.0 ? s : 0.0) + r);
-}
-
-// mu = pmax(exp(eta), eps); dpois_raw(y, mu) = y log(mu) - mu - lgamma(y + 1).  The lgamma term
-// does not depend on beta and is added once per sum.  exp overflow gives -Inf as in R
-// (!R_FINITE(lambda) -> R_D__0), never NaN.
-template <>
-__device__ __forceinline__ double row_term<CGG_POISSON>(double y, double eta, double) {
+__device__ __forceinline__ double row_term(double y, double eta, double inv_sd, const double2 *tab) {
+    if (FAMILY == CGG_GAUSSIAN) { const double z = (y - eta) * inv_sd; return -0.5 * z * z; }
+    if (FAMILY == CGG_BINOMIAL) {
+        double o0, o1;
+        const double s = (y > 0.5) ? -eta : eta;
+        softplus2(s, s, tab, o0, o1);
+        return -o0;
+    }
     double le = (eta < kLogEps) ? kLogEps : eta;
-    double mu = exp(le);
-    double v = y * le - mu;
-    return (mu > 1.7976931348623157e308) ? -INFINITY : v;
+    const double mu = exp(le);
+    return (mu > 1.7976931348623157e308) ? -INFINITY : fma(y, le, -mu);
+}
+
+// Cooperative copy of the log1p split table into shared memory (call from every thread, then sync).
+__device__ __forceinline__ void load_l1p_table(double2 *dst) {
+    for (int i = threadIdx.x; i <= L1P_N; i += blockDim.x) dst[i] = make_double2(L1P_TAB[2 * i], L1P_TAB[2 * i + 1]);
 }
 
 struct PriorParams {

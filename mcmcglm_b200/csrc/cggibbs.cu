@@ -70,8 +70,10 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
 template <int FAMILY>
 __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __grid_constant__ Dev d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double2 s_l1p[L1P_N + 1];
     CtaShared sh(smem_raw, d.C);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_l1p_table(s_l1p);
     for (int i = threadIdx.x; i < d.C; i += THREADS) { sh.ver[i] = 0ULL; sh.cnt[i] = 0; sh.lock[i] = 0; }
     for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
     __syncthreads();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             t_wait += tB - tA;
             // ---- stream this warp's rows for chain c
             int j = -1;
-            const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, acc, j);
+            const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j);
             if (nc < 0) continue;
             any = true;
             long long tC = prof ? clock64() : 0;
@@ -154,8 +156,10 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared sh(smem_raw, d.C);
     __shared__ int s_flag;
+    __shared__ double2 s_l1p[L1P_N + 1];
     if (d.hdr->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_l1p_table(s_l1p);
     for (int i = threadIdx.x; i < d.C; i += THREADS) sh.cnt[i] = 0;
     for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
     __syncthreads();
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     double acc[KMAX];
     for (int c = 0; c < d.C; ++c) {
         int j;
-        const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, acc, j);
+        const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j);
         if (nc > 0) cta_deliver(d, sh, c, nc, warp, lane, NWARPS, acc);
     }
     __syncthreads();
@@ -257,6 +261,22 @@ __global__ void __launch_bounds__(THREADS) axpy_eta_kernel(Dev d, int c, int64_t
         } else {
             eta[i] = eta_shift(eta[i], xj[i], diff);
         }
+    }
+}
+
+// Diagnostic: the per-row log-density term (without the per-dataset constant) of each (y_i, eta_i).
+__global__ void row_terms_kernel(int family, int64_t n, const double *y, const double *eta, double inv_sd, double *out) {
+    __shared__ double2 s_l1p[L1P_N + 1];
+    load_l1p_table(s_l1p);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        // scored through the same two-row code path as the sweep kernels (the row duplicated, x = 0)
+        const double2 yy = make_double2(y[i], y[i]), ee = make_double2(eta[i], eta[i]), xx = make_double2(0.0, 0.0);
+        double v;
+        if (family == CGG_GAUSSIAN) v = RowPair<CGG_GAUSSIAN>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
+        else if (family == CGG_BINOMIAL) v = RowPair<CGG_BINOMIAL>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
+        else v = RowPair<CGG_POISSON>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
+        out[i] = 0.5 * v;
     }
 }
 
@@ -650,6 +670,24 @@ extern "C" int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, do
     if (beta_host) CK(cudaMemcpyAsync(beta_host, d.beta + (int64_t)chain * d.p, sizeof(double) * d.p, cudaMemcpyDeviceToHost, h->stream));
     if (eta_host) CK(cudaMemcpyAsync(eta_host, d.eta + (int64_t)chain * d.lde, sizeof(double) * d.n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return CGG_OK;
+}
+
+extern "C" int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double *y_host, const double *eta_host,
+                                   double sd, double *out_host) {
+    if (n <= 0 || !y_host || !eta_host || !out_host) return fail(CGG_E_ARG, "cgg_debug_row_terms: bad argument");
+    if (family < CGG_GAUSSIAN || family > CGG_POISSON) return fail(CGG_E_UNSUPPORTED, "cgg_debug_row_terms: unsupported family");
+    CK(cudaSetDevice(device));
+    double *dy = nullptr, *de = nullptr, *dout = nullptr;
+    CK(cudaMalloc((void **)&dy, sizeof(double) * n));
+    CK(cudaMalloc((void **)&de, sizeof(double) * n));
+    CK(cudaMalloc((void **)&dout, sizeof(double) * n));
+    cudaError_t e = cudaMemcpy(dy, y_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(de, eta_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { row_terms_kernel<<<64, 256>>>(family, n, dy, de, 1.0 / sd, dout); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, dout, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(dy); cudaFree(de); cudaFree(dout);
+    CK(e);
     return CGG_OK;
 }
 

@@ -17,6 +17,16 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def debug_row_terms(family, y, eta, sd=1.0, device=0):
+    """Per-row log-density terms exactly as the kernels accumulate them (diagnostic; see cggibbs.h)."""
+    lib = L.load()
+    y, eta = _f64(y).ravel(), _f64(eta).ravel()
+    out = np.empty_like(y)
+    L.check(lib.cgg_debug_row_terms(device, FAMILIES[family][0], y.size, y.ctypes.data_as(_dp), eta.ctypes.data_as(_dp),
+                                    float(sd), out.ctypes.data_as(_dp)))
+    return out
+
+
 class Engine:
     """One device's CGGibbs state: data (X, y) + n_chains chains (beta, eta, slice state, RNG)."""
 

@@ -13,11 +13,13 @@ __global__ void k_dfma(double *out, int iters) {
 }
 template <int FAM>
 __global__ void k_term(double *out, int iters) {
-    double y = (threadIdx.x & 1), eta = 0.001 * threadIdx.x - 0.1, acc = 0.0, x = 1.0 + 1e-3 * blockIdx.x;
-    for (int i = 0; i < iters; ++i) {
-        acc += row_term<FAM>(y, eta_shift(eta, x, 1e-4 * i), 1.0);
-        acc += row_term<FAM>(y, eta_shift(-eta, x, 1e-4 * i), 1.0);
-    }
+    __shared__ double2 tab[L1P_N + 1];
+    load_l1p_table(tab);
+    __syncthreads();
+    const double yv = (threadIdx.x & 1), eta = 0.13 * (threadIdx.x & 31) - 2.0 + 1e-3 * (threadIdx.x >> 5), x = 1.0 + 1e-3 * blockIdx.x;
+    double acc = 0.0;
+    const RowPair<FAM> rp(make_double2(yv, 1.0 - yv), make_double2(eta, -eta), make_double2(x, x));
+    for (int i = 0; i < iters; ++i) acc += rp.term(1e-4 * i, 1.0, tab);   // two row evaluations per call
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 __global__ void k_exp(double *out, int iters) {
@@ -62,6 +64,14 @@ int main() {
     printf(" \"term_binomial_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
     ms = timeit([&] { k_term<CGG_POISSON><<<G, T>>>(out, iters); });
     printf(" \"term_poisson_per_s\": %.4g,\n", thr * iters * 2 / (ms * 1e-3));
+    // the sweep kernel's real occupancy: one 512-thread CTA per SM (4 warps per scheduler)
+    const double thr1 = (double)pr.multiProcessorCount * 512;
+    ms = timeit([&] { k_term<CGG_BINOMIAL><<<pr.multiProcessorCount, 512>>>(out, iters); });
+    printf(" \"term_binomial_per_s_16warps\": %.4g,\n", thr1 * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_term<CGG_POISSON><<<pr.multiProcessorCount, 512>>>(out, iters); });
+    printf(" \"term_poisson_per_s_16warps\": %.4g,\n", thr1 * iters * 2 / (ms * 1e-3));
+    ms = timeit([&] { k_term<CGG_BINOMIAL><<<pr.multiProcessorCount * 2, 512>>>(out, iters); });
+    printf(" \"term_binomial_per_s_32warps\": %.4g,\n", thr1 * 2 * iters * 2 / (ms * 1e-3));
     size_t bytes = 4ull << 30; double2 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
     ms = timeit([&] { k_read<<<pr.multiProcessorCount * 16, T>>>(buf, out, bytes / 16); });
     printf(" \"stream_read_GBps\": %.4g}\n", bytes / (ms * 1e-3) / 1e9);
