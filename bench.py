@@ -313,13 +313,23 @@ def main():
         torch.cuda.synchronize()
         it = a.e2e_iters
 
+        phases = {}
+
         def one_call():
+            t = [time.perf_counter()]
             e = new_engine()
+            t.append(time.perf_counter())
             e.set_data_ptr(Xp.data_ptr(), n, yp.data_ptr(), device=False, keepalive=(Xp, yp))   # H2D inside
+            t.append(time.perf_counter())
             for c in range(C):
                 e.init_chain(c, beta0[c])
+            t.append(time.perf_counter())
             S, _ = e.run(it, want_samples=True)                                                   # D2H inside
+            t.append(time.perf_counter())
             e.close()
+            t.append(time.perf_counter())
+            for k, a, b in zip(("create_ms", "upload_ms", "init_ms", "run_ms", "close_ms"), t[:-1], t[1:]):
+                phases[k] = 1e3 * (b - a)
             return S
 
         one_call()
@@ -337,7 +347,8 @@ def main():
         e2e = {"value": world * a.e2e_steps * it * C * p / el, "unit": "updates/s",
                "h2d_bytes_per_step": 8 * n * p + 8 * n + 8 * C * p, "d2h_bytes_per_step": 8 * C * it * p,
                "step": f"one engine call: upload X,y from pinned host memory, init {C} chains, {it} Gibbs iterations, download samples",
-               "ms_per_step": 1e3 * el / a.e2e_steps, "finite": bool(np.isfinite(S).all())}
+               "ms_per_step": 1e3 * el / a.e2e_steps, "finite": bool(np.isfinite(S).all()),
+               "phases_last_call": {k: round(v, 1) for k, v in phases.items()}}
         Xh, yh = Xp.numpy().T, yp.numpy()
     else:
         Xh = yh = None

@@ -121,6 +121,11 @@ int cgg_set_data_device(cgg_handle *h, const double *X_dev, int64_t ldx, const d
  * (the R shim uses distributional::generate exactly as the reference does). */
 int cgg_init_chain(cgg_handle *h, int32_t chain, const double *beta0_host);
 
+/* Sets a chain's state explicitly: current_beta[p] and current_eta[n] as the caller holds them (the
+ * operator forms of R/glm_utils.R:126,187 take both as arguments; also the resume path).  eta is NOT
+ * recomputed from beta. */
+int cgg_set_state(cgg_handle *h, int32_t chain, const double *beta_host, const double *eta_host);
+
 /* log_potential_from_betaj(new_beta_j, j, current_beta, current_eta, Y, X, family, beta_prior,
  * "update") of R/glm_utils.R:187-218 at K values of new_beta_j, against the chain's current
  * beta/eta.  Parity gate 1. */

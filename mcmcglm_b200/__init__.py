@@ -5,5 +5,10 @@ see DESIGN.md.  Importing the package does not load CUDA; constructing an Engine
 """
 from ._lib import CggError  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .api import (mcmcglm, samples, coef, quantile, log_potential_from_betaj, update_linear_predictor,  # noqa: F401
+                  mcmcglm_across_tuningparams, slice_stepping_out, dist_normal, dist_laplace, dist_student_t,
+                  gaussian, binomial, poisson, check_family, extract_model_data, McmcGlm)
 
-__all__ = ["Engine", "CggError"]
+__all__ = ["Engine", "CggError", "mcmcglm", "samples", "coef", "quantile", "log_potential_from_betaj",
+           "update_linear_predictor", "mcmcglm_across_tuningparams", "slice_stepping_out", "dist_normal",
+           "dist_laplace", "dist_student_t", "gaussian", "binomial", "poisson"]

@@ -17,7 +17,7 @@ MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 
 # every symbol include/cggibbs.h declares
 EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cgg_set_data",
-           "cgg_set_data_device", "cgg_init_chain", "cgg_log_potential", "cgg_update_eta", "cgg_run",
+           "cgg_set_data_device", "cgg_init_chain", "cgg_set_state", "cgg_log_potential", "cgg_update_eta", "cgg_run",
            "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms"]
 
 
@@ -70,6 +70,7 @@ def load():
     L.cgg_set_data.argtypes = [vp, vp, i64, vp]
     L.cgg_set_data_device.argtypes = [vp, vp, i64, vp]
     L.cgg_init_chain.argtypes = [vp, i32, dp]
+    L.cgg_set_state.argtypes = [vp, i32, dp, dp]
     L.cgg_log_potential.argtypes = [vp, i32, i64, i32, dp, dp]
     L.cgg_update_eta.argtypes = [vp, i32, i64, C.c_double]
     L.cgg_run.argtypes = [vp, i64, vp, u64, C.POINTER(u64), vp, C.POINTER(Stats)]

@@ -412,6 +412,13 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
+    {   // keep freed pool memory cached on the device (see cgg_set_data)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     h->num_sms = prop.multiProcessorCount;
     int occ = 0;
     h->smem = CtaShared::bytes(C);
@@ -475,7 +482,10 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     Dev &d = h->d;
     cudaFree(d.eta); cudaFree(d.beta); cudaFree(d.shat); cudaFree(d.acc); cudaFree(d.sync); cudaFree(d.xbuf);
     cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr);
-    cudaFree(h->scratch_dev); cudaFree(h->prof_dev); cudaFree(h->X_owned); cudaFree(h->y_owned);
+    cudaFree(h->scratch_dev); cudaFree(h->prof_dev);
+    if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
+    if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->replay_dev); cudaFree(h->samples_dev);
     if (h->hdr_pinned) cudaFreeHost(h->hdr_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -518,8 +528,10 @@ extern "C" int cgg_set_data(cgg_handle *h, const double *X_host, int64_t ldx, co
     if (ldx < d.n) return fail(CGG_E_ARG, "cgg_set_data: ldx (%lld) < n (%lld)", (long long)ldx, (long long)d.n);
     CK(cudaSetDevice(h->cfg.device));
     const int64_t ldd = (d.n + 31) / 32 * 32;
-    if (!h->X_owned) CK(cudaMalloc((void **)&h->X_owned, sizeof(double) * (size_t)ldd * d.p));
-    if (!h->y_owned) CK(cudaMalloc((void **)&h->y_owned, sizeof(double) * (size_t)ldd));
+    // stream-ordered pool allocation: a later handle on this device reuses the memory instead of paying
+    // cudaFree/cudaMalloc of several GB per mcmcglm() call
+    if (!h->X_owned) CK(cudaMallocAsync((void **)&h->X_owned, sizeof(double) * (size_t)ldd * d.p, h->stream));
+    if (!h->y_owned) CK(cudaMallocAsync((void **)&h->y_owned, sizeof(double) * (size_t)ldd, h->stream));
     CK(cudaMemcpy2DAsync(h->X_owned, sizeof(double) * ldd, X_host, sizeof(double) * ldx, sizeof(double) * d.n, d.p, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->y_owned, y_host, sizeof(double) * d.n, cudaMemcpyHostToDevice, h->stream));
     d.X = h->X_owned; d.y = h->y_owned; d.ldx = ldd;
@@ -554,6 +566,24 @@ extern "C" int cgg_init_chain(cgg_handle *h, int32_t chain, const double *beta0_
     int grid = (int)std::min<int64_t>((d.n / 2 + THREADS - 1) / THREADS + 1, 8 * h->num_sms);
     init_eta_kernel<<<grid, THREADS, 0, h->stream>>>(d, chain);
     CK(cudaGetLastError());
+    ChainState cs;
+    memset(&cs, 0, sizeof cs);
+    cs.phase = PH_START;
+    CK(cudaMemcpyAsync(d.cs + chain, &cs, sizeof cs, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->chain_init[chain] = 1;
+    h->fx_valid[chain] = 0;
+    return CGG_OK;
+}
+
+extern "C" int cgg_set_state(cgg_handle *h, int32_t chain, const double *beta_host, const double *eta_host) {
+    int rc = check_chain(h, chain, "cgg_set_state", false);
+    if (rc) return rc;
+    if (!beta_host || !eta_host) return fail(CGG_E_ARG, "cgg_set_state: NULL argument");
+    Dev &d = h->d;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(d.beta + (int64_t)chain * d.p, beta_host, sizeof(double) * d.p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.eta + (int64_t)chain * d.lde, eta_host, sizeof(double) * d.n, cudaMemcpyHostToDevice, h->stream));
     ChainState cs;
     memset(&cs, 0, sizeof cs);
     cs.phase = PH_START;

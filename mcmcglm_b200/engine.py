@@ -101,6 +101,12 @@ class Engine:
             raise L.CggError(L.E_ARG, f"beta0 has shape {b.shape}, expected {(self.p,)}")
         L.check(self._lib.cgg_init_chain(self._h, chain, b.ctypes.data_as(_dp)))
 
+    def set_state(self, chain, beta, eta):
+        b, e = _f64(beta), _f64(eta)
+        if b.shape != (self.p,) or e.shape != (self.n,):
+            raise L.CggError(L.E_ARG, "set_state: beta must have p entries and eta n entries")
+        L.check(self._lib.cgg_set_state(self._h, chain, b.ctypes.data_as(_dp), e.ctypes.data_as(_dp)))
+
     def log_potential(self, chain, j, cands):
         c = np.atleast_1d(_f64(cands))
         out = np.empty_like(c)
