@@ -176,6 +176,10 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
     double *eta = d.eta + (int64_t)c * d.lde;
     const int64_t n = d.n;
     const uint32_t slot0 = ring + (uint32_t)lane * 16u;
+    // The tile -> worker map is rotated per chain (fixed for the run): n_tiles is rarely a multiple of W, so
+    // some workers own one tile more than others; rotating by c * W / C spreads those extra tiles evenly over
+    // the workers within a round of C chains, which is the granularity at which workers have slack.
+    wid = (wid + (long long)c * (W / d.C)) % W;
     auto issue = [&](long long T, int stage) {
         const int64_t i = T * TILE_ROWS + 2 * lane;
         if (T < d.n_tiles && i + 1 < n) {

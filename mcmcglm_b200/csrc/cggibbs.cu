@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                             if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
                         }
                         if (*sv >= round) break;
-                        __nanosleep(64);
+                        __nanosleep(spins < 8 ? 64 : 256);
                         if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) return;
                     }
                 }
