@@ -157,6 +157,14 @@ int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double 
                         double sd, double *out_host);
 
 int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
+
+/* Built-in exchange for row-sharded handles over NCCL (NVLink / NVSwitch): all-gather of the per-candidate
+ * partial sums followed by a sum in rank order, so every rank sees bit-identical totals.  NCCL is resolved
+ * at run time (dlopen "libnccl.so.2"); rank 0 creates the id with cgg_nccl_unique_id and the host code
+ * distributes the 128 bytes to the other ranks by whatever means it has. */
+#define CGG_NCCL_ID_BYTES 128
+int cgg_nccl_unique_id(char out[CGG_NCCL_ID_BYTES]);
+int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, const char id[CGG_NCCL_ID_BYTES]);
 /* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void *cgg_stream(cgg_handle *h);
 /* Grid used by the sweep kernels: CTAs and threads per CTA (for launch accounting) */

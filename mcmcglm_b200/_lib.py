@@ -18,7 +18,8 @@ MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 # every symbol include/cggibbs.h declares
 EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cgg_set_data",
            "cgg_set_data_device", "cgg_init_chain", "cgg_set_state", "cgg_log_potential", "cgg_update_eta", "cgg_run",
-           "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms"]
+           "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms",
+           "cgg_nccl_unique_id", "cgg_comm_init_nccl"]
 
 
 class Config(C.Structure):
@@ -77,6 +78,8 @@ def load():
     L.cgg_get_state.argtypes = [vp, i32, dp, dp]
     L.cgg_get_fx.argtypes = [vp, i32, dp]
     L.cgg_set_exchange.argtypes = [vp, EXCHANGE_FN, vp]
+    L.cgg_nccl_unique_id.argtypes = [C.c_char_p]
+    L.cgg_comm_init_nccl.argtypes = [vp, i32, i32, C.c_char_p]
     L.cgg_debug_row_terms.argtypes = [i32, i32, i64, dp, dp, C.c_double, dp]
     L.cgg_stream.argtypes = [vp]
     L.cgg_stream.restype = vp

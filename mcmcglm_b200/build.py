@@ -9,7 +9,7 @@ SO = os.path.join(CSRC, "libcggibbs.so")
 SOURCES = ["cggibbs.cu"]
 DEPS = ["cggibbs.cu", "cgg_device.cuh", "cgg_math.cuh", os.path.join("..", "..", "include", "cggibbs.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-ldl"]
 
 
 def _nvcc():

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 #include "cgg_device.cuh"
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved with dlopen at run time
 
 using namespace cgg;
 
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
         if (mode == 0) decide_chain(&d, c, lane, -1, false);
         else {
             const int nc = d.ctl[c].ncand;
-            if (lane < nc) d.xbuf[c * KMAX + lane] = acc_take(d.acc + c * KMAX + lane) + d.ll_const;
+            if (lane < KMAX) d.xbuf[c * KMAX + lane] = (lane < nc) ? acc_take(d.acc + c * KMAX + lane) + d.ll_const : 0.0;
         }
     }
     __syncthreads();
@@ -306,11 +308,42 @@ __global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial,
     }
 }
 
+// Row-sharded exchange tail: totals in rank order => bit-identical on every rank.
+__global__ void rank_sum_kernel(const double *gathered, int world, int count, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = 0.0;
+    for (int r = 0; r < world; ++r) v += gathered[(size_t)r * count + i];
+    out[i] = v;
+}
+
 // ============================================================================================
 // Host side
 // ============================================================================================
 
 static thread_local std::string g_err;
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+    }
+};
+static NcclApi g_nccl;
 
 static int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -345,6 +378,7 @@ struct cgg_handle {
     std::vector<char> chain_init, fx_valid;
     int num_sms = 0, max_grid = 0;
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
+    ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr;
     double local_ll_const = 0.0;
 };
 
@@ -360,6 +394,22 @@ static void *kernel_ptr(int family, int which) {
     case CGG_POISSON * 2 + 0: return (void *)sweep_persistent_kernel<CGG_POISSON>;
     default: return (void *)pass_kernel<CGG_POISSON>;
     }
+}
+
+// Row-sharded mode: turn the local per-candidate sums in d.xbuf into global sums, identical on every rank.
+static int exchange(cgg_handle *h) {
+    Dev &d = h->d;
+    const int count = d.C * KMAX;
+    if (h->comm) {
+        ncclResult_t r = g_nccl.AllGather(d.xbuf, h->gather_dev, (size_t)count, ncclDouble, h->comm, h->stream);
+        if (r != ncclSuccess) return fail(CGG_E_COMM, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+        rank_sum_kernel<<<(count + 127) / 128, 128, 0, h->stream>>>(h->gather_dev, h->world, count, d.xbuf);
+        CK(cudaGetLastError());
+        return CGG_OK;
+    }
+    if (!h->xfn) return fail(CGG_E_STATE, "row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
+    if (h->xfn(h->xuser, d.xbuf, (int64_t)count, (void *)h->stream) != 0) return fail(CGG_E_COMM, "exchange callback failed");
+    return CGG_OK;
 }
 
 static int launch_pass(cgg_handle *h, int mode) {
@@ -486,7 +536,8 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->replay_dev); cudaFree(h->samples_dev);
+    cudaFree(h->replay_dev); cudaFree(h->samples_dev); cudaFree(h->gather_dev);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->hdr_pinned) cudaFreeHost(h->hdr_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -613,9 +664,8 @@ static int eval_chunk(cgg_handle *h, int32_t chain, int64_t j, int K, const doub
     int rc = launch_pass(h, 1);
     if (rc) return rc;
     if (h->d.sharded) {
-        if (!h->xfn) return fail(CGG_E_STATE, "row-sharded handle has no exchange function (cgg_set_exchange)");
-        CK(cudaStreamSynchronize(h->stream));
-        if (h->xfn(h->xuser, d.xbuf, (int64_t)d.C * KMAX, (void *)h->stream) != 0) return fail(CGG_E_COMM, "exchange callback failed");
+        rc = exchange(h);
+        if (rc) return rc;
     }
     finalize_eval_kernel<<<1, 32, 0, h->stream>>>(d, chain, (int)j, K, h->scratch_dev, h->scratch_dev + KMAX, h->scratch_dev + 2 * KMAX);
     CK(cudaGetLastError());
@@ -727,6 +777,32 @@ extern "C" int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user) {
     return CGG_OK;
 }
 
+extern "C" int cgg_nccl_unique_id(char out[CGG_NCCL_ID_BYTES]) {
+    if (!out) return fail(CGG_E_ARG, "cgg_nccl_unique_id: NULL output");
+    if (!g_nccl.load()) return fail(CGG_E_COMM, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+    static_assert(sizeof(ncclUniqueId) == CGG_NCCL_ID_BYTES, "NCCL unique id size");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(CGG_E_COMM, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    memcpy(out, &id, sizeof id);
+    return CGG_OK;
+}
+
+extern "C" int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, const char id_bytes[CGG_NCCL_ID_BYTES]) {
+    if (!h || !id_bytes) return fail(CGG_E_ARG, "cgg_comm_init_nccl: NULL argument");
+    if (!h->d.sharded) return fail(CGG_E_STATE, "cgg_comm_init_nccl: handle was not created with CGG_MODE_ROW_SHARDED");
+    if (world < 1 || rank < 0 || rank >= world) return fail(CGG_E_ARG, "cgg_comm_init_nccl: bad rank/world");
+    if (!g_nccl.load()) return fail(CGG_E_COMM, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+    CK(cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; return fail(CGG_E_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    h->world = world; h->rank = rank;
+    CK(cudaMalloc((void **)&h->gather_dev, sizeof(double) * (size_t)world * h->d.C * KMAX));
+    return CGG_OK;
+}
+
 extern "C" void *cgg_stream(cgg_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 extern "C" int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads) {
@@ -745,7 +821,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     const int C = d.C;
     for (int c = 0; c < C; ++c)
         if (!h->chain_init[c]) return fail(CGG_E_STATE, "cgg_run: chain %d not initialised (cgg_init_chain)", c);
-    if (d.sharded && !h->xfn) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange function");
+    if (d.sharded && !h->xfn && !h->comm) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
     CK(cudaSetDevice(h->cfg.device));
     for (int c = 0; c < C; ++c) {
         int rc = ensure_fx(h, c);
@@ -809,16 +885,17 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G), dim3(THREADS), args, h->smem, h->stream));
         launches = 1;
     } else {
-        const int batch = d.sharded ? 1 : 32;
+        const int batch = (d.sharded && !h->comm) ? 1 : 32;   // host callbacks are synchronous; NCCL and kernels queue up
         for (;;) {
             for (int i = 0; i < batch; ++i) {
                 int rc = launch_pass(h, d.sharded ? 1 : 0);
                 if (rc) return rc;
                 ++launches;
                 if (d.sharded) {
-                    if (h->xfn(h->xuser, d.xbuf, (int64_t)C * KMAX, (void *)h->stream) != 0) return fail(CGG_E_COMM, "cgg_run: exchange callback failed");
+                    rc = exchange(h);
+                    if (rc) return rc;
                     decide_kernel<<<1, THREADS, 0, h->stream>>>(d);
-                    ++launches;
+                    launches += h->comm ? 3 : 1;
                 }
             }
             CK(cudaMemcpyAsync(h->hdr_pinned, d.hdr, sizeof(Hdr), cudaMemcpyDeviceToHost, h->stream));

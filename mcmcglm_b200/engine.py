@@ -159,6 +159,10 @@ class Engine:
     def stream_ptr(self):
         return self._lib.cgg_stream(self._h)
 
+    def comm_init_nccl(self, rank, world, id_bytes):
+        """Row-sharded mode: join the NCCL communicator identified by the 128-byte id (see multigpu.init_nccl)."""
+        L.check(self._lib.cgg_comm_init_nccl(self._h, rank, world, id_bytes))
+
     def set_exchange(self, fn):
         """fn(device_ptr:int, count:int, stream_ptr:int) -> int; kept alive by the engine."""
         def tramp(user, buf, count, stream):
