@@ -38,6 +38,8 @@ WORKLOADS = {
                  desc="poisson-log n=1e6 p=500 student_t(4) w=0.5 K=8, 8 chains/GPU (BASELINE configs[3])"),
     "cfg5shard": dict(family="gaussian", n=6_250_000, p=200, prior="normal", chains=1, w=0.5, K=8, init_scale=1.0,
                       desc="gaussian n=6.25e6 (one of 8 row shards of n=5e7) p=200, 1 chain (BASELINE configs[4], local part)"),
+    "cfg5": dict(family="gaussian", n=50_000_000, p=200, prior="normal", chains=1, w=0.5, K=8, init_scale=1.0, sharded=True,
+                 desc="gaussian n=5e7 p=200 normal(0,1) w=0.5, 1 chain, rows sharded over the GPUs, NCCL exchange per pass (BASELINE configs[4])"),
     "tiny": dict(family="binomial", n=20_000, p=20, prior="laplace", chains=4, w=0.5, K=8, init_scale=1.0,
                  desc="tiny smoke workload"),
 }
@@ -53,8 +55,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int)
-    ap.add_argument("--p", type=int)
+    ap.add_argument("--rows", dest="n", type=int)
+    ap.add_argument("--cols", dest="p", type=int)
     ap.add_argument("--chains", type=int)
     ap.add_argument("--family")
     ap.add_argument("--prior")
@@ -89,19 +91,23 @@ def draw_beta0(wl, rng, C):
     return b * wl["init_scale"]      # reference: init_beta ~ prior (R/mcmcglm.R:208); poisson starts at 0 (exp overflow)
 
 
-def make_data(wl, device, seed):
+def make_data(wl, device, seed, n_rows=None, row_seed=0):
     """Synthetic X (column 0 == 1, rest N(0,1)), beta* ~ N(0, 1/p), y ~ family -- generated on the device.
-    Layout: tensor [p, n] row-major == column-major n x p with ld = n, exactly an R matrix."""
+    Layout: tensor [p, n] row-major == column-major n x p with ld = n, exactly an R matrix.
+    n_rows / row_seed: generate only this rank's row shard (beta* is common to all shards)."""
     import torch
+    g0 = torch.Generator(device=device)
+    g0.manual_seed(seed)
+    p = wl["p"]
+    n = wl["n"] if n_rows is None else n_rows
+    bt = torch.randn(p, dtype=torch.float64, device=device, generator=g0) / (p ** 0.5)
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    n, p = wl["n"], wl["p"]
+    g.manual_seed(seed + 7919 * (row_seed + 1))
     X = torch.empty((p, n), dtype=torch.float64, device=device)
     for j0 in range(0, p, 64):   # chunked: randn in fp64 without a second 8 GB temporary
         j1 = min(p, j0 + 64)
         X[j0:j1].normal_(generator=g)
     X[0].fill_(1.0)
-    bt = torch.randn(p, dtype=torch.float64, device=device, generator=g) / (p ** 0.5)
     eta = torch.mv(X.t(), bt)
     if wl["family"] == "gaussian":
         y = eta + torch.randn(n, dtype=torch.float64, device=device, generator=g)
@@ -214,8 +220,16 @@ def main():
     from mcmcglm_b200 import Engine
 
     n, p, C = wl["n"], wl["p"], wl["chains"]
-    X, y = make_data(wl, dev, a.seed)            # identical data on every rank (replicated, like the reference's workers)
-    rng = np.random.default_rng(a.seed + 1000 * rank)
+    sharded = bool(wl.get("sharded")) and world > 1
+    if sharded:
+        from mcmcglm_b200.multigpu import shard_rows, init_nccl
+        lo, hi = shard_rows(n, world, rank)
+        n_total, n = n, hi - lo
+        X, y = make_data(wl, dev, a.seed, n_rows=n, row_seed=rank)   # this rank's rows only
+    else:
+        n_total = n
+        X, y = make_data(wl, dev, a.seed)        # identical data on every rank (replicated, like the reference's workers)
+    rng = np.random.default_rng(a.seed + (0 if sharded else 1000 * rank))
     beta0 = draw_beta0(wl, rng, C)
     peaks = {}
     try:
@@ -225,9 +239,12 @@ def main():
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
     def new_engine():
-        return Engine(n, p, family=wl["family"], sd=1.0, w=wl["w"], n_chains=C, K=wl["K"], device=local,
-                      driver=a.driver, seed=a.seed, chain_offset=rank * C, spec_tau=a.tau,
-                      rows_per_cta_min=a.rows_per_cta_min, **PRIOR_KW[wl["prior"]])
+        e = Engine(n, p, family=wl["family"], sd=1.0, w=wl["w"], n_chains=C, K=wl["K"], device=local,
+                   driver="stepwise" if sharded else a.driver, seed=a.seed, chain_offset=0 if sharded else rank * C,
+                   spec_tau=a.tau, rows_per_cta_min=a.rows_per_cta_min, row_sharded=sharded, **PRIOR_KW[wl["prior"]])
+        if sharded:
+            init_nccl(e, rank, world)
+        return e
 
     # ---------------------------------------------------------------- reference arm (CPU port)
     if a.impl == "reference":
@@ -299,12 +316,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     updates_per_rank = a.steps * C * p
-    value = world * updates_per_rank / (ms * 1e-3)
+    value = (1 if sharded else world) * updates_per_rank / (ms * 1e-3)     # sharded: one chain set, rows split
     achieved = agg["algorithmic_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9
 
     # ---------------------------------------------------------------- e2e (host buffers through the C ABI)
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and not sharded:
         Xp = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
         yp = torch.empty(n, dtype=torch.float64, pin_memory=True)
         Xp.copy_(X)
@@ -377,15 +394,16 @@ def main():
         pass
     if rank == 0:
         line = {"metric": "coordinate updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["desc"], "n": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
+                "config": {"workload": wl["desc"], "n": n_total, "rows_per_gpu": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
                            "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver,
-                           "parallelism": f"chain-parallel x{world} (no collective)", "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
+                           "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 8} partial sums per pass, rank-ordered sum)" if sharded
+                                           else f"chain-parallel x{world} (no collective)"), "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
                            "beta0": "prior draw x %g" % wl["init_scale"]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(agg["launches"]),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if a.driver == "persistent" else "pass_kernel",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if (a.driver == "persistent" and not sharded) else "pass_kernel",
                              "algorithmic_bytes_per_step": agg["algorithmic_bytes"] / a.steps, "kernel_ms_per_step": agg["sweep_ms"] / a.steps,
                              "grid": [ctas, threads]},
                 "cpu_baseline": cpu,
