@@ -62,9 +62,12 @@ def parse():
     ap.add_argument("--prior")
     ap.add_argument("--w", type=float)
     ap.add_argument("--K", type=int)
-    ap.add_argument("--tau", type=float, default=0.5)
+    ap.add_argument("--tau", type=float, default=0.12)
     ap.add_argument("--driver", default="persistent", choices=["persistent", "stepwise"])
     ap.add_argument("--rows-per-cta-min", type=int, default=0)
+    ap.add_argument("--burnin-iters", type=int, default=30,
+                    help="untimed Gibbs iterations before the warm-up steps, so that the timed steps measure the stationary "
+                         "regime (chains start from a prior draw like the reference, whose own default burnin is 100)")
     ap.add_argument("--e2e-iters", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
@@ -194,8 +197,8 @@ def cpu_port_run(wl, Xh, yh, beta0, eta0, seconds, threads=None, per_thread_upda
     total = cores * per_thread_updates
     evals = sum(r[1] for r in res)
     info = {"cores": cores, "updates": total, "wall_s": wall, "evals_per_update": evals / total,
-            "sample": f"first {per_thread_updates} coordinate updates of iteration 1 on each of {cores} independent "
-                      f"chains (one per host thread), beta0 ~ prior, same X/y as the GPU run"}
+            "sample": f"{per_thread_updates} consecutive coordinate updates on each of {cores} independent "
+                      f"chains (one per host thread), started from the chains' state after the burn-in, same X/y as the GPU run"}
     return total / wall, info
 
 
@@ -252,10 +255,13 @@ def main():
         yh = y.cpu().numpy()
         eng = new_engine()
         eng.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
-        eta0 = []
         for c in range(C):
             eng.init_chain(c, beta0[c])
-            eta0.append(eng.state(c)[1])     # init eta = X beta0 (a GEMV the timed CPU sample does not repeat)
+        if a.burnin_iters > 0:               # untimed state preparation: the CPU sample starts from the same
+            eng.run(a.burnin_iters, want_samples=False)   # stationary regime the GPU arm is timed in
+        st_ = [eng.state(c) for c in range(C)]
+        beta0 = np.stack([b for b, _ in st_])
+        eta0 = [e_ for _, e_ in st_]
         eng.close()
         del X
         cores = os.cpu_count() or 1
@@ -289,6 +295,8 @@ def main():
         eng.init_chain(c, beta0[c])
     ctas, threads = eng.launch_shape()
     ext = torch.cuda.ExternalStream(eng.stream_ptr(), device=dev)
+    if a.burnin_iters > 0:
+        eng.run(a.burnin_iters, want_samples=False)
     for _ in range(max(a.warmup, 0)):
         eng.run(1, want_samples=False)
     torch.cuda.synchronize()
@@ -308,6 +316,7 @@ def main():
     e1.record(ext)
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    stationary = [eng.state(c) for c in range(C)] if (rank == 0 and world == 1 and not a.no_cpu) else None
     if multi:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -375,14 +384,10 @@ def main():
     if not a.no_cpu and rank == 0 and world == 1:
         if Xh is None:
             Xh, yh = X.cpu().numpy().T, y.cpu().numpy()
-        e = new_engine()
-        e.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
-        eta0 = []
-        for c in range(C):
-            e.init_chain(c, beta0[c])
-            eta0.append(e.state(c)[1])
-        e.close()
-        v, info = cpu_port_run(wl, Xh, yh, beta0, eta0, a.cpu_seconds)
+        # the CPU port starts from the same stationary state the GPU steps were timed in
+        beta_s = np.stack([b for b, _ in stationary])
+        eta_s = [e_ for _, e_ in stationary]
+        v, info = cpu_port_run(wl, Xh, yh, beta_s, eta_s, a.cpu_seconds)
         cpu = {"value": v, "unit": "updates/s", "cores": info["cores"], "kind": "port",
                "sample": info["sample"] + f" ({info['wall_s']:.1f} s, {info['evals_per_update']:.2f} evals/update). "
                "CPU restatement of the R algorithm (oracle/oracle.c), not R: R is not installed in this image"}
@@ -400,7 +405,7 @@ def main():
                            "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver,
                            "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 8} partial sums per pass, rank-ordered sum)" if sharded
                                            else f"chain-parallel x{world} (no collective)"), "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
-                           "beta0": "prior draw x %g" % wl["init_scale"]},
+                           "beta0": "prior draw x %g" % wl["init_scale"], "burnin_iterations": a.burnin_iters},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(agg["launches"]),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if (a.driver == "persistent" and not sharded) else "pass_kernel",
@@ -411,7 +416,9 @@ def main():
                                  "chain_passes_per_update": agg["chain_passes"] / max(agg["updates"], 1),
                                  "cand_evals_per_update": agg["cand_evals"] / max(agg["updates"], 1),
                                  "ref_evals_per_update": agg["ref_evals"] / max(agg["updates"], 1),
-                                 "row_evals_per_s": agg["cand_evals"] * n / (agg["sweep_ms"] * 1e-3)}}
+                                 "row_evals_per_s": agg["cand_evals"] * n / (agg["sweep_ms"] * 1e-3),
+                                 "prefiltered_share": agg.get("coarse_evals", 0) / max(agg["cand_evals"], 1),
+                                 "prefilter_undecided_per_update": agg.get("coarse_undecided", 0) / max(agg["updates"], 1)}}
         print(json.dumps(line))
     if multi:
         dist.destroy_process_group()

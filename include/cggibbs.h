@@ -60,6 +60,9 @@ enum {
                                  exchange callback installed with cgg_set_exchange() */
 };
 
+/* cfg.flags */
+#define CGG_FLAG_NO_PREFILTER 1 /* score every candidate in fp64 (the fp32 pre-filter never changes results, only cost) */
+
 typedef struct cgg_config {
     int32_t abi_version; /* must be CGG_ABI_VERSION */
     int32_t device;      /* CUDA device ordinal */
@@ -80,7 +83,7 @@ typedef struct cgg_config {
     uint64_t seed;       /* Philox key */
     double spec_tau;     /* speculate a candidate only if P(needed) >= spec_tau; <= 0 => always fill K */
     int32_t rows_per_cta_min; /* 0 => default */
-    int32_t reserved;
+    int32_t flags;       /* CGG_FLAG_* */
 } cgg_config;
 
 typedef struct cgg_stats {
@@ -95,6 +98,8 @@ typedef struct cgg_stats {
     uint64_t launches;       /* kernels launched by the last cgg_run */
     double sweep_ms;         /* device time of the last cgg_run's sweep kernels (CUDA events) */
     double algorithmic_bytes;/* 8n * (3*chain_passes + 2*commit_passes) of the last cgg_run */
+    uint64_t coarse_evals;   /* candidates scored by the fp32 pre-filter (subset of cand_evals) */
+    uint64_t coarse_undecided; /* passes that ended on a pre-filtered candidate the error bound could not decide */
 } cgg_stats;
 
 typedef struct cgg_handle cgg_handle;
@@ -155,6 +160,10 @@ int cgg_get_fx(cgg_handle *h, int32_t chain, double *fx);
  * beta (gaussian: -log(sqrt(2 pi) sd); poisson: -lgamma(y + 1)).  Used by the accuracy tests. */
 int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double *y_host, const double *eta_host,
                         double sd, double *out_host);
+
+/* Diagnostic: exhaustive scan over every fp32 s with |s| <= 37 of the fp32 pre-filter's softplus against the
+ * fp64 one; returns max |err| / (1 + |s|), the constant its error bound relies on (pre-filter). */
+int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plus_abs_s, double *at_s);
 
 int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
 

@@ -12,6 +12,7 @@
 namespace cgg {
 
 constexpr int KMAX = CGG_KMAX;
+constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate sums + the two error-bound sums of the pre-filter
 constexpr int THREADS = 512;   // one CTA per SM, 16 warp-workers each
 constexpr int NWARPS = THREADS / 32;
 constexpr int CMAX = 32;       // chains per device (shared-memory slots of the CTA-level reduction)
@@ -28,7 +29,7 @@ struct __align__(16) Ctl {
     int32_t j;          // column being sampled; -1: chain finished or failed, skip it for good
     int32_t ncand;      // candidates to score (0..KMAX)
     int32_t commit_j;   // column of a pending eta update to apply first (-1: none)
-    int32_t pad0;
+    int32_t coarse_mask;// bit k: candidate k is scored by the fp32 pre-filter (binomial only)
     double commit_delta;// new_beta_j - current_beta_j of that update (R/glm_utils.R:127)
     double delta[KMAX]; // cand_k - beta_j
     double pad1;
@@ -66,10 +67,12 @@ struct __align__(16) ChainState {
     int32_t sdrawn;     // shrink uniforms already consumed by rejected proposals of this update
     int32_t npass;      // passes spent on this update (non-termination guard)
     int32_t j;
-    int32_t pad[2];
+    int32_t fine_next;  // the previous pass left a pre-filtered candidate undecided: score everything in fp64 next
+    int32_t pad;
     int64_t iter;       // iterations completed in this run
     uint64_t cursor;    // uniforms consumed before this update
     uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
+    uint64_t coarse_evals, coarse_undecided;
 };
 static_assert(sizeof(ChainState) % 16 == 0, "ChainState is copied with 128-bit accesses");
 
@@ -89,9 +92,9 @@ struct Dev {
     int64_t n, p, ldx, lde, n_tiles, n_iter;
     uint64_t n_u, seed;
     int64_t max_steps;
-    double inv_sd, ll_const, w, tau;
+    double inv_sd, ll_const, w, tau, coarse_theta;
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, pad_;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -147,10 +150,11 @@ __device__ __forceinline__ void acc_add(Acc *a, double v) {
 }
 
 // Read-and-clear by the single deciding lane (all adds of this pass are ordered before by the arrive counter).
-__device__ __forceinline__ double acc_take(Acc *a) {
+__device__ __forceinline__ double acc_take(Acc *a, unsigned int *flags_out = nullptr) {
     const unsigned long long lo = __ldcg(&a->lo);
     const long long hi = __ldcg(&a->hi);
     const unsigned int fl = __ldcg(&a->flags);
+    if (flags_out) *flags_out = fl;
     a->lo = 0ULL; a->hi = 0LL; a->flags = 0u;
     if (fl & 2u) return NAN;
     if ((fl & 1u) && (fl & 4u)) return NAN;
@@ -170,7 +174,8 @@ __device__ __forceinline__ double acc_take(Acc *a) {
 template <int FAMILY>
 __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int nc, int cj, double cdelta,
                                                 const double *s_dl, long long wid, long long W, int lane,
-                                                uint32_t ring, const double2 *tab, double *sacc) {
+                                                uint32_t ring, const double2 *tab, double *sacc,
+                                                unsigned cmask, float &bE, float &bX, unsigned &nearmask) {
     const double *xj = d.X + (int64_t)j * d.ldx;
     const double *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
     double *eta = d.eta + (int64_t)c * d.lde;
@@ -209,8 +214,28 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
             }
             if (nc > 0) {
                 const RowPair<FAMILY> rp(lds2(s + 512u), e, lds2(s + 1024u));
+                if (FAMILY == CGG_BINOMIAL && cmask) {
+                    // pre-filter: candidates flagged in cmask are scored in fp32 (hardware ex2/lg2); the sums of
+                    // |eta| and |x| over the rows feed the rigorous error bound the decider applies
+                    const float ef0 = (float)rp.e0, ef1 = (float)rp.e1, xf0 = (float)rp.x0, xf1 = (float)rp.x1;
+                    bE += fabsf(ef0) + fabsf(ef1);
+                    bX += fabsf(xf0) + fabsf(xf1);
 #pragma unroll 1
-                for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
+                    for (int k = 0; k < nc; ++k) {
+                        if ((cmask >> k) & 1u) {
+                            const float df = (float)s_dl[k];
+                            bool near = false;
+                            const float v = softplus32(fmaf(xf0, df, ef0), near) + softplus32(fmaf(xf1, df, ef1), near);
+                            if (near) nearmask |= 1u << k;
+                            sacc[k * 32 + lane] -= (double)v;
+                        } else {
+                            sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
+                }
             }
         }
         stage = (stage + 1) & (RING_D - 1);
@@ -229,27 +254,44 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
 }
 
 // A worker's whole contribution to one pass of chain c: read the control block, stream the rows and
-// return the warp's partial sums (identical in every lane).  Return value: -1 chain finished,
-// otherwise the number of candidates scored (0 when the pass was idle or commit-only); j_out = column.
+// return the warp's partial sums (identical in every lane): acc[0..nc) candidate sums and, when the
+// pre-filter is active, acc[nc], acc[nc+1] = sum |eta|, sum |x| over the warp's rows.  Return value: -1
+// chain finished, otherwise the number of values delivered (0 when the pass was idle or commit-only).
 template <int FAMILY>
 __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw /* the CTA's shared copy of ctl[c] */,
                                            long long wid, long long W, int lane, uint32_t ring, const double2 *tab,
-                                           double *sacc, double (&acc)[KMAX], int &j_out) {
+                                           double *sacc, double (&acc)[NV], int &j_out) {
     const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
     const int j = (int)(w0 & 0xffffffffLL), nc = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
+    const unsigned cmask = (unsigned)(w1 >> 32);
     j_out = j;
     if (j < 0) return -1;
     if (nc == 0 && cj < 0) return 0;
-    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cw[2], cw + 3, wid, W, lane, ring, tab, sacc);
+    float bE = 0.0f, bX = 0.0f;
+    unsigned nearmask = 0;
+    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cw[2], cw + 3, wid, W, lane, ring, tab, sacc, cmask, bE, bX, nearmask);
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = (k < nc) ? warp_sum(sacc[k * 32 + lane]) : 0.0;
-    return nc;
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < nc) acc[k] = warp_sum(sacc[k * 32 + lane]);
+    if (!cmask) return nc;
+    const double sE = warp_sum((double)bE), sX = warp_sum((double)bX);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { if (k == nc) acc[k] = sE; if (k == nc + 1) acc[k] = sX; }
+    nearmask = __reduce_or_sync(0xffffffffu, nearmask);
+    if (nearmask && lane == 0) {   // a row sat on the |eta| = 30 clamp discontinuity: the bound does not hold
+        for (int k = 0; k < nc; ++k)
+            if ((nearmask >> k) & 1u) atomicOr(&d.acc[c * NV + k].flags, 8u);
+        fence_gpu();
+    }
+    return nc + 2;
 }
 
 // Shared memory of a sweep CTA: the warps' staging rings, per-chain slots of the non-blocking CTA-level
 // reduction and the CTA's cached view of the chains' version flags.
 struct CtaShared {                       // views into dynamic shared memory, sized by the chain count
-    double *part;                        // [C][NWARPS][KMAX] warp partial sums of the pass in flight
+    double *part;                        // [C][NWARPS][NV] warp partial sums of the pass in flight
     double *ctl;                         // [C][CTL_WORDS] the control block that goes with ver[c] (one L2 fetch per CTA)
     unsigned long long *ver;             // [C] last version of chain c seen by this CTA
     int *cnt;                            // [C] warps of this CTA that delivered their partials
@@ -260,26 +302,26 @@ struct CtaShared {                       // views into dynamic shared memory, si
         ring0 = (uint32_t)__cvta_generic_to_shared(base);
         sacc = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
         part = sacc + NWARPS * KMAX * 32;
-        ctl = part + (size_t)C * NWARPS * KMAX;
+        ctl = part + (size_t)C * NWARPS * NV;
         ver = reinterpret_cast<unsigned long long *>(ctl + (size_t)C * CTL_WORDS);
         cnt = reinterpret_cast<int *>(ver + C);
         lock = cnt + C;
     }
     static size_t bytes(int C) {
         return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * NWARPS * KMAX * 32 +
-               (size_t)C * (sizeof(double) * (NWARPS * KMAX + CTL_WORDS) + sizeof(unsigned long long) + 2 * sizeof(int));
+               (size_t)C * (sizeof(double) * (NWARPS * NV + CTL_WORDS) + sizeof(unsigned long long) + 2 * sizeof(int));
     }
 };
 
 // Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
 // has folded the CTA's NWARPS partials -- summed in warp order, so the value is reproducible -- into the
 // chain's exact accumulators; the other warps return at once and move on to their next chain.
-__device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers, const double (&acc)[KMAX]) {
+__device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers, const double (&acc)[NV]) {
     int last = 0;
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-            if (k < nc) sh.part[((size_t)c * NWARPS + warp) * KMAX + k] = acc[k];
+        for (int k = 0; k < NV; ++k)
+            if (k < nc) sh.part[((size_t)c * NWARPS + warp) * NV + k] = acc[k];
         __threadfence_block();
         last = (atomicAdd_block(&sh.cnt[c], 1) == nworkers - 1);
     }
@@ -290,8 +332,8 @@ __device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, 
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < NWARPS; ++w)
-            if (w < nworkers) v += sh.part[((size_t)c * NWARPS + w) * KMAX + lane];
-        acc_add(d.acc + c * KMAX + lane, v);
+            if (w < nworkers) v += sh.part[((size_t)c * NWARPS + w) * NV + lane];
+        acc_add(d.acc + c * NV + lane, v);
         fence_gpu();       // fences are per thread: each adding lane orders its atomics before the arrival
     }
     if (lane == 0) sh.cnt[c] = 0;
@@ -324,25 +366,54 @@ __device__ __forceinline__ void build_candidates(const Dev &d, ChainState &s, Ct
     s.nL = s.nR = s.nS = 0;
     double pneed = 1.0;  // P(the next speculative shrink proposal is needed)
     if (s.phase == PH_STEPOUT) {
-        if (s.openL) { s.cand[n++] = s.L; s.nL = 1; }
-        if (s.openR) { s.cand[n++] = s.R; s.nR = 1; }
+        // stepping-out tests: L, L - w, L - 2w, ... are known in advance too; score more than one per side when
+        // expansions have been frequent (each further one is needed only if the previous was inside the slice)
+        const int depth = (s.pexp > 0.6) ? 3 : ((s.pexp > 0.3) ? 2 : 1);
+        if (s.openL) {
+            int m = depth;
+            if (d.max_steps > 0 && (double)m > s.Jb) m = (int)s.Jb;
+            double v = s.L;
+            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nL++; v = __dadd_rn(v, -d.w); }
+        }
+        if (s.openR) {
+            int m = depth;
+            if (d.max_steps > 0 && (double)m > s.Kb) m = (int)s.Kb;
+            double v = s.R;
+            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nR++; v = __dadd_rn(v, d.w); }
+        }
         pneed = 1.0 - s.pexp;
     }
     double l = s.L, r = s.R;
+    const bool prefilter = d.coarse && !s.fine_next && shat > 0.0;
+    const double far = d.coarse_theta * shat;
     for (int i = 0; n < d.K; ++i) {
-        if (d.tau > 0.0 && (i > 0 || s.phase == PH_STEPOUT) && pneed < d.tau) break;
         if (i >= nU) {
             if (i == 0 && s.phase == PH_SHRINK) s.status = CGG_E_STREAM;  // a needed draw is missing
             break;
         }
         const double x = __dadd_rn(l, __dmul_rn(U[i], __dadd_rn(r, -l)));  // L + runif(1) * (R - L)
+        // speculation is a cost decision: a proposal that will go through the fp32 pre-filter costs ~1/5 of an
+        // fp64 one, so it is worth scoring at a much lower probability of being needed
+        const bool cheap = prefilter && fabs(x - s.x0) > far;
+        if (d.tau > 0.0 && (i > 0 || s.phase == PH_STEPOUT) && pneed < (cheap ? 0.2 * d.tau : d.tau)) break;
         s.cand[n++] = x; s.nS++;
-        double pacc = (shat > 0.0) ? shat / (r - l) : 0.0;
-        pacc = pacc < 1.0 ? pacc : 1.0;
+        // P(a proposal from a bracket of this width lands in the slice): shat is the bracket width at acceptance,
+        // about twice the slice width, and even a bracket as tight as the slice is hit with probability < 1
+        double pacc = (shat > 0.0) ? 0.5 * shat / (r - l) : 0.35;   // first sweep: no estimate yet
+        pacc = pacc < 0.85 ? pacc : 0.85;
         pneed *= (1.0 - pacc);
         if (x < s.x0) l = x; else r = x;
     }
     if (s.phase == PH_STEPOUT && n == 0 && s.status == CGG_OK) s.status = CGG_E_STREAM;
+    // pre-filter policy (cannot change results, only cost): a candidate further than coarse_theta slice widths
+    // from x0 is almost surely outside the slice by a wide margin -> score it in fp32 and let the bound decide
+    unsigned cm = 0;
+    if (d.coarse && !s.fine_next && shat > 0.0)
+        for (int k = 0; k < n; ++k)
+            if (fabs(s.cand[k] - s.x0) > d.coarse_theta * shat) cm |= 1u << k;
+    s.fine_next = 0;
+    ct.coarse_mask = (int32_t)cm;
+    s.coarse_evals += __popc(cm);
     ct.j = s.j; ct.ncand = (s.status == CGG_OK) ? n : 0;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) ct.delta[k] = (k < n) ? __dadd_rn(s.cand[k], -s.x0) : 0.0;
@@ -373,7 +444,10 @@ __device__ __forceinline__ void start_coordinate(const Dev &d, ChainState &s, do
 // Lane-0 scalar code: consume the log-potentials F[0..ncand) of the pass that just finished.
 // Returns true when the update was accepted (s.j / s.iter advanced, s.phase = START or FLUSH);
 // x1_out / shat_out then hold the accepted value and the refreshed width estimate of that coordinate.
-__device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState &s, Ctl &ct, const double *F,
+// stop_at: index of the first pre-filtered candidate the error bound could not decide (ncand if none).  The
+// sequence is consumed up to there; the chain then re-scores from that point in fp64 (fine_next).  Candidates
+// the pre-filter did decide carry F = -Inf ("outside the slice").
+__device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState &s, Ctl &ct, const double *F, int stop_at,
                                                 double shat_j, double &x1_out, double &shat_out) {
     s.npass++;
     if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
@@ -383,6 +457,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
     if (s.phase == PH_STEPOUT) {
         // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
         for (int i = 0; i < s.nL && s.openL; ++i) {
+            if (idx + i >= stop_at) { s.fine_next = 1; s.coarse_undecided++; return false; }
             const double f = F[idx + i];
             s.ref_evals++;
             if (f != f) { s.status = CGG_E_NAN; return false; }
@@ -393,6 +468,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
         }
         idx += s.nL;
         for (int i = 0; i < s.nR && s.openR; ++i) {
+            if (idx + i >= stop_at) { s.fine_next = 1; s.coarse_undecided++; return false; }
             const double f = F[idx + i];
             s.ref_evals++;
             if (f != f) { s.status = CGG_E_NAN; return false; }
@@ -409,6 +485,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
     }
     // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }
     for (int i = 0; i < s.nS; ++i) {
+        if (idx + i >= stop_at) { s.sdrawn += i; s.fine_next = 1; s.coarse_undecided++; return false; }
         const double f = F[idx + i], x1 = s.cand[idx + i];
         s.ref_evals++; s.shrinks++;
         if (f != f) { s.status = CGG_E_NAN; return false; }
@@ -456,11 +533,30 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     ChainState s = d.cs[c];
     if (s.phase == PH_FINISHED || s.status != CGG_OK) return true;
     const int nc = ct.ncand;
+    const unsigned cmask = (unsigned)ct.coarse_mask;
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
+    unsigned int aflags = 0;
     if (lane < nc) {
-        const double ll = from_xbuf ? __ldcg(d.xbuf + c * KMAX + lane) : acc_take(d.acc + c * KMAX + lane) + d.ll_const;
+        const double ll = from_xbuf ? __ldcg(d.xbuf + c * KMAX + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
         f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));
+    }
+    int stop_at = nc;
+    if (cmask) {
+        // pre-filtered candidates: |f32 sum - exact| <= B.  The candidate is outside the slice for certain iff
+        // f + B < ylev; anything else (including a row on the clamp discontinuity, or NaN) stays undecided.
+        double bsum = 0.0;
+        if (lane == nc || lane == nc + 1) bsum = acc_take(d.acc + c * NV + lane);
+        const double sE = __shfl_sync(0xffffffffu, bsum, nc), sX = __shfl_sync(0xffffffffu, bsum, nc + 1);
+        bool undecided = false;
+        if (lane < nc && ((cmask >> lane) & 1u)) {
+            const double B = 1.01 * ((2.384185791015625e-07 + (double)kCoarseKappa) * (sE + fabs(s.cand[lane] - s.x0) * sX)
+                                     + (double)kCoarseKappa * (double)d.n);
+            undecided = (aflags & 8u) || !(f + B < s.ylev);
+            if (!undecided) f = -INFINITY;
+        }
+        const unsigned um = __ballot_sync(0xffffffffu, undecided);
+        if (um) stop_at = __ffs(um) - 1;
     }
     double F[KMAX];
 #pragma unroll
@@ -469,7 +565,7 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     double x0 = beta_j, shat = shat_j;     // values of the coordinate that is sampled next
     if (lane == 0 && s.phase != PH_START) {
         double x1 = 0.0, sh1 = 0.0;
-        if (process_results(d, c, s, ct, F, shat_j, x1, sh1)) {
+        if (process_results(d, c, s, ct, F, stop_at, shat_j, x1, sh1)) {
             if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }   // p == 1: same column again
         }
     }

@@ -73,6 +73,24 @@ __device__ __forceinline__ void softplus2(double s0, double s1, const double2 *t
     o1 = ((s1 > 0.0) ? a1 : 0.0) + l1;
 }
 
+// ---- fp32 "coarse" softplus for the pre-filter ------------------------------------------------------
+// softplus32(s) = max(s,0) + log1p(exp(-|s|)) from the hardware approximations ex2.approx / lg2.approx.
+// Its absolute error against the exact value is bounded by kCoarseKappa * (1 + |s|) for every fp32 input
+// (measured exhaustively over all |s| <= 37 by tests/test_gpu_coarse.py, margin >= 2x), NaN propagates.
+// The stats logit clamp (|s| > 30 -> 36.04...) is a discontinuity: a row whose |s| is within 0.02 of 30
+// cannot be bounded, `near` reports it and the candidate is then treated as undecided.
+constexpr float kCoarseKappa = 4.76837158203125e-07f;   // 2^-21
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float softplus32(float s, bool &near) {
+    float a = fabsf(s);
+    near = near || (fabsf(a - 30.0f) < 0.02f);
+    a = (a > 30.0f) ? 36.0436534f : a;
+    const float t = ex2_approx(-a * 1.44269504f);
+    const float l = lg2_approx(1.0f + t) * 0.693147181f;
+    return ((s > 0.0f) ? a : 0.0f) + l;
+}
+
 // The two rows (i, i+1) a lane owns in a tile, with everything that does not depend on the candidate
 // hoisted out of the candidate loop.  term(delta) returns the sum of the two rows' log-density terms up to
 // a per-dataset constant (added once per sum, ll_const):

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     const long long wid = (long long)blockIdx.x * NWARPS + warp - ((int)blockIdx.x < ND ? (int)blockIdx.x : ND);
     const long long W = (long long)d.G * NWARPS - ND;
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
-    double acc[KMAX];
+    double acc[NV];
     long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0;
     const bool prof = d.prof != nullptr;
     for (unsigned long long round = 0;; ++round) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     __syncthreads();
     const long long wid = (long long)blockIdx.x * NWARPS + warp, W = (long long)d.G * NWARPS;
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
-    double acc[KMAX];
+    double acc[NV];
     for (int c = 0; c < d.C; ++c) {
         int j;
         const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
         if (mode == 0) decide_chain(&d, c, lane, -1, false);
         else {
             const int nc = d.ctl[c].ncand;
-            if (lane < KMAX) d.xbuf[c * KMAX + lane] = (lane < nc) ? acc_take(d.acc + c * KMAX + lane) + d.ll_const : 0.0;
+            if (lane < KMAX) d.xbuf[c * KMAX + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + d.ll_const : 0.0;
         }
     }
     __syncthreads();
@@ -279,6 +279,41 @@ __global__ void row_terms_kernel(int family, int64_t n, const double *y, const d
         else if (family == CGG_BINOMIAL) v = RowPair<CGG_BINOMIAL>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
         else v = RowPair<CGG_POISSON>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
         out[i] = 0.5 * v;
+    }
+}
+
+// Diagnostic: max over ALL fp32 s with |s| <= 37 of |softplus32(s) - softplus(s)| / (1 + |s|), the constant the
+// coarse pre-filter's error bound is built on.  out[0] = that maximum, out[1] = the s where it occurs.
+__global__ void coarse_error_scan_kernel(double *out, unsigned long long *out_bits) {
+    __shared__ double2 s_l1p[L1P_N + 1];
+    load_l1p_table(s_l1p);
+    __syncthreads();
+    double worst = 0.0;
+    unsigned int worst_bits = 0;
+    const unsigned int top = __float_as_uint(37.0f);
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= top; b += (unsigned long long)gridDim.x * blockDim.x) {
+        for (int sign = 0; sign < 2; ++sign) {
+            const float s = __uint_as_float((unsigned int)b | (sign ? 0x80000000u : 0u));
+            if (fabsf(fabsf(s) - 30.0f) < 0.02f) continue;           // excluded from the bound by construction
+            bool near = false;
+            const float got = softplus32(s, near);
+            double o0, o1;
+            softplus2((double)s, (double)s, s_l1p, o0, o1);
+            const double e = fabs((double)got - o0) / (1.0 + fabs((double)s));
+            if (e > worst) { worst = e; worst_bits = __float_as_uint(s); }
+        }
+    }
+    // block max
+    __shared__ double s_w[32]; __shared__ unsigned int s_b[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w2 = __shfl_xor_sync(0xffffffffu, worst, o); const unsigned int b2 = __shfl_xor_sync(0xffffffffu, worst_bits, o);
+        if (w2 > worst) { worst = w2; worst_bits = b2; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_w[threadIdx.x >> 5] = worst; s_b[threadIdx.x >> 5] = worst_bits; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) if (s_w[i] > worst) { worst = s_w[i]; worst_bits = s_b[i]; }
+        out[blockIdx.x] = worst; out_bits[blockIdx.x] = worst_bits;
     }
 }
 
@@ -454,6 +489,8 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     d.w = cfg->w; d.max_steps = cfg->max_steps < 0 ? -1 : cfg->max_steps;
     d.seed = cfg->seed; d.chain_offset = cfg->chain_offset; d.tau = cfg->spec_tau;
     d.sharded = cfg->mode == CGG_MODE_ROW_SHARDED;
+    d.coarse = (cfg->family == CGG_BINOMIAL) && !d.sharded && !(cfg->flags & CGG_FLAG_NO_PREFILTER);
+    d.coarse_theta = getenv("CGG_COARSE_THETA") ? atof(getenv("CGG_COARSE_THETA")) : 0.4;
     d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
     d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
     if (cfg->prior == CGG_PRIOR_NORMAL) d.prior.c0 = -(kLnSqrt2Pi + log(cfg->prior_sigma));
@@ -494,7 +531,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&d.eta, sizeof(double) * (size_t)C * d.lde);
     if (e == cudaSuccess) e = A((void **)&d.beta, sizeof(double) * (size_t)C * d.p);
     if (e == cudaSuccess) e = A((void **)&d.shat, sizeof(double) * (size_t)C * d.p);
-    if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * KMAX);
+    if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.sync, sizeof(ChainSync) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * KMAX);
     if (e == cudaSuccess) e = A((void **)&d.ctl, sizeof(Ctl) * (size_t)C);
@@ -514,7 +551,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     cudaMemsetAsync(d.cs, 0, sizeof(ChainState) * (size_t)C, h->stream);
     cudaMemsetAsync(d.ctl, 0, sizeof(Ctl) * (size_t)C, h->stream);
     cudaMemsetAsync(d.hdr, 0, sizeof(Hdr), h->stream);
-    cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * KMAX, h->stream);
+    cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * NV, h->stream);
     cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream);
     std::vector<double> neg((size_t)C * d.p, -1.0);
     cudaMemcpyAsync(d.shat, neg.data(), sizeof(double) * neg.size(), cudaMemcpyHostToDevice, h->stream);
@@ -771,6 +808,26 @@ extern "C" int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, co
     return CGG_OK;
 }
 
+extern "C" int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plus_abs_s, double *at_s) {
+    if (!max_err_over_1_plus_abs_s || !at_s) return fail(CGG_E_ARG, "cgg_debug_coarse_error: NULL output");
+    CK(cudaSetDevice(device));
+    const int G = 1024;
+    double *dv = nullptr; unsigned long long *db = nullptr;
+    CK(cudaMalloc((void **)&dv, sizeof(double) * G));
+    CK(cudaMalloc((void **)&db, sizeof(unsigned long long) * G));
+    coarse_error_scan_kernel<<<G, 256>>>(dv, db);
+    std::vector<double> hv(G); std::vector<unsigned long long> hb(G);
+    cudaError_t e = cudaMemcpy(hv.data(), dv, sizeof(double) * G, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hb.data(), db, sizeof(unsigned long long) * G, cudaMemcpyDeviceToHost);
+    cudaFree(dv); cudaFree(db);
+    CK(e);
+    double w = 0.0; unsigned int bits = 0;
+    for (int i = 0; i < G; ++i) if (hv[i] > w) { w = hv[i]; bits = (unsigned int)hb[i]; }
+    float f; memcpy(&f, &bits, 4);
+    *max_err_over_1_plus_abs_s = w; *at_s = (double)f;
+    return CGG_OK;
+}
+
 extern "C" int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user) {
     if (!h) return fail(CGG_E_ARG, "cgg_set_exchange: NULL handle");
     h->xfn = fn; h->xuser = user;
@@ -859,7 +916,8 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     for (int c = 0; c < C; ++c) {
         cs[c].phase = PH_START; cs[c].status = CGG_OK; cs[c].iter = 0; cs[c].j = 0;
         cs[c].updates = cs[c].chain_passes = cs[c].commit_passes = cs[c].cand_evals = 0;
-        cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = 0;
+        cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = cs[c].coarse_evals = cs[c].coarse_undecided = 0;
+        cs[c].fine_next = 0;
         ctl[c].commit_j = -1;
     }
     Hdr hdr;
@@ -868,7 +926,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemcpyAsync(d.cs, cs.data(), sizeof(ChainState) * C, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d.ctl, ctl.data(), sizeof(Ctl) * C, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d.hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * KMAX, h->stream));
+    CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * NV, h->stream));
     CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
     if (want_prof) {
@@ -908,6 +966,13 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaGetLastError());
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (want_prof) {
+        std::vector<double> sh((size_t)C * d.p), bt((size_t)C * d.p);
+        CK(cudaMemcpy(sh.data(), d.shat, sizeof(double) * sh.size(), cudaMemcpyDeviceToHost));
+        double m = 0; int cnt = 0; double mn = 1e300, mx = 0;
+        for (double v : sh) if (v > 0) { m += v; ++cnt; mn = std::min(mn, v); mx = std::max(mx, v); }
+        fprintf(stderr, "[cgg profile] slice-width estimate shat: mean %.4g min %.4g max %.4g (%d set)\n", cnt ? m / cnt : 0.0, mn, mx, cnt);
+    }
     if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT) {
         unsigned long long pr[8];
         CK(cudaMemcpy(pr, h->prof_dev, 64, cudaMemcpyDeviceToHost));
@@ -925,7 +990,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     for (int c = 0; c < C; ++c) {
         st.updates += cs[c].updates; st.chain_passes += cs[c].chain_passes; st.commit_passes += cs[c].commit_passes;
         st.cand_evals += cs[c].cand_evals; st.ref_evals += cs[c].ref_evals; st.stepouts += cs[c].stepouts; st.shrinks += cs[c].shrinks;
-        st.passes += cs[c].passes;
+        st.passes += cs[c].passes; st.coarse_evals += cs[c].coarse_evals; st.coarse_undecided += cs[c].coarse_undecided;
         if (u_consumed) u_consumed[c] = cs[c].cursor;
         if (cs[c].status != CGG_OK && bad == CGG_OK) { bad = cs[c].status; bad_chain = c; }
     }

@@ -32,7 +32,7 @@ class Engine:
 
     def __init__(self, n, p, family="gaussian", link=None, sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0,
                  prior_df=1.0, w=0.5, max_steps=-1, n_chains=1, K=8, device=0, driver="persistent", seed=0,
-                 chain_offset=0, spec_tau=0.5, rows_per_cta_min=0, row_sharded=False):
+                 chain_offset=0, spec_tau=0.12, rows_per_cta_min=0, row_sharded=False, prefilter=True):
         self._h = None
         self._lib = L.load()
         if family not in FAMILIES:
@@ -52,7 +52,8 @@ class Engine:
                        prior=PRIORS[prior], n_chains=n_chains, prior_mu=prior_mu, prior_sigma=prior_sigma,
                        prior_df=prior_df, w=w, max_steps=int(max_steps), K=K, driver=DRIVERS[driver],
                        mode=L.MODE_ROW_SHARDED if row_sharded else L.MODE_CHAINS, chain_offset=chain_offset,
-                       seed=seed, spec_tau=spec_tau, rows_per_cta_min=rows_per_cta_min, reserved=0)
+                       seed=seed, spec_tau=spec_tau, rows_per_cta_min=rows_per_cta_min,
+                       flags=0 if prefilter else L.FLAG_NO_PREFILTER)
         h = C.c_void_p()
         L.check(self._lib.cgg_create(C.byref(cfg), C.byref(h)))
         self._h = h
