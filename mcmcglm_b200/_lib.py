@@ -59,10 +59,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
-        raise ImportError(f"{SO_PATH} not found: build it with `python -m mcmcglm_b200.build` "
+    path = os.environ.get("CGG_LIB", SO_PATH)      # experiments only: an alternative build of the same ABI
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -m mcmcglm_b200.build` "
                           "(nvcc, sm_100a). There is no CPU fallback.")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(path)
     vp, dp, i32, i64, u64 = C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_int64, C.c_uint64
     L.cgg_last_error.restype = C.c_char_p
     L.cgg_last_error.argtypes = []

@@ -29,7 +29,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("CGG_NVCC_EXTRA", "").split()      # experiments: e.g. -DCGG_THREADS=640
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

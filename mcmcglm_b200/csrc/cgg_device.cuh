@@ -13,11 +13,17 @@ namespace cgg {
 
 constexpr int KMAX = CGG_KMAX;
 constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate sums + the two error-bound sums of the pre-filter
-constexpr int THREADS = 512;   // one CTA per SM, 16 warp-workers each
+#ifndef CGG_THREADS
+#define CGG_THREADS 512
+#endif
+#ifndef CGG_RING_D
+#define CGG_RING_D 4
+#endif
+constexpr int THREADS = CGG_THREADS;   // one CTA per SM, THREADS/32 warp-workers each
 constexpr int NWARPS = THREADS / 32;
 constexpr int CMAX = 32;       // chains per device (shared-memory slots of the CTA-level reduction)
 constexpr int NU = 12;         // uniforms fetched per decision: 3 start draws + KMAX proposals (+1 spare)
-constexpr int RING_D = 4;      // tiles in flight per warp (cp.async ring depth)
+constexpr int RING_D = CGG_RING_D;  // tiles in flight per warp (cp.async ring depth)
 constexpr int RING_OPS = 4;    // eta, y, X_j, X_commit
 constexpr int TILE_ROWS = 64;  // 32 lanes x one 128-bit transfer per operand
 constexpr int RING_BYTES_PER_WARP = RING_D * RING_OPS * 32 * 16;
@@ -164,47 +170,67 @@ __device__ __forceinline__ double acc_take(Acc *a, unsigned int *flags_out = nul
 }
 
 // ---------------------------------------------------------------------------------------------
-// One warp, one chain, one pass over the warp's tiles T = wid, wid + W, ... (64 rows each, one 128-bit
-// transfer per lane per operand).  Algorithmic traffic: 8 B/row each of y, eta, X_j; a pending commit
+// Streaming of one chain's operands by one warp.  The warp owns tiles T = vw, vw + W, ... (64 rows each, one
+// 128-bit transfer per lane per operand).  Algorithmic traffic: 8 B/row each of y, eta, X_j; a pending commit
 // adds X_commit (read) and eta (write).  Operand tiles are staged global -> shared with cp.async into a
-// RING_D-deep per-warp ring, so RING_D - 1 tiles are in flight while one is being scored; every lane
-// reads back only the 16-byte slots it copied itself, so no barrier of any kind is needed.
-// The candidate loop is a run-time loop (trip count nc is warp-uniform) with the per-lane running sums in
-// shared memory: sacc[k * 32 + lane].  s_dl[k] = cand_k - beta_j comes from the CTA's shared control block.
-template <int FAMILY>
-__device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int nc, int cj, double cdelta,
-                                                const double *s_dl, long long wid, long long W, int lane,
-                                                uint32_t ring, const double2 *tab, double *sacc,
-                                                unsigned cmask, float &bE, float &bX, unsigned &nearmask) {
-    const double *xj = d.X + (int64_t)j * d.ldx;
-    const double *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
-    double *eta = d.eta + (int64_t)c * d.lde;
-    const int64_t n = d.n;
-    const uint32_t slot0 = ring + (uint32_t)lane * 16u;
-    // The tile -> worker map is rotated per chain (fixed for the run): n_tiles is rarely a multiple of W, so
-    // some workers own one tile more than others; rotating by c * W / C spreads those extra tiles evenly over
-    // the workers within a round of C chains, which is the granularity at which workers have slack.
-    wid = (wid + (long long)c * (W / d.C)) % W;
-    auto issue = [&](long long T, int stage) {
+// RING_D-deep per-warp ring, so RING_D - 1 tiles are in flight while one is being scored; every lane reads
+// back only the 16-byte slots it copied itself, so no barrier of any kind is needed.
+struct ChainStream {
+    const double *xj, *xc, *y;
+    double *eta;
+    long long vw, W, n_tiles;
+    int64_t n;
+    int nc, cj;
+    uint32_t slot0;
+    // The tile -> worker map is rotated per chain (fixed for the run): n_tiles is rarely a multiple of W, so some
+    // workers own one tile more than others; rotating by c * W / C spreads those extra tiles evenly over the
+    // workers within a round of C chains, which is the granularity at which workers have slack.
+    __device__ __forceinline__ ChainStream(const Dev &d, int c, const double *cw, long long wid, long long W_, int lane, uint32_t ring) {
+        const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
+        const int j = (int)(w0 & 0xffffffffLL);
+        nc = (int)(w0 >> 32); cj = (int)(w1 & 0xffffffffLL);
+        xj = d.X + (int64_t)(j < 0 ? 0 : j) * d.ldx;
+        xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
+        y = d.y; eta = d.eta + (int64_t)c * d.lde;
+        W = W_; vw = (wid + (long long)c * (W / d.C)) % W; n_tiles = d.n_tiles; n = d.n;
+        slot0 = ring + (uint32_t)lane * 16u;
+    }
+    __device__ __forceinline__ void issue(long long T, int stage, int lane) const {
         const int64_t i = T * TILE_ROWS + 2 * lane;
-        if (T < d.n_tiles && i + 1 < n) {
+        if (T < n_tiles && i + 1 < n) {
             const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
             cp_async16(s, eta + i);
-            if (nc > 0) { cp_async16(s + 512u, d.y + i); cp_async16(s + 1024u, xj + i); }
+            if (nc > 0) { cp_async16(s + 512u, y + i); cp_async16(s + 1024u, xj + i); }
             if (cj >= 0) cp_async16(s + 1536u, xc + i);
         }
         cp_async_commit();
-    };
+    }
+    // first RING_D - 1 tiles; may be issued early, while the previous chain is still being reduced
+    __device__ __forceinline__ void prologue(int lane) const {
 #pragma unroll
-    for (int s = 0; s < RING_D - 1; ++s) issue(wid + s * W, s);
+        for (int s = 0; s < RING_D - 1; ++s) issue(vw + s * W, s, lane);
+    }
+};
+
+// One warp, one chain, one pass.  The candidate loop is a run-time loop (trip count nc is warp-uniform) with
+// the per-lane running sums in shared memory: sacc[k * 32 + lane].  s_dl[k] = cand_k - beta_j comes from the
+// CTA's shared control block.  `prefetched`: the prologue of this chain was already issued.
+template <int FAMILY>
+__device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream &cs, double cdelta, const double *s_dl,
+                                                int lane, const double2 *tab, double *sacc, bool prefetched,
+                                                unsigned cmask, float &bE, float &bX, unsigned &nearmask) {
+    const int nc = cs.nc, cj = cs.cj;
+    const int64_t n = cs.n;
+    double *eta = cs.eta;
+    if (!prefetched) cs.prologue(lane);
     for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] = 0.0;
     int stage = 0;
-    for (long long T = wid; T < d.n_tiles; T += W) {
-        issue(T + (RING_D - 1) * W, (stage + RING_D - 1) & (RING_D - 1));
+    for (long long T = cs.vw; T < cs.n_tiles; T += cs.W) {
+        cs.issue(T + (RING_D - 1) * cs.W, (stage + RING_D - 1) % RING_D, lane);
         cp_async_wait<RING_D - 1>();
         const int64_t i = T * TILE_ROWS + 2 * lane;
         if (i + 1 < n) {
-            const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
+            const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
             double2 e = lds2(s);
             if (cj >= 0) {
                 const double2 cv = lds2(s + 1536u);
@@ -214,40 +240,53 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
             }
             if (nc > 0) {
                 const RowPair<FAMILY> rp(lds2(s + 512u), e, lds2(s + 1024u));
+                // Two candidates per iteration: a warp is bound by the latency of one candidate's dependency chain,
+                // so two independent candidates (x two rows) in flight nearly halve the time per candidate.
+                const unsigned all = (nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u);
+                unsigned fine = all & ~cmask;
                 if (FAMILY == CGG_BINOMIAL && cmask) {
                     // pre-filter: candidates flagged in cmask are scored in fp32 (hardware ex2/lg2); the sums of
                     // |eta| and |x| over the rows feed the rigorous error bound the decider applies
                     const float ef0 = (float)rp.e0, ef1 = (float)rp.e1, xf0 = (float)rp.x0, xf1 = (float)rp.x1;
                     bE += fabsf(ef0) + fabsf(ef1);
                     bX += fabsf(xf0) + fabsf(xf1);
-#pragma unroll 1
-                    for (int k = 0; k < nc; ++k) {
-                        if ((cmask >> k) & 1u) {
-                            const float df = (float)s_dl[k];
-                            bool near = false;
-                            const float v = softplus32(fmaf(xf0, df, ef0), near) + softplus32(fmaf(xf1, df, ef1), near);
-                            if (near) nearmask |= 1u << k;
-                            sacc[k * 32 + lane] -= (double)v;
-                        } else {
-                            sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
-                        }
+                    unsigned cm = cmask & all;
+                    while (cm) {
+                        const int k0 = __ffs(cm) - 1; cm &= cm - 1;
+                        const int k1 = cm ? __ffs(cm) - 1 : k0;
+                        if (cm) cm &= cm - 1;
+                        const float d0 = (float)s_dl[k0], d1 = (float)s_dl[k1];
+                        bool n0 = false, n1 = false;
+                        const float v0 = softplus32(fmaf(xf0, d0, ef0), n0) + softplus32(fmaf(xf1, d0, ef1), n0);
+                        const float v1 = softplus32(fmaf(xf0, d1, ef0), n1) + softplus32(fmaf(xf1, d1, ef1), n1);
+                        if (n0) nearmask |= 1u << k0;
+                        sacc[k0 * 32 + lane] -= (double)v0;
+                        if (k1 != k0) { if (n1) nearmask |= 1u << k1; sacc[k1 * 32 + lane] -= (double)v1; }
                     }
-                } else {
-#pragma unroll 1
-                    for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += rp.term(s_dl[k], d.inv_sd, tab);
+                }
+                while (fine) {
+                    const int k0 = __ffs(fine) - 1; fine &= fine - 1;
+                    if (fine) {
+                        const int k1 = __ffs(fine) - 1; fine &= fine - 1;
+                        const double t0 = rp.term(s_dl[k0], d.inv_sd, tab), t1 = rp.term(s_dl[k1], d.inv_sd, tab);
+                        sacc[k0 * 32 + lane] += t0;
+                        sacc[k1 * 32 + lane] += t1;
+                    } else {
+                        sacc[k0 * 32 + lane] += rp.term(s_dl[k0], d.inv_sd, tab);
+                    }
                 }
             }
         }
-        stage = (stage + 1) & (RING_D - 1);
+        stage = (stage + 1 == RING_D) ? 0 : stage + 1;
     }
     cp_async_wait<0>();
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
         const int64_t t = n - 1;
         const long long Tl = t / TILE_ROWS;
-        if (Tl % W == wid && lane == (int)((t % TILE_ROWS) >> 1)) {
+        if (Tl % cs.W == cs.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
             double e = __ldcg(eta + t);
-            if (cj >= 0) { e = eta_shift(e, __ldg(xc + t), cdelta); eta[t] = e; }
-            const double yy = __ldg(d.y + t), xx = __ldg(xj + t);
+            if (cj >= 0) { e = eta_shift(e, __ldg(cs.xc + t), cdelta); eta[t] = e; }
+            const double yy = __ldg(cs.y + t), xx = __ldg(cs.xj + t);
             for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += row_term<FAMILY>(yy, eta_shift(e, xx, s_dl[k]), d.inv_sd, tab);
         }
     }
@@ -257,19 +296,36 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, int c, int j, int 
 // return the warp's partial sums (identical in every lane): acc[0..nc) candidate sums and, when the
 // pre-filter is active, acc[nc], acc[nc+1] = sum |eta|, sum |x| over the warp's rows.  Return value: -1
 // chain finished, otherwise the number of values delivered (0 when the pass was idle or commit-only).
+// next_cw: the control block of the chain this warp will stream next if its decision is already published
+// (else nullptr); its first ring stages are then issued as soon as this chain's tiles are consumed, so the
+// loads are in flight during the reduction and delivery below.  `prefetched` is updated accordingly.
 template <int FAMILY>
 __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw /* the CTA's shared copy of ctl[c] */,
                                            long long wid, long long W, int lane, uint32_t ring, const double2 *tab,
-                                           double *sacc, double (&acc)[NV], int &j_out) {
+                                           double *sacc, double (&acc)[NV], int &j_out, bool &prefetched,
+                                           int next_c, const double *next_cw, long long *t_tiles = nullptr) {
     const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
     const int j = (int)(w0 & 0xffffffffLL), nc = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
     const unsigned cmask = (unsigned)(w1 >> 32);
     j_out = j;
+    const bool was_prefetched = prefetched;
+    prefetched = false;
     if (j < 0) return -1;
     if (nc == 0 && cj < 0) return 0;
     float bE = 0.0f, bX = 0.0f;
     unsigned nearmask = 0;
-    warp_pass_chain<FAMILY>(d, c, j, nc, cj, cw[2], cw + 3, wid, W, lane, ring, tab, sacc, cmask, bE, bX, nearmask);
+    {
+        const long long t0 = t_tiles ? clock64() : 0;
+        const ChainStream cs(d, c, cw, wid, W, lane, ring);
+        warp_pass_chain<FAMILY>(d, cs, cw[2], cw + 3, lane, tab, sacc, was_prefetched, cmask, bE, bX, nearmask);
+        if (t_tiles) *t_tiles += clock64() - t0;
+    }
+    if (next_cw) {
+        const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
+        const long long nw0 = __double_as_longlong(next_cw[0]);
+        const int nj = (int)(nw0 & 0xffffffffLL);
+        if (nj >= 0 && (ns.nc > 0 || ns.cj >= 0)) { ns.prologue(lane); prefetched = true; }
+    }
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
 #pragma unroll

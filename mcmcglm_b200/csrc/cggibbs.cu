@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     const long long W = (long long)d.G * NWARPS - ND;
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
     double acc[NV];
-    long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0;
+    bool prefetched = false;
+    long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0;
     const bool prof = d.prof != nullptr;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
@@ -127,11 +128,38 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             }
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
-            // ---- stream this warp's rows for chain c
+            // ---- stream this warp's rows for chain c; if the next chain's decision is already published, its
+            // first tiles are requested as soon as this chain's tiles are consumed (cross-chain prefetch)
             int j = -1;
-            const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j);
+            const int nxt = (c + 1 == d.C) ? 0 : c + 1;
+            const unsigned long long nround = (c + 1 == d.C) ? round + 1 : round;
+            if (d.C > 1 && *(volatile unsigned long long *)&sh.ver[nxt] < nround) {
+                // one non-blocking look at the next chain's flag (same election as the wait loop above)
+                int got = 0;
+                if (lane == 0) got = (atomicCAS_block(&sh.lock[nxt], 0, 1) == 0);
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got) {
+                    unsigned long long v = 0;
+                    if (lane == 0) v = ld_acquire_u64(&d.sync[nxt].version);
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (v >= nround && v > *(volatile unsigned long long *)&sh.ver[nxt]) {
+                        if (lane < CTL_WORDS) sh.ctl[nxt * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + nxt) + lane);
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); *(volatile unsigned long long *)&sh.ver[nxt] = v; }
+                    }
+                    if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[nxt], 0); }
+                    __syncwarp();
+                }
+            }
+            const bool nready = (d.C > 1) && (*(volatile unsigned long long *)&sh.ver[nxt] >= nround) &&
+                                (*(volatile unsigned long long *)&sh.ver[nxt] < VERSION_FINISHED);
+            // the shared control block of `nxt` belongs to version sh.ver[nxt]: usable only if that is exactly the pass we will run
+            const bool nexact = nready && (*(volatile unsigned long long *)&sh.ver[nxt] == nround);
+            const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
+                                               acc, j, prefetched, nxt, nexact ? sh.ctl + nxt * CTL_WORDS : nullptr, prof ? &t_tiles : nullptr);
             if (nc < 0) continue;
             any = true;
+            n_pref += prefetched ? 1 : 0;
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
@@ -146,6 +174,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     if (prof && lane == 0) {
         atomicAdd(d.prof + 0, (unsigned long long)t_wait); atomicAdd(d.prof + 1, (unsigned long long)t_rows);
         atomicAdd(d.prof + 2, (unsigned long long)t_arrive); atomicAdd(d.prof + 5, (unsigned long long)n_slow);
+        atomicAdd(d.prof + 3, (unsigned long long)t_tiles); atomicAdd(d.prof + 4, (unsigned long long)n_pref);
         atomicAdd(d.prof + 6, 1ULL);
     }
 }
@@ -170,7 +199,9 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     double acc[NV];
     for (int c = 0; c < d.C; ++c) {
         int j;
-        const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j);
+        bool prefetched = false;
+        const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
+                                           acc, j, prefetched, 0, nullptr);
         if (nc > 0) cta_deliver(d, sh, c, nc, warp, lane, NWARPS, acc);
     }
     __syncthreads();
@@ -977,8 +1008,8 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         unsigned long long pr[8];
         CK(cudaMemcpy(pr, h->prof_dev, 64, cudaMemcpyDeviceToHost));
         const double nw = pr[6] ? (double)pr[6] : 1.0;
-        fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g arrive %.3g | slow-waits/worker %.1f workers %llu\n",
-                ms, pr[0] / nw, pr[1] / nw, pr[2] / nw, pr[5] / nw, pr[6]);
+        fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-passes/worker %.1f workers %llu\n",
+                ms, pr[0] / nw, pr[1] / nw, pr[3] / nw, pr[2] / nw, pr[5] / nw, pr[4] / nw, pr[6]);
     }
 
     CK(cudaMemcpy(&hdr, d.hdr, sizeof hdr, cudaMemcpyDeviceToHost));
