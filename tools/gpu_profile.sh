@@ -1,5 +1,5 @@
 # Profiling recipe of this repo (run under gpurun).  1) launch list + DRAM traffic of the bench command,
-# 2) full-set capture of the sweep kernel on a shorter variant (p=100) for stall reasons / source view.
+# 2) full-set capture of the sweep kernel in the stationary regime on a shorter variant (p=100).
 mkdir -p gpurun_out
 unset CGG_PROFILE
 CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu"
@@ -7,10 +7,10 @@ $CMD > gpurun_out/plain_cfg3.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_cfg3.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 tail -1 gpurun_out/plain_cfg3.log | cut -c1-200
-CMD2="python bench.py --workload cfg3 --cols 100 --steps 1 --warmup 1 --no-e2e --no-cpu"
+CMD2="python bench.py --workload cfg3 --cols 100 --steps 1 --warmup 1 --burnin-iters 30 --no-e2e --no-cpu"
 $CMD2 > gpurun_out/plain_p100.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_persistent -s 1 -c 1 -f -o gpurun_out/prof_binom_c8 $CMD2 > gpurun_out/ncu_full.log 2>&1
-CMD3="python bench.py --workload cfg3 --cols 100 --family gaussian --steps 1 --warmup 1 --no-e2e --no-cpu"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_persistent -s 2 -c 1 -f -o gpurun_out/prof_binom_stationary $CMD2 > gpurun_out/ncu_full.log 2>&1
+CMD3="python bench.py --workload cfg3 --cols 100 --family gaussian --steps 1 --warmup 1 --burnin-iters 30 --no-e2e --no-cpu"
 $CMD3 > gpurun_out/plain_g100.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_persistent -s 1 -c 1 -f -o gpurun_out/prof_gauss_c8 $CMD3 > gpurun_out/ncu_full_g.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_persistent -s 2 -c 1 -f -o gpurun_out/prof_gauss_stationary $CMD3 > gpurun_out/ncu_full_g.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches_cfg3.csv
