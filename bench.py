@@ -70,6 +70,7 @@ def parse():
                          "regime (chains start from a prior draw like the reference, whose own default burnin is 100)")
     ap.add_argument("--e2e-iters", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-jet", action="store_true", help="decide every candidate from exact passes (no jet passes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -244,7 +245,8 @@ def main():
     def new_engine():
         e = Engine(n, p, family=wl["family"], sd=1.0, w=wl["w"], n_chains=C, K=wl["K"], device=local,
                    driver="stepwise" if sharded else a.driver, seed=a.seed, chain_offset=0 if sharded else rank * C,
-                   spec_tau=a.tau, rows_per_cta_min=a.rows_per_cta_min, row_sharded=sharded, **PRIOR_KW[wl["prior"]])
+                   spec_tau=a.tau, rows_per_cta_min=a.rows_per_cta_min, row_sharded=sharded, jet=not a.no_jet,
+                   **PRIOR_KW[wl["prior"]])
         if sharded:
             init_nccl(e, rank, world)
         return e
@@ -402,7 +404,7 @@ def main():
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "n": n_total, "rows_per_gpu": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
-                           "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver,
+                           "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver, "jet_passes": not a.no_jet,
                            "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 8} partial sums per pass, rank-ordered sum)" if sharded
                                            else f"chain-parallel x{world} (no collective)"), "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
                            "beta0": "prior draw x %g" % wl["init_scale"], "burnin_iterations": a.burnin_iters},
@@ -418,7 +420,9 @@ def main():
                                  "ref_evals_per_update": agg["ref_evals"] / max(agg["updates"], 1),
                                  "row_evals_per_s": agg["cand_evals"] * n / (agg["sweep_ms"] * 1e-3),
                                  "prefiltered_share": agg.get("coarse_evals", 0) / max(agg["cand_evals"], 1),
-                                 "prefilter_undecided_per_update": agg.get("coarse_undecided", 0) / max(agg["updates"], 1)}}
+                                 "prefilter_undecided_per_update": agg.get("coarse_undecided", 0) / max(agg["updates"], 1),
+                                 "jet_passes_per_update": agg.get("jet_passes", 0) / max(agg["updates"], 1),
+                                 "jet_fallbacks_per_update": agg.get("jet_fallbacks", 0) / max(agg["updates"], 1)}}
         print(json.dumps(line))
     if multi:
         dist.destroy_process_group()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CGG_ABI_VERSION 1
+#define CGG_ABI_VERSION 2
 #define CGG_KMAX 8 /* most candidates one chain can score in one pass over its rows */
 
 typedef enum cgg_status {
@@ -62,6 +62,8 @@ enum {
 
 /* cfg.flags */
 #define CGG_FLAG_NO_PREFILTER 1 /* score every candidate in fp64 (the fp32 pre-filter never changes results, only cost) */
+#define CGG_FLAG_NO_JET 2       /* decide every candidate from an exact pass over the rows (jet passes never change
+                                   results, only cost: one pass per update instead of one per few candidates) */
 
 typedef struct cgg_config {
     int32_t abi_version; /* must be CGG_ABI_VERSION */
@@ -84,6 +86,8 @@ typedef struct cgg_config {
     double spec_tau;     /* speculate a candidate only if P(needed) >= spec_tau; <= 0 => always fill K */
     int32_t rows_per_cta_min; /* 0 => default */
     int32_t flags;       /* CGG_FLAG_* */
+    double jet_bound_scale; /* test knob: multiplies the jet enclosure's error bound (<= 0 => 1); any value >= 1 gives
+                               the same chain, large values force the exact-pass fallback */
 } cgg_config;
 
 typedef struct cgg_stats {
@@ -100,6 +104,8 @@ typedef struct cgg_stats {
     double algorithmic_bytes;/* 8n * (3*chain_passes + 2*commit_passes) of the last cgg_run */
     uint64_t coarse_evals;   /* candidates scored by the fp32 pre-filter (subset of cand_evals) */
     uint64_t coarse_undecided; /* passes that ended on a pre-filtered candidate the error bound could not decide */
+    uint64_t jet_passes;     /* (chain, pass) pairs that were jet passes (subset of chain_passes) */
+    uint64_t jet_fallbacks;  /* updates a jet pass could not finish: exact passes took over from that point */
 } cgg_stats;
 
 typedef struct cgg_handle cgg_handle;
@@ -164,6 +170,13 @@ int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double 
 /* Diagnostic: exhaustive scan over every fp32 s with |s| <= 37 of the fp32 pre-filter's softplus against the
  * fp64 one; returns max |err| / (1 + |s|), the constant its error bound relies on (pre-filter). */
 int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plus_abs_s, double *at_s);
+
+/* Diagnostic: runs one jet pass of chain `chain` along column j (no state change) and evaluates its enclosure at K
+ * (<= CGG_KMAX) values of new_beta_j: value[k] = surrogate log-LIKELIHOOD (per-dataset constant included, prior
+ * excluded), bound[k] = the error bound the decider uses (Inf: enclosure not applicable), sums[CGG_KMAX + 2] = the
+ * pass's raw sums (nullable).  Used by the tests that check the bound against exact evaluations. */
+int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host, double *value_host,
+                  double *bound_host, double *sums_host);
 
 int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
 

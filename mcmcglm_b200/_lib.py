@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libcggibbs.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KMAX = 8
 OK, E_ARG, E_UNSUPPORTED, E_CUDA, E_NAN, E_STREAM, E_NOTERM, E_STATE, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 GAUSSIAN, BINOMIAL, POISSON = 0, 1, 2
@@ -15,12 +15,14 @@ PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2
 DRIVER_PERSISTENT, DRIVER_STEPWISE = 0, 1
 MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 FLAG_NO_PREFILTER = 1
+FLAG_NO_JET = 2
+JET_NV = KMAX + 2
 
 # every symbol include/cggibbs.h declares
 EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cgg_set_data",
            "cgg_set_data_device", "cgg_init_chain", "cgg_set_state", "cgg_log_potential", "cgg_update_eta", "cgg_run",
            "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms",
-           "cgg_nccl_unique_id", "cgg_comm_init_nccl", "cgg_debug_coarse_error"]
+           "cgg_nccl_unique_id", "cgg_comm_init_nccl", "cgg_debug_coarse_error", "cgg_debug_jet"]
 
 
 class Config(C.Structure):
@@ -29,7 +31,8 @@ class Config(C.Structure):
                 ("n_chains", C.c_int32), ("prior_mu", C.c_double), ("prior_sigma", C.c_double),
                 ("prior_df", C.c_double), ("w", C.c_double), ("max_steps", C.c_int64), ("K", C.c_int32),
                 ("driver", C.c_int32), ("mode", C.c_int32), ("chain_offset", C.c_int32), ("seed", C.c_uint64),
-                ("spec_tau", C.c_double), ("rows_per_cta_min", C.c_int32), ("flags", C.c_int32)]
+                ("spec_tau", C.c_double), ("rows_per_cta_min", C.c_int32), ("flags", C.c_int32),
+                ("jet_bound_scale", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -37,7 +40,7 @@ class Stats(C.Structure):
                 ("commit_passes", C.c_uint64), ("cand_evals", C.c_uint64), ("ref_evals", C.c_uint64),
                 ("stepouts", C.c_uint64), ("shrinks", C.c_uint64), ("launches", C.c_uint64),
                 ("sweep_ms", C.c_double), ("algorithmic_bytes", C.c_double), ("coarse_evals", C.c_uint64),
-                ("coarse_undecided", C.c_uint64)]
+                ("coarse_undecided", C.c_uint64), ("jet_passes", C.c_uint64), ("jet_fallbacks", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -84,6 +87,7 @@ def load():
     L.cgg_nccl_unique_id.argtypes = [C.c_char_p]
     L.cgg_comm_init_nccl.argtypes = [vp, i32, i32, C.c_char_p]
     L.cgg_debug_coarse_error.argtypes = [i32, dp, dp]
+    L.cgg_debug_jet.argtypes = [vp, i32, i64, i32, dp, dp, dp, dp]
     L.cgg_debug_row_terms.argtypes = [i32, i32, i64, dp, dp, C.c_double, dp]
     L.cgg_stream.argtypes = [vp]
     L.cgg_stream.restype = vp

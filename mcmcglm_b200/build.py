@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libcggibbs.so")
 SOURCES = ["cggibbs.cu"]
-DEPS = ["cggibbs.cu", "cgg_device.cuh", "cgg_math.cuh", os.path.join("..", "..", "include", "cggibbs.h")]
+DEPS = ["cggibbs.cu", "cgg_device.cuh", "cgg_math.cuh", "cgg_jet.cuh", "cgg_math_tables.cuh", os.path.join("..", "..", "include", "cggibbs.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-ldl"]
 

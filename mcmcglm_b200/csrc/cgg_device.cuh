@@ -8,6 +8,7 @@
 // arrival counter and version flag, so there is no grid-wide barrier anywhere.
 #pragma once
 #include "cgg_math.cuh"
+#include "cgg_jet.cuh"
 
 namespace cgg {
 
@@ -28,7 +29,9 @@ constexpr int RING_OPS = 4;    // eta, y, X_j, X_commit
 constexpr int TILE_ROWS = 64;  // 32 lanes x one 128-bit transfer per operand
 constexpr int RING_BYTES_PER_WARP = RING_D * RING_OPS * 32 * 16;
 
-enum Phase : int32_t { PH_START = 0, PH_STEPOUT = 1, PH_SHRINK = 2, PH_FLUSH = 3, PH_FINISHED = 4 };
+enum Phase : int32_t { PH_START = 0, PH_STEPOUT = 1, PH_SHRINK = 2, PH_FLUSH = 3, PH_FINISHED = 4, PH_JET = 5 };
+static_assert(JET_NV == NV, "a jet pass delivers through the same accumulators as a candidate pass");
+constexpr unsigned JET_BIT = 0x80000000u;   // Ctl::coarse_mask: this pass is a jet pass (cgg_jet.cuh), ncand = 0
 
 // What every worker needs to know about a chain for its coming pass.  12 x 8 bytes.
 struct __align__(16) Ctl {
@@ -79,6 +82,7 @@ struct __align__(16) ChainState {
     uint64_t cursor;    // uniforms consumed before this update
     uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
     uint64_t coarse_evals, coarse_undecided;
+    uint64_t jet_passes, jet_fallbacks;
 };
 static_assert(sizeof(ChainState) % 16 == 0, "ChainState is copied with 128-bit accesses");
 
@@ -93,14 +97,15 @@ struct Dev {
     const double *X; const double *y;
     double *eta, *beta, *shat, *samples, *xbuf;
     const double *replay;
+    const double *colstat;     // [p][CS_STRIDE] per-column scale and absolute moments (jet passes)
     Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
     unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
     int64_t n, p, ldx, lde, n_tiles, n_iter;
     uint64_t n_u, seed;
     int64_t max_steps;
-    double inv_sd, ll_const, w, tau, coarse_theta;
+    double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale;
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, pad_;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -181,6 +186,7 @@ struct ChainStream {
     long long vw, W, n_tiles;
     int64_t n;
     int nc, cj;
+    bool need_yx;            // the pass reads y and X_j (candidates to score, or a jet pass)
     uint32_t slot0;
     // The tile -> worker map is rotated per chain (fixed for the run): n_tiles is rarely a multiple of W, so some
     // workers own one tile more than others; rotating by c * W / C spreads those extra tiles evenly over the
@@ -189,6 +195,7 @@ struct ChainStream {
         const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
         const int j = (int)(w0 & 0xffffffffLL);
         nc = (int)(w0 >> 32); cj = (int)(w1 & 0xffffffffLL);
+        need_yx = nc > 0 || (((unsigned)(w1 >> 32)) & JET_BIT);
         xj = d.X + (int64_t)(j < 0 ? 0 : j) * d.ldx;
         xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
         y = d.y; eta = d.eta + (int64_t)c * d.lde;
@@ -200,7 +207,7 @@ struct ChainStream {
         if (T < n_tiles && i + 1 < n) {
             const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
             cp_async16(s, eta + i);
-            if (nc > 0) { cp_async16(s + 512u, y + i); cp_async16(s + 1024u, xj + i); }
+            if (need_yx) { cp_async16(s + 512u, y + i); cp_async16(s + 1024u, xj + i); }
             if (cj >= 0) cp_async16(s + 1536u, xc + i);
         }
         cp_async_commit();
@@ -292,6 +299,49 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
     }
 }
 
+// One warp, one chain, one JET pass (cgg_jet.cuh): applies the pending eta update like any pass and accumulates
+// the exact log-likelihood at the committed eta plus the derivative moments along column j in registers.
+template <int FAMILY>
+__device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &cs, double cdelta, double cscale, int lane,
+                                              const double2 *tab, bool prefetched, double (&m)[NV]) {
+    const int cj = cs.cj;
+    const int64_t n = cs.n;
+    double *eta = cs.eta;
+    if (!prefetched) cs.prologue(lane);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) m[k] = 0.0;
+    int stage = 0;
+    for (long long T = cs.vw; T < cs.n_tiles; T += cs.W) {
+        cs.issue(T + (RING_D - 1) * cs.W, (stage + RING_D - 1) % RING_D, lane);
+        cp_async_wait<RING_D - 1>();
+        const int64_t i = T * TILE_ROWS + 2 * lane;
+        if (i + 1 < n) {
+            const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
+            double2 e = lds2(s);
+            if (cj >= 0) {
+                const double2 cv = lds2(s + 1536u);
+                e.x = eta_shift(e.x, cv.x, cdelta);
+                e.y = eta_shift(e.y, cv.y, cdelta);
+                *reinterpret_cast<double2 *>(eta + i) = e;
+            }
+            double2 xs = lds2(s + 1024u);
+            xs.x *= cscale; xs.y *= cscale;           // power of two: exact
+            JetRow<FAMILY>::add2(lds2(s + 512u), e, xs, d.inv_sd, tab, m);
+        }
+        stage = (stage + 1 == RING_D) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+    if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
+        const int64_t t = n - 1;
+        const long long Tl = t / TILE_ROWS;
+        if (Tl % cs.W == cs.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
+            double e = __ldcg(eta + t);
+            if (cj >= 0) { e = eta_shift(e, __ldg(cs.xc + t), cdelta); eta[t] = e; }
+            JetRow<FAMILY>::add1(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m);
+        }
+    }
+}
+
 // A worker's whole contribution to one pass of chain c: read the control block, stream the rows and
 // return the warp's partial sums (identical in every lane): acc[0..nc) candidate sums and, when the
 // pre-filter is active, acc[nc], acc[nc+1] = sum |eta|, sum |x| over the warp's rows.  Return value: -1
@@ -311,6 +361,23 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
     const bool was_prefetched = prefetched;
     prefetched = false;
     if (j < 0) return -1;
+    if (cmask & JET_BIT) {
+        {
+            const long long t0 = t_tiles ? clock64() : 0;
+            const ChainStream cs(d, c, cw, wid, W, lane, ring);
+            warp_pass_jet<FAMILY>(d, cs, cw[2], __ldg(d.colstat + (int64_t)j * CS_STRIDE), lane, tab, was_prefetched, acc);
+            if (t_tiles) *t_tiles += clock64() - t0;
+        }
+        if (next_cw) {
+            const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
+            const long long nw0 = __double_as_longlong(next_cw[0]);
+            const int nj = (int)(nw0 & 0xffffffffLL);
+            if (nj >= 0 && (ns.need_yx || ns.cj >= 0)) { ns.prologue(lane); prefetched = true; }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
+        return NV;
+    }
     if (nc == 0 && cj < 0) return 0;
     float bE = 0.0f, bX = 0.0f;
     unsigned nearmask = 0;
@@ -324,7 +391,7 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
         const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
         const long long nw0 = __double_as_longlong(next_cw[0]);
         const int nj = (int)(nw0 & 0xffffffffLL);
-        if (nj >= 0 && (ns.nc > 0 || ns.cj >= 0)) { ns.prologue(lane); prefetched = true; }
+        if (nj >= 0 && (ns.need_yx || ns.cj >= 0)) { ns.prologue(lane); prefetched = true; }
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -497,6 +564,30 @@ __device__ __forceinline__ void start_coordinate(const Dev &d, ChainState &s, do
     s.phase = (s.openL || s.openR) ? PH_STEPOUT : PH_SHRINK;
 }
 
+// The accepted value x1 of coordinate s.j (R/mcmcglm.R:262-271): beta, sample store, the eta update deferred to the
+// next pass of this chain, uniform cursor, and on to the next coordinate.  `writer`: this lane does the global stores
+// (the state update itself may be replicated over the lanes of the deciding warp).
+__device__ __forceinline__ void accept_value(const Dev &d, int c, ChainState &s, Ctl &ct, double x1, double f, double shat_j,
+                                             int shrink_draws, bool writer, double &x1_out, double &shat_out) {
+    const int64_t pj = (int64_t)c * d.p + s.j;
+    shat_out = (shat_j > 0.0) ? 0.75 * shat_j + 0.25 * (s.R - s.L) : (s.R - s.L);  // bracket width at acceptance
+    x1_out = x1;
+    if (writer) {
+        d.shat[pj] = shat_out;
+        d.beta[pj] = x1;                                        // R/mcmcglm.R:264
+        if (d.samples) d.samples[((int64_t)c * d.n_iter + s.iter) * d.p + s.j] = x1;  // :271
+    }
+    ct.commit_j = s.j;                                      // eta update deferred to the next pass
+    ct.commit_delta = __dadd_rn(x1, -s.x0);
+    s.fx0 = f;
+    s.prior_sum = s.prior_rest + prior_logdens(d.prior, x1);
+    s.cursor += base_draws(d) + shrink_draws;
+    s.updates++;
+    s.j++;
+    if (s.j == d.p) { s.j = 0; s.iter++; }
+    s.phase = (s.iter >= d.n_iter) ? PH_FLUSH : PH_START;
+}
+
 // Lane-0 scalar code: consume the log-potentials F[0..ncand) of the pass that just finished.
 // Returns true when the update was accepted (s.j / s.iter advanced, s.phase = START or FLUSH);
 // x1_out / shat_out then hold the accepted value and the refreshed width estimate of that coordinate.
@@ -546,21 +637,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
         s.ref_evals++; s.shrinks++;
         if (f != f) { s.status = CGG_E_NAN; return false; }
         if (s.ylev < f) {
-            const int64_t pj = (int64_t)c * d.p + s.j;
-            shat_out = (shat_j > 0.0) ? 0.75 * shat_j + 0.25 * (s.R - s.L) : (s.R - s.L);  // bracket width at acceptance
-            x1_out = x1;
-            d.shat[pj] = shat_out;
-            d.beta[pj] = x1;                                        // R/mcmcglm.R:264
-            ct.commit_j = s.j;                                      // eta update deferred to the next pass
-            ct.commit_delta = __dadd_rn(x1, -s.x0);
-            s.fx0 = f;
-            s.prior_sum = s.prior_rest + prior_logdens(d.prior, x1);
-            s.cursor += base_draws(d) + s.sdrawn + i + 1;
-            if (d.samples) d.samples[((int64_t)c * d.n_iter + s.iter) * d.p + s.j] = x1;  // :271
-            s.updates++;
-            s.j++;
-            if (s.j == d.p) { s.j = 0; s.iter++; }
-            s.phase = (s.iter >= d.n_iter) ? PH_FLUSH : PH_START;
+            accept_value(d, c, s, ct, x1, f, shat_j, s.sdrawn + i + 1, true, x1_out, shat_out);
             return true;
         }
         if (x1 < s.x0) s.L = x1; else s.R = x1;
@@ -568,6 +645,113 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
     s.sdrawn += s.nS;
     if (s.npass > 100000) s.status = CGG_E_NOTERM;
     return false;
+}
+
+// The whole slice_stepping_out update of coordinate s.j from the sums of ONE jet pass (cgg_jet.cuh).  Run by all 32
+// lanes with the chain state replicated (every lane performs the same scalar updates); lanes evaluate different
+// candidates: stepping-out tests L, L-w, ... (lanes 0..15) and R, R+w, ... (lanes 16..31), then 32 shrink proposals.
+// Each candidate's exact log-potential is enclosed as [f_lo, f_hi]; "inside the slice" needs ylev < f_lo, "outside"
+// needs f_hi <= ylev.  The sequence is consumed while the verdicts are certain.  Returns true when the update was
+// accepted.  Otherwise s.phase is PH_STEPOUT / PH_SHRINK with the bracket, budgets, counters and consumed draws
+// exactly as the reference algorithm has them at that point, and the exact passes take over from there.
+__device__ __forceinline__ bool jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV],
+                                           double x0, double shat_j, double &x1_out, double &shat_out) {
+    s.npass++; s.jet_passes++;
+    if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
+    ct.coarse_mask = 0;
+    if (!(fabs(m[0]) < INFINITY)) { s.status = CGG_E_NAN; return false; }     // f(x0) itself is not finite
+    s.fx0 = (m[0] + d.ll_const) + s.prior_sum;       // the reference's first evaluation, f(x0), at the committed eta
+    const double *cst = d.colstat + (int64_t)s.j * CS_STRIDE;
+    // ---- uniforms: 2 (3 with a finite max) start draws + up to 32 shrink draws
+    double uA = 0.5, uB = 0.5;
+    const bool okA = draw_uniform(d, c, s.cursor + lane, uA);
+    const bool okB = draw_uniform(d, c, s.cursor + 32 + lane, uB);
+    const unsigned mA = __ballot_sync(0xffffffffu, okA), mB = __ballot_sync(0xffffffffu, okB);
+    const int nAvail = (mA == 0xffffffffu) ? 32 + ((mB == 0xffffffffu) ? 32 : __ffs(~mB) - 1) : __ffs(~mA) - 1;
+    const int base = base_draws(d);
+    double U3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) U3[i] = __shfl_sync(0xffffffffu, uA, i);
+    start_coordinate(d, s, x0, U3, nAvail < 3 ? nAvail : 3);
+    if (s.status != CGG_OK) return false;
+    const int sidx = base + lane;                     // this lane's shrink draw
+    const double usA = __shfl_sync(0xffffffffu, uA, sidx & 31), usB = __shfl_sync(0xffffffffu, uB, sidx & 31);
+    const double us = (sidx < 32) ? usA : usB;
+    const bool us_ok = sidx < nAvail;
+    const double bscale = d.jet_bscale;
+    // enclosure of f at candidate v (same expression order as the exact path: ll + ll_const, then + prior)
+    auto verdict = [&](double v, bool &in, bool &out, double &fmid) {
+        double B;
+        const double ll = jet_eval(d.family, m, cst, (double)d.n, d.inv_sd, __dadd_rn(v, -s.x0), B);
+        B = B * bscale + 4.0 * JET_EPS * fabs(ll);    // + the rounding of ll -+ B itself
+        const double pr = s.prior_rest + prior_logdens(d.prior, v);
+        const double flo = ((ll - B) + d.ll_const) + pr, fhi = ((ll + B) + d.ll_const) + pr;
+        fmid = (ll + d.ll_const) + pr;
+        in = s.ylev < flo;
+        out = fhi <= s.ylev;
+    };
+    if (s.phase == PH_STEPOUT) {
+        const bool left = lane < 16;
+        const int i = lane & 15;
+        double v = left ? s.L : s.R;
+        const double step = left ? -d.w : d.w;
+        for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
+        bool in = false, out = false; double fm;
+        if (left ? s.openL : s.openR) verdict(v, in, out, fm);
+        const unsigned min_ = __ballot_sync(0xffffffffu, in), mout = __ballot_sync(0xffffffffu, out);
+        bool expanded = false;
+        // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
+        for (int t = 0; t < 16 && s.openL; ++t) {
+            const bool tin = (min_ >> t) & 1u, tout = (mout >> t) & 1u;
+            if (!tin && !tout) break;
+            s.ref_evals++;
+            if (tin) {
+                s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true;
+                if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; }
+            } else s.openL = 0;
+        }
+        for (int t = 0; t < 16 && s.openR; ++t) {
+            const bool tin = (min_ >> (16 + t)) & 1u, tout = (mout >> (16 + t)) & 1u;
+            if (!tin && !tout) break;
+            s.ref_evals++;
+            if (tin) {
+                s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true;
+                if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; }
+            } else s.openR = 0;
+        }
+        s.pexp = 0.9 * s.pexp + (expanded ? 0.1 : 0.0);
+        if (s.openL || s.openR) { s.jet_fallbacks++; return false; }     // a test the enclosure could not decide
+        s.phase = PH_SHRINK;
+    }
+    // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }: the proposals depend on (L, R, x0, u) only
+    double l = s.L, r = s.R, xi = 0.0, li = l, ri = r;
+    for (int t = 0; t < 32; ++t) {
+        const double ut = __shfl_sync(0xffffffffu, us, t);
+        const double x = __dadd_rn(l, __dmul_rn(ut, __dadd_rn(r, -l)));
+        if (lane == t) { xi = x; li = l; ri = r; }
+        if (x < s.x0) l = x; else r = x;
+    }
+    bool in = false, out = false; double fm = 0.0;
+    if (us_ok) verdict(xi, in, out, fm);
+    const unsigned mout = __ballot_sync(0xffffffffu, out);
+    const int k = (mout == 0xffffffffu) ? 32 : __ffs(~mout) - 1;      // first proposal that is not certainly rejected
+    if (k == 32) {
+        s.shrinks += 32; s.ref_evals += 32; s.sdrawn = 32; s.L = l; s.R = r;
+        s.jet_fallbacks++;
+        return false;
+    }
+    const bool kin = __shfl_sync(0xffffffffu, (int)in, k);
+    s.L = __shfl_sync(0xffffffffu, li, k); s.R = __shfl_sync(0xffffffffu, ri, k);   // the bracket proposal k was drawn from
+    s.shrinks += k; s.ref_evals += k;
+    if (!kin) {                 // undecided (or its draw is not available): the exact passes continue from proposal k
+        s.sdrawn = k;
+        s.jet_fallbacks++;
+        return false;
+    }
+    s.shrinks++; s.ref_evals++;
+    const double x1 = __shfl_sync(0xffffffffu, xi, k), f1 = __shfl_sync(0xffffffffu, fm, k);
+    accept_value(d, c, s, ct, x1, f1, shat_j, k + 1, lane == 0, x1_out, shat_out);
+    return true;
 }
 
 // One warp decides one chain after every worker's contribution to the pass is visible.
@@ -588,13 +772,20 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     Ctl ct = d.ctl[c];
     ChainState s = d.cs[c];
     if (s.phase == PH_FINISHED || s.status != CGG_OK) return true;
-    const int nc = ct.ncand;
-    const unsigned cmask = (unsigned)ct.coarse_mask;
+    const bool jetpass = ((unsigned)ct.coarse_mask & JET_BIT) != 0u && s.phase == PH_JET;
+    const int nc = jetpass ? 0 : ct.ncand;
+    const unsigned cmask = jetpass ? 0u : (unsigned)ct.coarse_mask;
+    double jm[NV];
+    if (jetpass) {
+        const double mv = (lane < NV) ? (from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
+    }
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
     unsigned int aflags = 0;
     if (lane < nc) {
-        const double ll = from_xbuf ? __ldcg(d.xbuf + c * KMAX + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
+        const double ll = from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
         f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));
     }
     int stop_at = nc;
@@ -619,7 +810,12 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     for (int k = 0; k < KMAX; ++k) F[k] = __shfl_sync(0xffffffffu, f, k);
     s.passes++;
     double x0 = beta_j, shat = shat_j;     // values of the coordinate that is sampled next
-    if (lane == 0 && s.phase != PH_START) {
+    if (jetpass) {
+        double x1 = 0.0, sh1 = 0.0;
+        if (jet_decide(d, c, lane, s, ct, jm, beta_j, shat_j, x1, sh1)) {
+            if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }
+        }
+    } else if (lane == 0 && s.phase != PH_START) {
         double x1 = 0.0, sh1 = 0.0;
         if (process_results(d, c, s, ct, F, stop_at, shat_j, x1, sh1)) {
             if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }   // p == 1: same column again
@@ -636,7 +832,14 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
         v = warp_sum(v);
         s.prior_sum = v;
     }
-    if (status == CGG_OK && (phase == PH_START || phase == PH_SHRINK || phase == PH_STEPOUT)) {
+    if (status == CGG_OK && phase == PH_START && d.jet) {
+        // jet mode: the next pass of this chain applies the pending eta update and delivers f(x0) and the derivative
+        // moments along the new column; the whole update is then decided from them
+        if (lane == 0) {
+            ct.j = s.j; ct.ncand = 0; ct.coarse_mask = (int32_t)JET_BIT;
+            s.phase = PH_JET; s.chain_passes++;
+        }
+    } else if (status == CGG_OK && (phase == PH_START || phase == PH_SHRINK || phase == PH_STEPOUT)) {
         // uniforms the next decision steps can need, fetched by the lanes in parallel
         const uint64_t cursor = __shfl_sync(0xffffffffu, (unsigned long long)s.cursor, 0);
         const int sdrawn = __shfl_sync(0xffffffffu, s.sdrawn, 0);
@@ -655,7 +858,7 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
             if (s.status == CGG_OK) build_candidates(d, s, ct, shat, U + off, nU - off > 0 ? nU - off : 0);
         }
     } else if (lane == 0) {
-        ct.ncand = 0;
+        ct.ncand = 0; ct.coarse_mask = 0;
     }
     bool fin = false;
     if (lane == 0) {

@@ -216,8 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     for (int c = warp; c < d.C; c += NWARPS) {
         if (mode == 0) decide_chain(&d, c, lane, -1, false);
         else {
-            const int nc = d.ctl[c].ncand;
-            if (lane < KMAX) d.xbuf[c * KMAX + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + d.ll_const : 0.0;
+            const bool jet = ((unsigned)d.ctl[c].coarse_mask & JET_BIT) != 0u;
+            const int nc = jet ? NV : d.ctl[c].ncand;
+            if (lane < NV) d.xbuf[c * NV + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + (jet ? 0.0 : d.ll_const) : 0.0;
         }
     }
     __syncthreads();
@@ -253,7 +254,7 @@ __global__ void finalize_eval_kernel(Dev d, int c, int j, int K, const double *c
     }
     v = warp_sum(v);
     vall = warp_sum(vall);
-    if (lane < K) out[lane] = d.xbuf[c * KMAX + lane] + (v + prior_logdens(d.prior, cand[lane]));
+    if (lane < K) out[lane] = d.xbuf[c * NV + lane] + (v + prior_logdens(d.prior, cand[lane]));
     if (lane == 0 && prior_sum_out) *prior_sum_out = vall;
 }
 
@@ -374,6 +375,69 @@ __global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial,
     }
 }
 
+// Per-column statistics for the jet passes (cgg_jet.cuh), one CTA per column: cs = 2^-e with max|x| * cs in [0.5, 1)
+// (exact scaling), S_k = sum_i |x_i cs|^k for k = 1..8 rounded UP (they enter error bounds), max|x|.
+__global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, int64_t n, int64_t ldx, int64_t p, double *out) {
+    __shared__ double s_red[NWARPS][8];
+    __shared__ double s_cs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {
+        const double *x = X + j * ldx;
+        double mx = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += THREADS) { const double a = fabs(x[i]); mx = (a > mx || a != a) ? a : mx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); mx = (t > mx || t != t) ? t : mx; }
+        if (lane == 0) s_red[warp][0] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int w = 0; w < NWARPS; ++w) { const double t = s_red[w][0]; m = (t > m || t != t) ? t : m; }
+            int e = 0;
+            double cs = 1.0;
+            if (m > 0.0 && m < INFINITY) { frexp(m, &e); cs = ldexp(1.0, -e); }
+            if (!(cs > 0.0) || !(cs < INFINITY)) cs = 1.0;      // subnormal / huge columns: no scaling (the bounds then simply fail to decide)
+            s_cs = cs;
+            out[j * CS_STRIDE + 0] = cs; out[j * CS_STRIDE + 1] = 1.0 / cs; out[j * CS_STRIDE + 10] = m; out[j * CS_STRIDE + 11] = 0.0;
+        }
+        __syncthreads();
+        const double cs = s_cs;
+        double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int64_t i = threadIdx.x; i < n; i += THREADS) {
+            const double a = fabs(x[i]) * cs;
+            double pw = a;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { S[k] += pw; pw *= a; }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { S[k] = warp_sum(S[k]); if (lane == 0) s_red[warp][k] = S[k]; }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double v = 0.0;
+            for (int w = 0; w < NWARPS; ++w) v += s_red[w][threadIdx.x];
+            // fp64 summation of n non-negative terms: relative error <= n * 2^-53; inflate so the value is an upper bound
+            out[j * CS_STRIDE + 2 + threadIdx.x] = v * (1.0 + 4.0 * (double)n * 1.1102230246251565e-16 + 1e-12);
+        }
+        __syncthreads();
+    }
+}
+
+// Diagnostic (cgg_debug_jet): evaluate the enclosure of chain c's current jet sums at K candidates.
+__global__ void jet_debug_kernel(Dev d, int c, int j, int K, const double *cand, double *out /* [K] value, [K] bound, [NV] sums */) {
+    const int lane = threadIdx.x;
+    double m[NV];
+    const double mv = (lane < NV) ? d.xbuf[c * NV + lane] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) m[k] = __shfl_sync(0xffffffffu, mv, k);
+    const double x0 = d.beta[(int64_t)c * d.p + j];
+    if (lane < K) {
+        double B;
+        const double f = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, (double)d.n, d.inv_sd, __dadd_rn(cand[lane], -x0), B);
+        out[lane] = f + d.ll_const;
+        out[K + lane] = B * d.jet_bscale + 4.0 * JET_EPS * fabs(f);
+    }
+    if (lane < NV) out[2 * K + lane] = m[lane];
+}
+
 // Row-sharded exchange tail: totals in rank order => bit-identical on every rank.
 __global__ void rank_sum_kernel(const double *gathered, int world, int count, double *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,6 +501,7 @@ struct cgg_handle {
     double *replay_dev = nullptr; uint64_t replay_cap = 0;
     double *samples_dev = nullptr; size_t samples_cap = 0;
     double *scratch_dev = nullptr;  // KMAX cand + KMAX out + 1
+    double *colstat_dev = nullptr;  // [p][CS_STRIDE]
     size_t smem = 0;
     unsigned long long *prof_dev = nullptr;
     Hdr *hdr_pinned = nullptr;
@@ -465,7 +530,7 @@ static void *kernel_ptr(int family, int which) {
 // Row-sharded mode: turn the local per-candidate sums in d.xbuf into global sums, identical on every rank.
 static int exchange(cgg_handle *h) {
     Dev &d = h->d;
-    const int count = d.C * KMAX;
+    const int count = d.C * NV;
     if (h->comm) {
         ncclResult_t r = g_nccl.AllGather(d.xbuf, h->gather_dev, (size_t)count, ncclDouble, h->comm, h->stream);
         if (r != ncclSuccess) return fail(CGG_E_COMM, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
@@ -522,6 +587,8 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     d.sharded = cfg->mode == CGG_MODE_ROW_SHARDED;
     d.coarse = (cfg->family == CGG_BINOMIAL) && !d.sharded && !(cfg->flags & CGG_FLAG_NO_PREFILTER);
     d.coarse_theta = getenv("CGG_COARSE_THETA") ? atof(getenv("CGG_COARSE_THETA")) : 0.4;
+    d.jet = !d.sharded && !(cfg->flags & CGG_FLAG_NO_JET);
+    d.jet_bscale = (cfg->jet_bound_scale > 0.0) ? cfg->jet_bound_scale : 1.0;
     d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
     d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
     if (cfg->prior == CGG_PRIOR_NORMAL) d.prior.c0 = -(kLnSqrt2Pi + log(cfg->prior_sigma));
@@ -564,11 +631,12 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&d.shat, sizeof(double) * (size_t)C * d.p);
     if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.sync, sizeof(ChainSync) * (size_t)C);
-    if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * KMAX);
+    if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.ctl, sizeof(Ctl) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.cs, sizeof(ChainState) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.hdr, sizeof(Hdr));
-    if (e == cudaSuccess) e = A((void **)&h->scratch_dev, sizeof(double) * (2 * KMAX + 2));
+    if (e == cudaSuccess) e = A((void **)&h->scratch_dev, sizeof(double) * (3 * KMAX + NV + 2));
+    if (e == cudaSuccess) e = A((void **)&h->colstat_dev, sizeof(double) * (size_t)d.p * CS_STRIDE);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->hdr_pinned, sizeof(Hdr));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -589,6 +657,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     CK(cudaStreamSynchronize(h->stream));
     h->chain_init.assign(C, 0);
     h->fx_valid.assign(C, 0);
+    d.colstat = h->colstat_dev;
     *out = h;
     return CGG_OK;
 }
@@ -600,7 +669,7 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     Dev &d = h->d;
     cudaFree(d.eta); cudaFree(d.beta); cudaFree(d.shat); cudaFree(d.acc); cudaFree(d.sync); cudaFree(d.xbuf);
     cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr);
-    cudaFree(h->scratch_dev); cudaFree(h->prof_dev);
+    cudaFree(h->scratch_dev); cudaFree(h->prof_dev); cudaFree(h->colstat_dev);
     if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -635,6 +704,12 @@ static int finish_set_data(cgg_handle *h) {
     if (d.family == CGG_GAUSSIAN) d.ll_const = -(double)d.n * (kLnSqrt2Pi + log(h->cfg.sd));
     else if (d.family == CGG_POISSON) d.ll_const = -(double)s;
     else d.ll_const = 0.0;
+    if (d.jet) {
+        const int grid = (int)std::min<int64_t>(d.p, 4 * (int64_t)h->num_sms);
+        col_stats_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.n, d.ldx, d.p, h->colstat_dev);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    }
     h->has_data = true;
     std::fill(h->chain_init.begin(), h->chain_init.end(), 0);
     std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);
@@ -859,6 +934,36 @@ extern "C" int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plu
     return CGG_OK;
 }
 
+extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host,
+                             double *value_host, double *bound_host, double *sums_host) {
+    int rc = check_chain(h, chain, "cgg_debug_jet", true);
+    if (rc) return rc;
+    Dev &d = h->d;
+    if (!d.jet) return fail(CGG_E_STATE, "cgg_debug_jet: handle was created without jet passes");
+    if (j < 0 || j >= d.p) return fail(CGG_E_ARG, "cgg_debug_jet: j out of range");
+    if (K < 1 || K > KMAX || !cand_host || !value_host || !bound_host) return fail(CGG_E_ARG, "cgg_debug_jet: K must be in 1..%d and buffers non-NULL", KMAX);
+    CK(cudaSetDevice(h->cfg.device));
+    std::vector<Ctl> ctl(d.C), saved(d.C);
+    memset(ctl.data(), 0, sizeof(Ctl) * d.C);
+    for (int c = 0; c < d.C; ++c) ctl[c].commit_j = -1;
+    ctl[chain].j = (int32_t)j; ctl[chain].ncand = 0; ctl[chain].coarse_mask = (int32_t)JET_BIT;
+    CK(cudaMemcpyAsync(saved.data(), d.ctl, sizeof(Ctl) * d.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(d.ctl, ctl.data(), sizeof(Ctl) * d.C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->scratch_dev, cand_host, sizeof(double) * K, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(&d.hdr->done, 0, sizeof(int32_t), h->stream));
+    rc = launch_pass(h, 1);
+    if (rc) return rc;
+    jet_debug_kernel<<<1, 32, 0, h->stream>>>(d, chain, (int)j, K, h->scratch_dev, h->scratch_dev + KMAX);
+    CK(cudaGetLastError());
+    std::vector<double> out(2 * K + NV);
+    CK(cudaMemcpyAsync(out.data(), h->scratch_dev + KMAX, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(d.ctl, saved.data(), sizeof(Ctl) * d.C, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < K; ++k) { value_host[k] = out[k]; bound_host[k] = out[K + k]; }
+    if (sums_host) for (int k = 0; k < NV; ++k) sums_host[k] = out[2 * K + k];
+    return CGG_OK;
+}
+
 extern "C" int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user) {
     if (!h) return fail(CGG_E_ARG, "cgg_set_exchange: NULL handle");
     h->xfn = fn; h->xuser = user;
@@ -887,7 +992,7 @@ extern "C" int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, co
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
     if (r != ncclSuccess) { h->comm = nullptr; return fail(CGG_E_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
     h->world = world; h->rank = rank;
-    CK(cudaMalloc((void **)&h->gather_dev, sizeof(double) * (size_t)world * h->d.C * KMAX));
+    CK(cudaMalloc((void **)&h->gather_dev, sizeof(double) * (size_t)world * h->d.C * NV));
     return CGG_OK;
 }
 
@@ -948,6 +1053,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         cs[c].phase = PH_START; cs[c].status = CGG_OK; cs[c].iter = 0; cs[c].j = 0;
         cs[c].updates = cs[c].chain_passes = cs[c].commit_passes = cs[c].cand_evals = 0;
         cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = cs[c].coarse_evals = cs[c].coarse_undecided = 0;
+        cs[c].jet_passes = cs[c].jet_fallbacks = 0;
         cs[c].fine_next = 0;
         ctl[c].commit_j = -1;
     }
@@ -1022,6 +1128,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         st.updates += cs[c].updates; st.chain_passes += cs[c].chain_passes; st.commit_passes += cs[c].commit_passes;
         st.cand_evals += cs[c].cand_evals; st.ref_evals += cs[c].ref_evals; st.stepouts += cs[c].stepouts; st.shrinks += cs[c].shrinks;
         st.passes += cs[c].passes; st.coarse_evals += cs[c].coarse_evals; st.coarse_undecided += cs[c].coarse_undecided;
+        st.jet_passes += cs[c].jet_passes; st.jet_fallbacks += cs[c].jet_fallbacks;
         if (u_consumed) u_consumed[c] = cs[c].cursor;
         if (cs[c].status != CGG_OK && bad == CGG_OK) { bad = cs[c].status; bad_chain = c; }
     }
