@@ -41,7 +41,7 @@ struct __align__(16) Ctl {
     int32_t coarse_mask;// bit k: candidate k is scored by the fp32 pre-filter (binomial only)
     double commit_delta;// new_beta_j - current_beta_j of that update (R/glm_utils.R:127)
     double delta[KMAX]; // cand_k - beta_j
-    double pad1;
+    double cscale;      // jet pass: the column's power-of-two scale (colstat[j][0]), so workers need no dependent load
 };
 static_assert(sizeof(Ctl) == 96, "Ctl must be 12 doubles");
 constexpr int CTL_WORDS = sizeof(Ctl) / 8;
@@ -212,6 +212,16 @@ struct ChainStream {
         }
         cp_async_commit();
     }
+    // same, addressed by the row index i = T * TILE_ROWS + 2 * lane of this lane's pair (i + 1 < n implies T < n_tiles)
+    __device__ __forceinline__ void issue_at(int64_t i, int stage) const {
+        if (i + 1 < n) {
+            const uint32_t s = slot0 + (uint32_t)stage * (RING_OPS * 512u);
+            cp_async16(s, eta + i);
+            if (need_yx) { cp_async16(s + 512u, y + i); cp_async16(s + 1024u, xj + i); }
+            if (cj >= 0) cp_async16(s + 1536u, xc + i);
+        }
+        cp_async_commit();
+    }
     // first RING_D - 1 tiles; may be issued early, while the previous chain is still being reduced
     __device__ __forceinline__ void prologue(int lane) const {
 #pragma unroll
@@ -302,6 +312,22 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
 // One warp, one chain, one JET pass (cgg_jet.cuh): applies the pending eta update like any pass and accumulates
 // the exact log-likelihood at the committed eta plus the derivative moments along column j in registers.
 template <int FAMILY>
+__device__ __forceinline__ void jet_tile(const ChainStream &cs, double cdelta, double cscale, double inv_sd, int stage, double *eta_i,
+                                         const double2 *tab, double (&m)[NV], unsigned &risk) {
+    const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
+    double2 e = lds2(s);
+    if (cs.cj >= 0) {
+        const double2 cv = lds2(s + 1536u);
+        e.x = eta_shift(e.x, cv.x, cdelta);
+        e.y = eta_shift(e.y, cv.y, cdelta);
+        *reinterpret_cast<double2 *>(eta_i) = e;
+    }
+    double2 xs = lds2(s + 1024u);
+    xs.x *= cscale; xs.y *= cscale;           // power of two: exact
+    JetRow<FAMILY>::add2(lds2(s + 512u), e, xs, inv_sd, tab, m, risk);
+}
+
+template <int FAMILY>
 __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &cs, double cdelta, double cscale, int lane,
                                               const double2 *tab, bool prefetched, double (&m)[NV]) {
     const int cj = cs.cj;
@@ -310,25 +336,32 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
     if (!prefetched) cs.prologue(lane);
 #pragma unroll
     for (int k = 0; k < NV; ++k) m[k] = 0.0;
-    int stage = 0;
-    for (long long T = cs.vw; T < cs.n_tiles; T += cs.W) {
-        cs.issue(T + (RING_D - 1) * cs.W, (stage + RING_D - 1) % RING_D, lane);
-        cp_async_wait<RING_D - 1>();
-        const int64_t i = T * TILE_ROWS + 2 * lane;
-        if (i + 1 < n) {
-            const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
-            double2 e = lds2(s);
-            if (cj >= 0) {
-                const double2 cv = lds2(s + 1536u);
-                e.x = eta_shift(e.x, cv.x, cdelta);
-                e.y = eta_shift(e.y, cv.y, cdelta);
-                *reinterpret_cast<double2 *>(eta + i) = e;
+    unsigned risk = 0;     // running max of a per-row integer key (JetRow): compared with the family's threshold at the end
+    // Running pointers of the tile being ISSUED (RING_D - 1 tiles ahead of the one being scored), advanced by one
+    // stride per iteration: four 64-bit adds instead of re-deriving four addresses from the chain/column indices.
+    {
+        static_assert((RING_D & (RING_D - 1)) == 0, "ring depth must be a power of two");
+        unsigned stage = 0;
+        const int64_t step = cs.W * TILE_ROWS;
+        const int64_t i0 = cs.vw * TILE_ROWS + 2 * lane;
+        const double *pe = eta + i0 + (RING_D - 1) * step, *py = cs.y + i0 + (RING_D - 1) * step;
+        const double *px = cs.xj + i0 + (RING_D - 1) * step, *pc = cs.xc + i0 + (RING_D - 1) * step;
+        const double *const pe_last = eta + (n - 1);                   // a pair at p is inside the matrix iff p < pe_last
+        const double *const pe_end = eta + cs.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
+        const uint32_t sbase = cs.slot0;
+        for (; pe < pe_end; pe += step, py += step, px += step, pc += step) {
+            if (pe < pe_last) {
+                const uint32_t sa = sbase + ((stage + RING_D - 1) & (RING_D - 1)) * (RING_OPS * 512u);
+                cp_async16(sa, pe);
+                cp_async16(sa + 512u, py); cp_async16(sa + 1024u, px);
+                if (cj >= 0) cp_async16(sa + 1536u, pc);
             }
-            double2 xs = lds2(s + 1024u);
-            xs.x *= cscale; xs.y *= cscale;           // power of two: exact
-            JetRow<FAMILY>::add2(lds2(s + 512u), e, xs, d.inv_sd, tab, m);
+            cp_async_commit();
+            cp_async_wait<RING_D - 1>();
+            double *ecur = const_cast<double *>(pe) - (RING_D - 1) * step;
+            if (ecur < pe_last) jet_tile<FAMILY>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk);
+            stage = (stage + 1) & (RING_D - 1);
         }
-        stage = (stage + 1 == RING_D) ? 0 : stage + 1;
     }
     cp_async_wait<0>();
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
@@ -337,9 +370,10 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
         if (Tl % cs.W == cs.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
             double e = __ldcg(eta + t);
             if (cj >= 0) { e = eta_shift(e, __ldg(cs.xc + t), cdelta); eta[t] = e; }
-            JetRow<FAMILY>::add1(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m);
+            JetRow<FAMILY>::add1(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m, risk);
         }
     }
+    if (FAMILY != CGG_GAUSSIAN) m[9] = (risk >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
 }
 
 // A worker's whole contribution to one pass of chain c: read the control block, stream the rows and
@@ -365,7 +399,7 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
         {
             const long long t0 = t_tiles ? clock64() : 0;
             const ChainStream cs(d, c, cw, wid, W, lane, ring);
-            warp_pass_jet<FAMILY>(d, cs, cw[2], __ldg(d.colstat + (int64_t)j * CS_STRIDE), lane, tab, was_prefetched, acc);
+            warp_pass_jet<FAMILY>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
             if (t_tiles) *t_tiles += clock64() - t0;
         }
         if (next_cw) {
@@ -837,6 +871,7 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
         // moments along the new column; the whole update is then decided from them
         if (lane == 0) {
             ct.j = s.j; ct.ncand = 0; ct.coarse_mask = (int32_t)JET_BIT;
+            ct.cscale = __ldcg(d.colstat + (int64_t)s.j * CS_STRIDE);
             s.phase = PH_JET; s.chain_passes++;
         }
     } else if (status == CGG_OK && (phase == PH_START || phase == PH_SHRINK || phase == PH_STEPOUT)) {

@@ -17,18 +17,22 @@
 //
 // Slot layout of the NV values a jet pass delivers:
 //   gaussian : 0..2 M_0..M_2 (exact quadratic, no remainder) | 3 sum|z||eta| | 4 sum|z| | 5 sum|eta|
-//   binomial : 0..7 M_0..M_7 | 8 sum|eta| | 9 rows too close to the stats logit clamp (|eta| = 30)
+//   binomial : 0 M_0 | 1..7 the positive-form sums m_1..m_7 (see JetRow<CGG_BINOMIAL>) | 9 rows with |eta| >= 21.9 (the
+//              stats logit clamp at |eta| = 30 is then within reach of the enclosure's radius)
 //   poisson  : 0..6 M_0..M_6 | 7 sum|xs|^7 mu | 8 sum(|y| + mu)(|eta| + 1) | 9 rows too close to the pmax(., eps) clamp
 #pragma once
 #include "cgg_math.cuh"
 
 namespace cgg {
 
+#ifndef CGG_JET_D
+#define CGG_JET_D 5                        // order of the binomial expansion (5 or 7)
+#endif
 constexpr int JET_NV = CGG_KMAX + 2;       // same number of accumulators as a candidate pass
-constexpr int CS_STRIDE = 12;              // per-column statistics: {cs, 1/cs, S_1..S_8, max|x|, pad}
+constexpr int CS_STRIDE = 12;              // per-column statistics: {cs, 1/cs, S_1..S_8, max|x|, C1 = sum xs (y - 1/2)}
 constexpr double JET_AMAX = 8.0;           // the enclosure is only used for |h| <= JET_AMAX (binomial, poisson)
 constexpr double JET_EPS = 1.1102230246251565e-16;   // 2^-53
-constexpr double JET_CROUND = 64.0;        // rounding allowance of one accumulated moment, in units of eps * sum|terms|
+constexpr double JET_CROUND = 256.0;       // rounding allowance of one accumulated moment, in units of eps * sum|terms|
 
 // sup_t |softplus^(k)(t)|, k = 1..8, rounded up (tools/gen_math_tables.py prints them; polynomial in sigmoid)
 __device__ __constant__ double JET_G[9] = {0.0, 1.0, 0.25, 0.0962250449, 0.125, 0.127683922, 0.25, 0.408327759, 1.0625};
@@ -40,8 +44,9 @@ __device__ __constant__ double JET_IFACT[9] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 2
 template <int FAMILY> struct JetRow;
 
 template <> struct JetRow<CGG_GAUSSIAN> {
+    static constexpr unsigned RISK_KEY = 0xffffffffu;
     static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *,
-                                                double (&m)[JET_NV]) {
+                                                double (&m)[JET_NV], unsigned &) {
         // M_0 with the exact pass's own expression (RowPair<GAUSSIAN>::term at delta = 0)
         const double z0 = (y.x - e.x) * inv_sd, z1 = (y.y - e.y) * inv_sd;
         m[0] += -0.5 * fma(z0, z0, z1 * z1);
@@ -53,81 +58,80 @@ template <> struct JetRow<CGG_GAUSSIAN> {
         m[4] += az0 + az1;
         m[5] += ae0 + ae1;
     }
-    static __device__ __forceinline__ void add1(double y, double e, double xs, double inv_sd, const double2 *, double (&m)[JET_NV]) {
+    static __device__ __forceinline__ void add1(double y, double e, double xs, double inv_sd, const double2 *, double (&m)[JET_NV], unsigned &) {
         const double z = (y - e) * inv_sd, g = xs * inv_sd;
         m[0] += -0.5 * z * z; m[1] += g * z; m[2] -= g * g;
         m[3] += fabs(z) * fabs(e); m[4] += fabs(z); m[5] += fabs(e);
     }
 };
 
-// binomial-logit: l(t) = y t - softplus(t); l' = y - s, l^(k) = -softplus^(k) (k >= 2), all polynomials in
-// s = sigmoid(t): with v = s(1-s), u = 1-2s:  sp2 = v, sp3 = v u, sp4 = v(1-6v), sp5 = v u (1-12v),
-// sp6 = v(1-30v+120v^2), sp7 = v u (1-60v+360v^2).  One exp(-|t|) feeds both the softplus (M_0, same code as
-// softplus2) and the sigmoid: 1/(1+T) = tab.x / (1+w) with the log1p split T = c + w(1+c), |w| <= 1/64.
-struct BinomJetPieces { double sp, s, v, u; };
-__device__ __forceinline__ BinomJetPieces binom_pieces(double sarg /* +-eta as softplus2 gets it */, double eta, const double2 *tab) {
-    const double SHIFT = 6755399441055744.0;
-    double a = fabs(sarg);
-    a = (a > 30.0) ? kLogitClampEta : a;
-    const double kd = fma(-a, 1.4426950408889634, SHIFT);
-    const double kf = kd - SHIFT;
-    double r = fma(kf, -6.93147180369123816490e-01, -a);
-    r = fma(kf, -1.90821492927058770002e-10, r);
-    const double p = poly_exp(r);
-    const double T = __hiloint2double(__double2hiint(p) + (__double2loint(kd) << 20), __double2loint(p));   // exp(-a)
-    const double md = fma(T, (double)L1P_N, SHIFT);
-    int mi = __double2loint(md);
-    mi = min(max(mi, 0), L1P_N);
-    const double2 tb = tab[mi];
-    const double w = fma(md - SHIFT, -1.0 / L1P_N, T) * tb.x;
-    const double w2 = w * w;
-    const double q = poly_l1p_q(w, w2);
-    const double l1p = tb.y + fma(w2, q, w);
-    BinomJetPieces o;
-    o.sp = ((sarg > 0.0) ? a : 0.0) + l1p;
-    // 1/(1+w): (1-w)(1+w^2) then two Newton steps (error w^4 -> w^8 -> w^16)
-    const double omw = 1.0 - w, opw = 1.0 + w;
-    double rr = fma(w2, omw, omw);
-    rr = fma(rr, fma(-opw, rr, 1.0), rr);
-    rr = fma(rr, fma(-opw, rr, 1.0), rr);
-    rr *= tb.x;                                   // 1/(1+T) = sigmoid(a)
-    const double sneg = T * rr;                   // sigmoid(-a)
-    o.s = (eta > 0.0) ? rr : sneg;                // sigmoid(eta)
-    o.v = sneg * rr;                              // s (1 - s)
-    const double ua = (1.0 - T) * rr;             // |1 - 2 s|
-    o.u = (eta > 0.0) ? -ua : ua;
-    return o;
-}
-
+// binomial-logit: l(t) = y t - softplus(t).  Everything is evaluated at a = |eta| >= 0 with ONE exp(-a):
+//   M_0 term  -softplus(s), s = +-eta by y (the exact passes' own expression: relu(s) + log1p(exp(-a)));
+//   l'(eta)   = y - sigmoid(eta) = (y - 1/2) - sign(eta) ua / 2,         ua = 2 sigmoid(a) - 1 = tanh(a/2) >= 0;
+//   l^(k)(eta) = -sign(eta)^k sp^(k)(a) for k >= 2 (sp2 is even, sp3 odd, ...), polynomials in v = s(1-s) and ua:
+//       sp2 = v, sp3 = -v ua, sp4 = v(1-6v), sp5 = -v ua (1-12v), sp6 = v(1-30v+120v^2), sp7 = -v ua (1-60v+360v^2).
+// With xh = sign(eta) * xs (a sign-bit XOR) the pass accumulates the all-positive-form sums
+//   m1 = sum xh ua, m2 = sum xh^2 v, m3 = sum xh^3 v ua, m4 = sum xh^4 v(1-6v), ...      and jet_eval() forms
+//   M_1 = C1 - m1/2 (C1 = sum xs (y - 1/2), a per-column constant), M_2 = -m2, M_3 = +m3, M_4 = -m4, M_5 = +m5, ...
+// No fp64 select or compare besides the clamp: signs are handled on the high words with integer logic, which
+// runs on the ALU pipe while the fp64 pipe is the bottleneck.  1/(1+T) = tab.x / (1+w) with the log1p split
+// T = c + w (1+c), |w| <= 1/64: (1-w)(1+w^2) and one Newton step (absolute error < 4e-15, inside JET_CROUND).
 template <> struct JetRow<CGG_BINOMIAL> {
-    static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *tab, double (&m)[JET_NV]) {
-        const double sarg = (y > 0.5) ? -e : e;
-        const BinomJetPieces b = binom_pieces(sarg, e, tab);
-        m[0] -= b.sp;
-        const double q2 = -b.v, qu = q2 * b.u;
-        const double a4 = fma(-6.0, b.v, 1.0), a5 = fma(-12.0, b.v, 1.0);
-        const double a6 = fma(fma(120.0, b.v, -30.0), b.v, 1.0), a7 = fma(fma(360.0, b.v, -60.0), b.v, 1.0);
-        const double x2 = xs * xs, x3 = x2 * xs, x4 = x2 * x2, x5 = x4 * xs, x6 = x3 * x3, x7 = x6 * xs;
-        m[1] = fma(xs, y - b.s, m[1]);
-        m[2] = fma(x2, q2, m[2]);
-        m[3] = fma(x3, qu, m[3]);
-        m[4] = fma(x4, q2 * a4, m[4]);
-        m[5] = fma(x5, qu * a5, m[5]);
-        m[6] = fma(x6, q2 * a6, m[6]);
-        m[7] = fma(x7, qu * a7, m[7]);
-        const double ae = fabs(e);
-        m[8] += ae;
-        m[9] += (fma(fabs(xs), JET_AMAX, ae) >= 29.9) ? 1.0 : 0.0;
+    static constexpr unsigned RISK_KEY = 0x4035e666u;     // |eta| >= 21.9: the clamp at |eta| = 30 is within JET_AMAX
+    static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
+        const double SHIFT = 6755399441055744.0;
+        const int he = __double2hiint(e);
+        const int hs = he ^ ((__double2hiint(y) << 2) & 0x80000000);        // sign of s = (y == 1) ? -eta : eta
+        risk = max(risk, (unsigned)he & 0x7fffffffu);                       // max |eta| (high word): checked against 21.9 at the end
+        double a = fabs(e);
+        a = (a > 30.0) ? kLogitClampEta : a;
+        const double kd = fma(-a, 1.4426950408889634, SHIFT);
+        const double kf = kd - SHIFT;
+        double r = fma(kf, -6.93147180369123816490e-01, -a);
+        r = fma(kf, -1.90821492927058770002e-10, r);
+        const double p = poly_exp(r);
+        const double T = __hiloint2double(__double2hiint(p) + (__double2loint(kd) << 20), __double2loint(p));   // exp(-a)
+        const double md = fma(T, (double)L1P_N, SHIFT);
+        int mi = __double2loint(md);
+        mi = min(max(mi, 0), L1P_N);
+        const double2 tb = tab[mi];
+        const double w = fma(md - SHIFT, -1.0 / L1P_N, T) * tb.x;
+        const double w2 = w * w;
+        const double q = poly_l1p_q(w, w2);
+        const double l1p = tb.y + fma(w2, q, w);
+        const int keep = ~(hs >> 31);                                        // all ones iff s >= 0
+        const double relu = __hiloint2double(__double2hiint(a) & keep, __double2loint(a) & keep);
+        m[0] -= relu + l1p;
+        const double omw = 1.0 - w;
+        double rr = fma(w2, omw, omw);
+        rr = fma(rr, fma(-(1.0 + w), rr, 1.0), rr);
+        rr *= tb.x;                                                          // sigmoid(a)
+        const double v = fma(-rr, rr, rr);                                   // s(1-s), absolute error ~eps
+        const double ua = fma(2.0, rr, -1.0);                                // 2 sigmoid(a) - 1
+        const double xh = __hiloint2double(__double2hiint(xs) ^ (he & 0x80000000), __double2loint(xs));
+        const double vu = v * ua;
+        const double x2 = xh * xh, x3 = x2 * xh, x4 = x2 * x2, x5 = x4 * xh;
+        m[1] = fma(xh, ua, m[1]);
+        m[2] = fma(x2, v, m[2]);
+        m[3] = fma(x3, vu, m[3]);
+        m[4] = fma(x4, v * fma(-6.0, v, 1.0), m[4]);
+        m[5] = fma(x5, vu * fma(-12.0, v, 1.0), m[5]);
+#if CGG_JET_D >= 7
+        const double x6 = x3 * x3, x7 = x6 * xh;
+        m[6] = fma(x6, v * fma(fma(120.0, v, -30.0), v, 1.0), m[6]);
+        m[7] = fma(x7, vu * fma(fma(360.0, v, -60.0), v, 1.0), m[7]);
+#endif
     }
-    static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV]) {
-        add1(y.x, e.x, xs.x, inv_sd, tab, m);
-        add1(y.y, e.y, xs.y, inv_sd, tab, m);
+    static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
+        add1(y.x, e.x, xs.x, inv_sd, tab, m, risk);
+        add1(y.y, e.y, xs.y, inv_sd, tab, m, risk);
     }
 };
 
 // poisson-log: l(t) = y t - exp(t) (- lgamma(y+1), per-dataset constant); l' = y - mu, l^(k) = -mu for k >= 2.
 template <> struct JetRow<CGG_POISSON> {
-    static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *, double (&m)[JET_NV]) {
+    static constexpr unsigned RISK_KEY = 0xc03be666u;     // eta <= -27.9: the pmax(., eps) clamp at -36.04 is within JET_AMAX
+    static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *, double (&m)[JET_NV], unsigned &risk) {
         const double l = (e < kLogEps) ? kLogEps : e;
         const double mu = exp(l);
         m[0] += (mu > 1.7976931348623157e308) ? -INFINITY : fma(y, l, -mu);      // row_term<POISSON>
@@ -142,11 +146,11 @@ template <> struct JetRow<CGG_POISSON> {
         m[7] = fma(fabs(x7), mu, m[7]);
         const double ae = fabs(e);
         m[8] = fma(fabs(y) + mu, ae + 1.0, m[8]);
-        m[9] += (fma(-fabs(xs), JET_AMAX, e) <= kLogEps + 0.1) ? 1.0 : 0.0;
+        risk = max(risk, (unsigned)__double2hiint(e));                     // most negative eta (high word): checked against -27.9
     }
-    static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV]) {
-        add1(y.x, e.x, xs.x, inv_sd, tab, m);
-        add1(y.y, e.y, xs.y, inv_sd, tab, m);
+    static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
+        add1(y.x, e.x, xs.x, inv_sd, tab, m, risk);
+        add1(y.y, e.y, xs.y, inv_sd, tab, m, risk);
     }
 };
 
@@ -171,17 +175,21 @@ __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV]
         return f;
     }
     if (family == CGG_BINOMIAL) {
-        double f = m[7] * JET_IFACT[7];
+        constexpr int D = CGG_JET_D;
+        // signed moments from the positive-form sums: M_1 = C1 - m1/2, M_k = (-1)^(k+1) m_k
+        double f = m[D] * JET_IFACT[D];                       // D odd: + sign
 #pragma unroll
-        for (int k = 6; k >= 1; --k) f = fma(f, h, m[k] * JET_IFACT[k]);
+        for (int k = D - 1; k >= 2; --k) f = fma(f, h, ((k & 1) ? m[k] : -m[k]) * JET_IFACT[k]);
+        f = fma(f, h, fma(-0.5, m[1], cst[11]));
         f = fma(f, h, m[0]);
-        // remainder: G_8 S_8 a^8 / 8!;  moment k: rounding <= ce G_k S_k (terms are bounded by |xs|^k G_k)
+        // remainder: G_(D+1) S_(D+1) a^(D+1) / (D+1)!;  moment k: rounding <= ce G_k S_k (terms are bounded by |xs|^k G_k)
         double pw = a, bmom = fabs(m[0]);
 #pragma unroll
-        for (int k = 1; k <= 7; ++k) { bmom = fma(JET_G[k] * JET_IFACT[k] * cst[1 + k], pw, bmom); pw *= a; }
-        const double bt = JET_G[8] * JET_IFACT[8] * cst[9] * pw;
-        // exact pass: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|); softplus and sums relative to |f|
-        const double bex = JET_EPS * (m[8] + 2.0 * a * cst[2]) + ce * (fabs(f) + bt);
+        for (int k = 1; k <= D; ++k) { bmom = fma(JET_G[k] * JET_IFACT[k] * cst[1 + k], pw, bmom); pw *= a; }
+        const double bt = JET_G[D + 1] * JET_IFACT[D + 1] * cst[2 + D] * pw;
+        // exact pass: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|) with every |eta| < 21.9 (else
+        // m[9] != 0); softplus and sums relative to |f|
+        const double bex = JET_EPS * (21.9 * n + 2.0 * a * cst[2]) + ce * (fabs(f) + bt);
         B = 1.01 * (bt + ce * bmom + bex);
         if (!(a <= JET_AMAX) || m[9] != 0.0) B = INFINITY;
         return f;

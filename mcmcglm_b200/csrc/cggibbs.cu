@@ -56,8 +56,10 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             a = __shfl_sync(0xffffffffu, a, 0);
             if (a < (v + 1) * (unsigned long long)d.G) continue;   // pass #v still has CTAs streaming
             fence_gpu();
+            const long long td0 = d.prof ? clock64() : 0;
             const bool fin = decide_chain(dp, c, lane, -1, false);
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
+            if (d.prof && lane == 0) { atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL); }
             progressed = true;
         }
         if (all_fin) break;
@@ -376,9 +378,16 @@ __global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial,
 }
 
 // Per-column statistics for the jet passes (cgg_jet.cuh), one CTA per column: cs = 2^-e with max|x| * cs in [0.5, 1)
-// (exact scaling), S_k = sum_i |x_i cs|^k for k = 1..8 rounded UP (they enter error bounds), max|x|.
-__global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, int64_t n, int64_t ldx, int64_t p, double *out) {
-    __shared__ double s_red[NWARPS][8];
+// (exact scaling), S_k = sum_i |x_i cs|^k for k = 1..8 rounded UP (they enter error bounds), max|x|, and for the
+// binomial family C1 = sum_i x_i cs (y_i - 1/2) with compensated (two-sum) accumulation.
+__device__ __forceinline__ void two_sum_acc(double &s, double &c, double v) {
+    const double t = s + v;
+    const double bp = t - s;
+    c += (s - (t - bp)) + (v - bp);
+    s = t;
+}
+__global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, const double *y, int family, int64_t n, int64_t ldx, int64_t p, double *out) {
+    __shared__ double s_red[NWARPS][10];
     __shared__ double s_cs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {
@@ -397,25 +406,40 @@ __global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, int
             if (m > 0.0 && m < INFINITY) { frexp(m, &e); cs = ldexp(1.0, -e); }
             if (!(cs > 0.0) || !(cs < INFINITY)) cs = 1.0;      // subnormal / huge columns: no scaling (the bounds then simply fail to decide)
             s_cs = cs;
-            out[j * CS_STRIDE + 0] = cs; out[j * CS_STRIDE + 1] = 1.0 / cs; out[j * CS_STRIDE + 10] = m; out[j * CS_STRIDE + 11] = 0.0;
+            out[j * CS_STRIDE + 0] = cs; out[j * CS_STRIDE + 1] = 1.0 / cs; out[j * CS_STRIDE + 10] = m;
         }
         __syncthreads();
         const double cs = s_cs;
         double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double c1s = 0.0, c1c = 0.0;
         for (int64_t i = threadIdx.x; i < n; i += THREADS) {
-            const double a = fabs(x[i]) * cs;
+            const double xs = x[i] * cs;
+            const double a = fabs(xs);
             double pw = a;
 #pragma unroll
             for (int k = 0; k < 8; ++k) { S[k] += pw; pw *= a; }
+            if (family == CGG_BINOMIAL) two_sum_acc(c1s, c1c, xs * (y[i] - 0.5));     // y - 1/2 = +-1/2: the product is exact
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) { S[k] = warp_sum(S[k]); if (lane == 0) s_red[warp][k] = S[k]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double s2 = __shfl_xor_sync(0xffffffffu, c1s, o), c2 = __shfl_xor_sync(0xffffffffu, c1c, o);
+            c1c += c2;
+            two_sum_acc(c1s, c1c, s2);
+        }
+        if (lane == 0) { s_red[warp][8] = c1s; s_red[warp][9] = c1c; }
         __syncthreads();
         if (threadIdx.x < 8) {
             double v = 0.0;
             for (int w = 0; w < NWARPS; ++w) v += s_red[w][threadIdx.x];
             // fp64 summation of n non-negative terms: relative error <= n * 2^-53; inflate so the value is an upper bound
             out[j * CS_STRIDE + 2 + threadIdx.x] = v * (1.0 + 4.0 * (double)n * 1.1102230246251565e-16 + 1e-12);
+        }
+        if (threadIdx.x == 8) {
+            double ss = 0.0, cc = 0.0;
+            for (int w = 0; w < NWARPS; ++w) { cc += s_red[w][9]; two_sum_acc(ss, cc, s_red[w][8]); }
+            out[j * CS_STRIDE + 11] = ss + cc;
         }
         __syncthreads();
     }
@@ -706,7 +730,7 @@ static int finish_set_data(cgg_handle *h) {
     else d.ll_const = 0.0;
     if (d.jet) {
         const int grid = (int)std::min<int64_t>(d.p, 4 * (int64_t)h->num_sms);
-        col_stats_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.n, d.ldx, d.p, h->colstat_dev);
+        col_stats_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.y, d.family, d.n, d.ldx, d.p, h->colstat_dev);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -947,6 +971,8 @@ extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K,
     memset(ctl.data(), 0, sizeof(Ctl) * d.C);
     for (int c = 0; c < d.C; ++c) ctl[c].commit_j = -1;
     ctl[chain].j = (int32_t)j; ctl[chain].ncand = 0; ctl[chain].coarse_mask = (int32_t)JET_BIT;
+    CK(cudaMemcpyAsync(&ctl[chain].cscale, h->colstat_dev + j * CS_STRIDE, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpyAsync(saved.data(), d.ctl, sizeof(Ctl) * d.C, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(d.ctl, ctl.data(), sizeof(Ctl) * d.C, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->scratch_dev, cand_host, sizeof(double) * K, cudaMemcpyHostToDevice, h->stream));
@@ -1067,8 +1093,8 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
     if (want_prof) {
-        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 64));
-        CK(cudaMemsetAsync(h->prof_dev, 0, 64, h->stream));
+        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 128));
+        CK(cudaMemsetAsync(h->prof_dev, 0, 128, h->stream));
     }
     d.prof = want_prof ? h->prof_dev : nullptr;
 
@@ -1111,11 +1137,12 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         fprintf(stderr, "[cgg profile] slice-width estimate shat: mean %.4g min %.4g max %.4g (%d set)\n", cnt ? m / cnt : 0.0, mn, mx, cnt);
     }
     if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT) {
-        unsigned long long pr[8];
-        CK(cudaMemcpy(pr, h->prof_dev, 64, cudaMemcpyDeviceToHost));
+        unsigned long long pr[16];
+        CK(cudaMemcpy(pr, h->prof_dev, 128, cudaMemcpyDeviceToHost));
         const double nw = pr[6] ? (double)pr[6] : 1.0;
         fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-passes/worker %.1f workers %llu\n",
                 ms, pr[0] / nw, pr[1] / nw, pr[3] / nw, pr[2] / nw, pr[5] / nw, pr[4] / nw, pr[6]);
+        fprintf(stderr, "[cgg profile] decisions %llu, mean cycles per decision %.0f\n", pr[8], pr[8] ? (double)pr[7] / (double)pr[8] : 0.0);
     }
 
     CK(cudaMemcpy(&hdr, d.hdr, sizeof hdr, cudaMemcpyDeviceToHost));
