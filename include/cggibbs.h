@@ -64,6 +64,8 @@ enum {
 #define CGG_FLAG_NO_PREFILTER 1 /* score every candidate in fp64 (the fp32 pre-filter never changes results, only cost) */
 #define CGG_FLAG_NO_JET 2       /* decide every candidate from an exact pass over the rows (jet passes never change
                                    results, only cost: one pass per update instead of one per few candidates) */
+#define CGG_FLAG_NO_JET_LIGHT 4 /* binomial: every jet pass also evaluates the exact f(x0) (light passes skip it because
+                                   the slice tests only involve differences f(v) - f(x0); never changes results) */
 
 typedef struct cgg_config {
     int32_t abi_version; /* must be CGG_ABI_VERSION */
@@ -106,6 +108,7 @@ typedef struct cgg_stats {
     uint64_t coarse_undecided; /* passes that ended on a pre-filtered candidate the error bound could not decide */
     uint64_t jet_passes;     /* (chain, pass) pairs that were jet passes (subset of chain_passes) */
     uint64_t jet_fallbacks;  /* updates a jet pass could not finish: exact passes took over from that point */
+    uint64_t jet_retries;    /* light jet passes (binomial) that were repeated as full jet passes */
 } cgg_stats;
 
 typedef struct cgg_handle cgg_handle;
@@ -174,9 +177,10 @@ int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plus_abs_s, do
 /* Diagnostic: runs one jet pass of chain `chain` along column j (no state change) and evaluates its enclosure at K
  * (<= CGG_KMAX) values of new_beta_j: value[k] = surrogate log-LIKELIHOOD (per-dataset constant included, prior
  * excluded), bound[k] = the error bound the decider uses (Inf: enclosure not applicable), sums[CGG_KMAX + 2] = the
- * pass's raw sums (nullable).  Used by the tests that check the bound against exact evaluations. */
-int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host, double *value_host,
-                  double *bound_host, double *sums_host);
+ * pass's raw sums (nullable).  light != 0 (binomial only): a light pass; value[k] is then the log-likelihood
+ * DIFFERENCE to the current point.  Used by the tests that check the bound against exact evaluations. */
+int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, int32_t light, const double *cand_host,
+                  double *value_host, double *bound_host, double *sums_host);
 
 int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
 

@@ -16,6 +16,7 @@ DRIVER_PERSISTENT, DRIVER_STEPWISE = 0, 1
 MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 FLAG_NO_PREFILTER = 1
 FLAG_NO_JET = 2
+FLAG_NO_JET_LIGHT = 4
 JET_NV = KMAX + 2
 
 # every symbol include/cggibbs.h declares
@@ -40,7 +41,8 @@ class Stats(C.Structure):
                 ("commit_passes", C.c_uint64), ("cand_evals", C.c_uint64), ("ref_evals", C.c_uint64),
                 ("stepouts", C.c_uint64), ("shrinks", C.c_uint64), ("launches", C.c_uint64),
                 ("sweep_ms", C.c_double), ("algorithmic_bytes", C.c_double), ("coarse_evals", C.c_uint64),
-                ("coarse_undecided", C.c_uint64), ("jet_passes", C.c_uint64), ("jet_fallbacks", C.c_uint64)]
+                ("coarse_undecided", C.c_uint64), ("jet_passes", C.c_uint64), ("jet_fallbacks", C.c_uint64),
+                ("jet_retries", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -87,7 +89,7 @@ def load():
     L.cgg_nccl_unique_id.argtypes = [C.c_char_p]
     L.cgg_comm_init_nccl.argtypes = [vp, i32, i32, C.c_char_p]
     L.cgg_debug_coarse_error.argtypes = [i32, dp, dp]
-    L.cgg_debug_jet.argtypes = [vp, i32, i64, i32, dp, dp, dp, dp]
+    L.cgg_debug_jet.argtypes = [vp, i32, i64, i32, i32, dp, dp, dp, dp]
     L.cgg_debug_row_terms.argtypes = [i32, i32, i64, dp, dp, C.c_double, dp]
     L.cgg_stream.argtypes = [vp]
     L.cgg_stream.restype = vp

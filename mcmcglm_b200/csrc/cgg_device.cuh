@@ -32,6 +32,7 @@ constexpr int RING_BYTES_PER_WARP = RING_D * RING_OPS * 32 * 16;
 enum Phase : int32_t { PH_START = 0, PH_STEPOUT = 1, PH_SHRINK = 2, PH_FLUSH = 3, PH_FINISHED = 4, PH_JET = 5 };
 static_assert(JET_NV == NV, "a jet pass delivers through the same accumulators as a candidate pass");
 constexpr unsigned JET_BIT = 0x80000000u;   // Ctl::coarse_mask: this pass is a jet pass (cgg_jet.cuh), ncand = 0
+constexpr unsigned JET_FULL = 0x40000000u;  // ... that also delivers the exact M_0 (always, except binomial light passes)
 
 // What every worker needs to know about a chain for its coming pass.  12 x 8 bytes.
 struct __align__(16) Ctl {
@@ -82,7 +83,7 @@ struct __align__(16) ChainState {
     uint64_t cursor;    // uniforms consumed before this update
     uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
     uint64_t coarse_evals, coarse_undecided;
-    uint64_t jet_passes, jet_fallbacks;
+    uint64_t jet_passes, jet_fallbacks, jet_retries, pad2;
 };
 static_assert(sizeof(ChainState) % 16 == 0, "ChainState is copied with 128-bit accesses");
 
@@ -105,7 +106,7 @@ struct Dev {
     int64_t max_steps;
     double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale;
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, pad_;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -311,7 +312,7 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
 
 // One warp, one chain, one JET pass (cgg_jet.cuh): applies the pending eta update like any pass and accumulates
 // the exact log-likelihood at the committed eta plus the derivative moments along column j in registers.
-template <int FAMILY>
+template <int FAMILY, bool FULL>
 __device__ __forceinline__ void jet_tile(const ChainStream &cs, double cdelta, double cscale, double inv_sd, int stage, double *eta_i,
                                          const double2 *tab, double (&m)[NV], unsigned &risk) {
     const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
@@ -324,10 +325,10 @@ __device__ __forceinline__ void jet_tile(const ChainStream &cs, double cdelta, d
     }
     double2 xs = lds2(s + 1024u);
     xs.x *= cscale; xs.y *= cscale;           // power of two: exact
-    JetRow<FAMILY>::add2(lds2(s + 512u), e, xs, inv_sd, tab, m, risk);
+    JetRow<FAMILY>::template add2<FULL>(lds2(s + 512u), e, xs, inv_sd, tab, m, risk);
 }
 
-template <int FAMILY>
+template <int FAMILY, bool FULL>
 __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &cs, double cdelta, double cscale, int lane,
                                               const double2 *tab, bool prefetched, double (&m)[NV]) {
     const int cj = cs.cj;
@@ -359,7 +360,7 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
             cp_async_commit();
             cp_async_wait<RING_D - 1>();
             double *ecur = const_cast<double *>(pe) - (RING_D - 1) * step;
-            if (ecur < pe_last) jet_tile<FAMILY>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk);
+            if (ecur < pe_last) jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk);
             stage = (stage + 1) & (RING_D - 1);
         }
     }
@@ -370,7 +371,7 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
         if (Tl % cs.W == cs.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
             double e = __ldcg(eta + t);
             if (cj >= 0) { e = eta_shift(e, __ldg(cs.xc + t), cdelta); eta[t] = e; }
-            JetRow<FAMILY>::add1(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m, risk);
+            JetRow<FAMILY>::template add1<FULL>(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m, risk);
         }
     }
     if (FAMILY != CGG_GAUSSIAN) m[9] = (risk >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
@@ -399,7 +400,8 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
         {
             const long long t0 = t_tiles ? clock64() : 0;
             const ChainStream cs(d, c, cw, wid, W, lane, ring);
-            warp_pass_jet<FAMILY>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
+            if (FAMILY != CGG_BINOMIAL || (cmask & JET_FULL)) warp_pass_jet<FAMILY, true>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
+            else warp_pass_jet<FAMILY, false>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
             if (t_tiles) *t_tiles += clock64() - t0;
         }
         if (next_cw) {
@@ -684,17 +686,26 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
 // The whole slice_stepping_out update of coordinate s.j from the sums of ONE jet pass (cgg_jet.cuh).  Run by all 32
 // lanes with the chain state replicated (every lane performs the same scalar updates); lanes evaluate different
 // candidates: stepping-out tests L, L-w, ... (lanes 0..15) and R, R+w, ... (lanes 16..31), then 32 shrink proposals.
-// Each candidate's exact log-potential is enclosed as [f_lo, f_hi]; "inside the slice" needs ylev < f_lo, "outside"
-// needs f_hi <= ylev.  The sequence is consumed while the verdicts are certain.  Returns true when the update was
-// accepted.  Otherwise s.phase is PH_STEPOUT / PH_SHRINK with the bracket, budgets, counters and consumed draws
-// exactly as the reference algorithm has them at that point, and the exact passes take over from there.
-__device__ __forceinline__ bool jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV],
-                                           double x0, double shat_j, double &x1_out, double &shat_out) {
+// The reference's test `y < f(v)` with y = log(u) + f(x0) is decided from an enclosure of f(v) (full pass: M_0 is
+// the exact f(x0)) or of the difference f(v) - f(x0) (light pass: M_0 cancels, the test reads log(u) < f(v) - f(x0));
+// "inside the slice" and "outside" both need the comparison to hold with the enclosure's margin.  The sequence is
+// consumed while the verdicts are certain.
+//   JET_ACCEPTED  the update was accepted
+//   JET_EXACT     (full passes) s.phase is PH_STEPOUT / PH_SHRINK with the bracket, budgets, counters and consumed
+//                 draws exactly as the reference algorithm has them at that point: the exact passes take over from there
+//   JET_RETRY     (light passes) some test was not certain: the caller discards every change made here and asks for a
+//                 full jet pass of the same coordinate
+enum JetOutcome : int { JET_EXACT = 0, JET_ACCEPTED = 1, JET_RETRY = 2 };
+__device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV], bool light,
+                                          double x0, double shat_j, double &x1_out, double &shat_out) {
     s.npass++; s.jet_passes++;
     if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
     ct.coarse_mask = 0;
-    if (!(fabs(m[0]) < INFINITY)) { s.status = CGG_E_NAN; return false; }     // f(x0) itself is not finite
-    s.fx0 = (m[0] + d.ll_const) + s.prior_sum;       // the reference's first evaluation, f(x0), at the committed eta
+    if (!light) {
+        if (!(fabs(m[0]) < INFINITY)) { s.status = CGG_E_NAN; return JET_EXACT; }     // f(x0) itself is not finite
+        s.fx0 = (m[0] + d.ll_const) + s.prior_sum;   // the reference's first evaluation, f(x0), at the committed eta
+    }
+    const double fmag = light ? fabs(s.fx0) + 1.0 : fabs(m[0]);
     const double *cst = d.colstat + (int64_t)s.j * CS_STRIDE;
     // ---- uniforms: 2 (3 with a finite max) start draws + up to 32 shrink draws
     double uA = 0.5, uB = 0.5;
@@ -707,22 +718,33 @@ __device__ __forceinline__ bool jet_decide(const Dev &d, int c, int lane, ChainS
 #pragma unroll
     for (int i = 0; i < 3; ++i) U3[i] = __shfl_sync(0xffffffffu, uA, i);
     start_coordinate(d, s, x0, U3, nAvail < 3 ? nAvail : 3);
-    if (s.status != CGG_OK) return false;
+    if (s.status != CGG_OK) return JET_EXACT;
+    const double logu = log(U3[0]);
+    const double prior_x0 = prior_logdens(d.prior, s.x0);
     const int sidx = base + lane;                     // this lane's shrink draw
     const double usA = __shfl_sync(0xffffffffu, uA, sidx & 31), usB = __shfl_sync(0xffffffffu, uB, sidx & 31);
     const double us = (sidx < 32) ? usA : usB;
     const bool us_ok = sidx < nAvail;
     const double bscale = d.jet_bscale;
-    // enclosure of f at candidate v (same expression order as the exact path: ll + ll_const, then + prior)
-    auto verdict = [&](double v, bool &in, bool &out, double &fmid) {
+    // verdict on candidate v; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
+    auto verdict = [&](double v, bool &in, bool &out, double &fnew) {
         double B;
-        const double ll = jet_eval(d.family, m, cst, (double)d.n, d.inv_sd, __dadd_rn(v, -s.x0), B);
-        B = B * bscale + 4.0 * JET_EPS * fabs(ll);    // + the rounding of ll -+ B itself
-        const double pr = s.prior_rest + prior_logdens(d.prior, v);
-        const double flo = ((ll - B) + d.ll_const) + pr, fhi = ((ll + B) + d.ll_const) + pr;
-        fmid = (ll + d.ll_const) + pr;
-        in = s.ylev < flo;
-        out = fhi <= s.ylev;
+        const double dl = jet_eval(d.family, m, cst, (double)d.n, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B);
+        B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
+        if (light) {
+            const double t = dl + (prior_logdens(d.prior, v) - prior_x0);
+            fnew = s.fx0 + t;
+            in = logu + B < t;
+            out = t + B <= logu;
+        } else {
+            // same expression order as the exact path: (ll + ll_const) + (prior_rest + prior(v)), monotone in ll
+            const double ll = m[0] + dl;
+            const double pr = s.prior_rest + prior_logdens(d.prior, v);
+            const double flo = ((ll - B) + d.ll_const) + pr, fhi = ((ll + B) + d.ll_const) + pr;
+            fnew = (ll + d.ll_const) + pr;
+            in = s.ylev < flo;
+            out = fhi <= s.ylev;
+        }
     };
     if (s.phase == PH_STEPOUT) {
         const bool left = lane < 16;
@@ -754,7 +776,11 @@ __device__ __forceinline__ bool jet_decide(const Dev &d, int c, int lane, ChainS
             } else s.openR = 0;
         }
         s.pexp = 0.9 * s.pexp + (expanded ? 0.1 : 0.0);
-        if (s.openL || s.openR) { s.jet_fallbacks++; return false; }     // a test the enclosure could not decide
+        if (s.openL || s.openR) {                    // a test the enclosure could not decide
+            if (light) return JET_RETRY;
+            s.jet_fallbacks++;
+            return JET_EXACT;
+        }
         s.phase = PH_SHRINK;
     }
     // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }: the proposals depend on (L, R, x0, u) only
@@ -770,22 +796,24 @@ __device__ __forceinline__ bool jet_decide(const Dev &d, int c, int lane, ChainS
     const unsigned mout = __ballot_sync(0xffffffffu, out);
     const int k = (mout == 0xffffffffu) ? 32 : __ffs(~mout) - 1;      // first proposal that is not certainly rejected
     if (k == 32) {
+        if (light) return JET_RETRY;
         s.shrinks += 32; s.ref_evals += 32; s.sdrawn = 32; s.L = l; s.R = r;
         s.jet_fallbacks++;
-        return false;
+        return JET_EXACT;
     }
     const bool kin = __shfl_sync(0xffffffffu, (int)in, k);
     s.L = __shfl_sync(0xffffffffu, li, k); s.R = __shfl_sync(0xffffffffu, ri, k);   // the bracket proposal k was drawn from
     s.shrinks += k; s.ref_evals += k;
     if (!kin) {                 // undecided (or its draw is not available): the exact passes continue from proposal k
+        if (light) return JET_RETRY;
         s.sdrawn = k;
         s.jet_fallbacks++;
-        return false;
+        return JET_EXACT;
     }
     s.shrinks++; s.ref_evals++;
     const double x1 = __shfl_sync(0xffffffffu, xi, k), f1 = __shfl_sync(0xffffffffu, fm, k);
     accept_value(d, c, s, ct, x1, f1, shat_j, k + 1, lane == 0, x1_out, shat_out);
-    return true;
+    return JET_ACCEPTED;
 }
 
 // One warp decides one chain after every worker's contribution to the pass is visible.
@@ -844,10 +872,20 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     for (int k = 0; k < KMAX; ++k) F[k] = __shfl_sync(0xffffffffu, f, k);
     s.passes++;
     double x0 = beta_j, shat = shat_j;     // values of the coordinate that is sampled next
+    bool retry_full = false;
     if (jetpass) {
         double x1 = 0.0, sh1 = 0.0;
-        if (jet_decide(d, c, lane, s, ct, jm, beta_j, shat_j, x1, sh1)) {
+        const bool light = ((unsigned)ct.coarse_mask & JET_FULL) == 0u;
+        const int oc = jet_decide(d, c, lane, s, ct, jm, light, beta_j, shat_j, x1, sh1);
+        if (oc == JET_ACCEPTED) {
             if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }
+        } else if (oc == JET_RETRY) {
+            // a light pass left a test undecided: forget everything it changed, keep only the facts of the pass itself
+            // (the pending eta update has been applied), and ask for a full jet pass of the same coordinate
+            s = d.cs[c]; ct = d.ctl[c];
+            s.npass++; s.jet_passes++; s.jet_retries++;
+            if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
+            retry_full = true;
         }
     } else if (lane == 0 && s.phase != PH_START) {
         double x1 = 0.0, sh1 = 0.0;
@@ -866,11 +904,12 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
         v = warp_sum(v);
         s.prior_sum = v;
     }
-    if (status == CGG_OK && phase == PH_START && d.jet) {
-        // jet mode: the next pass of this chain applies the pending eta update and delivers f(x0) and the derivative
-        // moments along the new column; the whole update is then decided from them
+    if (status == CGG_OK && d.jet && (phase == PH_START || retry_full)) {
+        // jet mode: the next pass of this chain applies the pending eta update and delivers the derivative moments along
+        // the new column (and the exact f(x0) if it is a full pass); the whole update is then decided from them
         if (lane == 0) {
-            ct.j = s.j; ct.ncand = 0; ct.coarse_mask = (int32_t)JET_BIT;
+            const bool full = retry_full || !d.jet_light || d.family != CGG_BINOMIAL;
+            ct.j = s.j; ct.ncand = 0; ct.coarse_mask = (int32_t)(JET_BIT | (full ? JET_FULL : 0u));
             ct.cscale = __ldcg(d.colstat + (int64_t)s.j * CS_STRIDE);
             s.phase = PH_JET; s.chain_passes++;
         }

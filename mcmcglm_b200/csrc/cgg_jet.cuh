@@ -17,7 +17,7 @@
 //
 // Slot layout of the NV values a jet pass delivers:
 //   gaussian : 0..2 M_0..M_2 (exact quadratic, no remainder) | 3 sum|z||eta| | 4 sum|z| | 5 sum|eta|
-//   binomial : 0 M_0 | 1..7 the positive-form sums m_1..m_7 (see JetRow<CGG_BINOMIAL>) | 9 rows with |eta| >= 21.9 (the
+//   binomial : 0 M_0 (full passes only; light passes leave it 0) | 1..7 the positive-form sums m_1..m_7 (see JetRow<CGG_BINOMIAL>) | 9 rows with |eta| >= 21.9 (the
 //              stats logit clamp at |eta| = 30 is then within reach of the enclosure's radius)
 //   poisson  : 0..6 M_0..M_6 | 7 sum|xs|^7 mu | 8 sum(|y| + mu)(|eta| + 1) | 9 rows too close to the pmax(., eps) clamp
 #pragma once
@@ -45,6 +45,7 @@ template <int FAMILY> struct JetRow;
 
 template <> struct JetRow<CGG_GAUSSIAN> {
     static constexpr unsigned RISK_KEY = 0xffffffffu;
+    template <bool FULL>
     static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *,
                                                 double (&m)[JET_NV], unsigned &) {
         // M_0 with the exact pass's own expression (RowPair<GAUSSIAN>::term at delta = 0)
@@ -58,6 +59,7 @@ template <> struct JetRow<CGG_GAUSSIAN> {
         m[4] += az0 + az1;
         m[5] += ae0 + ae1;
     }
+    template <bool FULL>
     static __device__ __forceinline__ void add1(double y, double e, double xs, double inv_sd, const double2 *, double (&m)[JET_NV], unsigned &) {
         const double z = (y - e) * inv_sd, g = xs * inv_sd;
         m[0] += -0.5 * z * z; m[1] += g * z; m[2] -= g * g;
@@ -78,34 +80,46 @@ template <> struct JetRow<CGG_GAUSSIAN> {
 // T = c + w (1+c), |w| <= 1/64: (1-w)(1+w^2) and one Newton step (absolute error < 4e-15, inside JET_CROUND).
 template <> struct JetRow<CGG_BINOMIAL> {
     static constexpr unsigned RISK_KEY = 0x4035e666u;     // |eta| >= 21.9: the clamp at |eta| = 30 is within JET_AMAX
+    // FULL: also the exact M_0 term (softplus through the log1p table, stats' clamp).  Light passes skip it: the slice
+    // decisions only involve differences f(v) - f(x0), in which M_0 cancels; 1/(1+T) then comes from the hardware
+    // reciprocal seed (rcp.approx.ftz.f64, 2^-23) and two Newton steps instead of the table split.
+    template <bool FULL>
     static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
         const double SHIFT = 6755399441055744.0;
         const int he = __double2hiint(e);
-        const int hs = he ^ ((__double2hiint(y) << 2) & 0x80000000);        // sign of s = (y == 1) ? -eta : eta
         risk = max(risk, (unsigned)he & 0x7fffffffu);                       // max |eta| (high word): checked against 21.9 at the end
         double a = fabs(e);
-        a = (a > 30.0) ? kLogitClampEta : a;
+        if (FULL) a = (a > 30.0) ? kLogitClampEta : a;
         const double kd = fma(-a, 1.4426950408889634, SHIFT);
         const double kf = kd - SHIFT;
         double r = fma(kf, -6.93147180369123816490e-01, -a);
         r = fma(kf, -1.90821492927058770002e-10, r);
         const double p = poly_exp(r);
         const double T = __hiloint2double(__double2hiint(p) + (__double2loint(kd) << 20), __double2loint(p));   // exp(-a)
-        const double md = fma(T, (double)L1P_N, SHIFT);
-        int mi = __double2loint(md);
-        mi = min(max(mi, 0), L1P_N);
-        const double2 tb = tab[mi];
-        const double w = fma(md - SHIFT, -1.0 / L1P_N, T) * tb.x;
-        const double w2 = w * w;
-        const double q = poly_l1p_q(w, w2);
-        const double l1p = tb.y + fma(w2, q, w);
-        const int keep = ~(hs >> 31);                                        // all ones iff s >= 0
-        const double relu = __hiloint2double(__double2hiint(a) & keep, __double2loint(a) & keep);
-        m[0] -= relu + l1p;
-        const double omw = 1.0 - w;
-        double rr = fma(w2, omw, omw);
-        rr = fma(rr, fma(-(1.0 + w), rr, 1.0), rr);
-        rr *= tb.x;                                                          // sigmoid(a)
+        double rr;
+        if (FULL) {
+            const int hs = he ^ ((__double2hiint(y) << 2) & 0x80000000);    // sign of s = (y == 1) ? -eta : eta
+            const double md = fma(T, (double)L1P_N, SHIFT);
+            int mi = __double2loint(md);
+            mi = min(max(mi, 0), L1P_N);
+            const double2 tb = tab[mi];
+            const double w = fma(md - SHIFT, -1.0 / L1P_N, T) * tb.x;
+            const double w2 = w * w;
+            const double q = poly_l1p_q(w, w2);
+            const double l1p = tb.y + fma(w2, q, w);
+            const int keep = ~(hs >> 31);                                    // all ones iff s >= 0
+            const double relu = __hiloint2double(__double2hiint(a) & keep, __double2loint(a) & keep);
+            m[0] -= relu + l1p;
+            const double omw = 1.0 - w;
+            rr = fma(w2, omw, omw);
+            rr = fma(rr, fma(-(1.0 + w), rr, 1.0), rr);
+            rr *= tb.x;                                                      // sigmoid(a)
+        } else {
+            const double dd = 1.0 + T;                                       // in (1, 2]
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(dd));
+            rr = fma(rr, fma(-dd, rr, 1.0), rr);
+            rr = fma(rr, fma(-dd, rr, 1.0), rr);
+        }
         const double v = fma(-rr, rr, rr);                                   // s(1-s), absolute error ~eps
         const double ua = fma(2.0, rr, -1.0);                                // 2 sigmoid(a) - 1
         const double xh = __hiloint2double(__double2hiint(xs) ^ (he & 0x80000000), __double2loint(xs));
@@ -122,15 +136,17 @@ template <> struct JetRow<CGG_BINOMIAL> {
         m[7] = fma(x7, vu * fma(fma(360.0, v, -60.0), v, 1.0), m[7]);
 #endif
     }
+    template <bool FULL>
     static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
-        add1(y.x, e.x, xs.x, inv_sd, tab, m, risk);
-        add1(y.y, e.y, xs.y, inv_sd, tab, m, risk);
+        add1<FULL>(y.x, e.x, xs.x, inv_sd, tab, m, risk);
+        add1<FULL>(y.y, e.y, xs.y, inv_sd, tab, m, risk);
     }
 };
 
 // poisson-log: l(t) = y t - exp(t) (- lgamma(y+1), per-dataset constant); l' = y - mu, l^(k) = -mu for k >= 2.
 template <> struct JetRow<CGG_POISSON> {
     static constexpr unsigned RISK_KEY = 0xc03be666u;     // eta <= -27.9: the pmax(., eps) clamp at -36.04 is within JET_AMAX
+    template <bool FULL>
     static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *, double (&m)[JET_NV], unsigned &risk) {
         const double l = (e < kLogEps) ? kLogEps : e;
         const double mu = exp(l);
@@ -148,31 +164,33 @@ template <> struct JetRow<CGG_POISSON> {
         m[8] = fma(fabs(y) + mu, ae + 1.0, m[8]);
         risk = max(risk, (unsigned)__double2hiint(e));                     // most negative eta (high word): checked against -27.9
     }
+    template <bool FULL>
     static __device__ __forceinline__ void add2(double2 y, double2 e, double2 xs, double inv_sd, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
-        add1(y.x, e.x, xs.x, inv_sd, tab, m, risk);
-        add1(y.y, e.y, xs.y, inv_sd, tab, m, risk);
+        add1<FULL>(y.x, e.x, xs.x, inv_sd, tab, m, risk);
+        add1<FULL>(y.y, e.y, xs.y, inv_sd, tab, m, risk);
     }
 };
 
 // ---- the enclosure --------------------------------------------------------------------------------
-// m[]: the pass's sums; cst: the column's statistics; delta = cand - x0.  Returns the surrogate
-// log-likelihood (without ll_const and without the prior) and in B a bound on its distance from the value an
-// exact fp64 pass of this engine would deliver (Taylor remainder + rounding of the accumulated moments +
-// rounding envelope of the exact evaluation itself).  B is +Inf (or NaN) when the enclosure does not apply:
-// the caller must treat any comparison that is not strictly decided as undecided.
+// m[]: the pass's sums; cst: the column's statistics; delta = cand - x0; fmag: the magnitude of the log-likelihood
+// (|M_0|, or the carried |f(x0)| after a light pass).  Returns the surrogate log-likelihood DIFFERENCE
+// sum_{k>=1} M_k h^k / k! and in B a bound on its distance from the difference (f(cand) - f(x0)) of two exact fp64
+// evaluations of this engine: Taylor remainder + rounding of the accumulated moments + the rounding envelopes of the
+// two exact evaluations.  B is +Inf (or NaN) when the enclosure does not apply: the caller must treat any comparison
+// that is not strictly decided as undecided.
 __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV], const double *cst, double n, double inv_sd,
-                                           double delta, double &B) {
+                                           double delta, double fmag, double &B) {
     const double h = delta * cst[1];
     const double a = fabs(h);
     const double ce = JET_CROUND * JET_EPS;
     if (family == CGG_GAUSSIAN) {
-        const double f = fma(h, fma(0.5 * h, m[2], m[1]), m[0]);
-        // moments: |M_0| (same-sign terms), sum|xs z|/sd <= sqrt(S_2 * 2|M_0|)/sd, |M_2|
-        const double bmom = ce * (fabs(m[0]) + a * sqrt(cst[3] * 2.0 * fabs(m[0])) * inv_sd + 0.5 * a * a * fabs(m[2]));
+        const double dl = h * fma(0.5 * h, m[2], m[1]);
+        // moments: sum|xs z|/sd <= sqrt(S_2 * 2|M_0|)/sd, |M_2|
+        const double bmom = ce * (a * sqrt(cst[3] * 2.0 * fabs(m[0])) * inv_sd + 0.5 * a * a * fabs(m[2]));
         // exact pass: t = fl(eta + fl(x delta)) perturbs -z^2/2 by <= |z| |dt| / sd, the rest is relative to z^2
-        const double bex = JET_EPS * inv_sd * (m[3] + 2.0 * a * m[4] + a * inv_sd * (m[5] + 2.0 * a * n)) + ce * fabs(f);
+        const double bex = JET_EPS * inv_sd * (m[3] + 2.0 * a * m[4] + a * inv_sd * (m[5] + 2.0 * a * n)) + ce * (2.0 * fmag + fabs(dl));
         B = 1.01 * (bmom + bex);
-        return f;
+        return dl;
     }
     if (family == CGG_BINOMIAL) {
         constexpr int D = CGG_JET_D;
@@ -181,31 +199,31 @@ __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV]
 #pragma unroll
         for (int k = D - 1; k >= 2; --k) f = fma(f, h, ((k & 1) ? m[k] : -m[k]) * JET_IFACT[k]);
         f = fma(f, h, fma(-0.5, m[1], cst[11]));
-        f = fma(f, h, m[0]);
+        const double dl = f * h;
         // remainder: G_(D+1) S_(D+1) a^(D+1) / (D+1)!;  moment k: rounding <= ce G_k S_k (terms are bounded by |xs|^k G_k)
-        double pw = a, bmom = fabs(m[0]);
+        double pw = a, bmom = 0.0;
 #pragma unroll
         for (int k = 1; k <= D; ++k) { bmom = fma(JET_G[k] * JET_IFACT[k] * cst[1 + k], pw, bmom); pw *= a; }
         const double bt = JET_G[D + 1] * JET_IFACT[D + 1] * cst[2 + D] * pw;
-        // exact pass: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|) with every |eta| < 21.9 (else
-        // m[9] != 0); softplus and sums relative to |f|
-        const double bex = JET_EPS * (21.9 * n + 2.0 * a * cst[2]) + ce * (fabs(f) + bt);
+        // exact passes: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|) with every |eta| < 21.9 (else
+        // m[9] != 0); softplus and sums relative to |f|, for both evaluations
+        const double bex = JET_EPS * (21.9 * n + 2.0 * a * cst[2]) + ce * (2.0 * fmag + fabs(dl) + bt);
         B = 1.01 * (bt + ce * bmom + bex);
         if (!(a <= JET_AMAX) || m[9] != 0.0) B = INFINITY;
-        return f;
+        return dl;
     }
     double f = m[6] * JET_IFACT[6];
 #pragma unroll
     for (int k = 5; k >= 1; --k) f = fma(f, h, m[k] * JET_IFACT[k]);
-    f = fma(f, h, m[0]);
+    const double dl = f * h;
     const double ea = exp(a);
     const double a2 = a * a, a4 = a2 * a2;
     const double bt = ea * (a4 * a2 * a) * JET_IFACT[7] * m[7] * (1.0 + 1e-6);
-    // every term of every moment, of the exact pass and of its t-rounding is bounded by e^a (1 + 2a) (|y| + mu)(|eta| + 1)
-    const double brnd = (JET_CROUND + 50.0) * JET_EPS * ea * (1.0 + 2.0 * a) * m[8];
+    // every term of every moment, of the exact passes and of their t-rounding is bounded by e^a (1 + 2a) (|y| + mu)(|eta| + 1)
+    const double brnd = (JET_CROUND + 100.0) * JET_EPS * ea * (1.0 + 2.0 * a) * m[8];
     B = 1.01 * (bt + brnd);
     if (!(a <= JET_AMAX) || m[9] != 0.0) B = INFINITY;
-    return f;
+    return dl;
 }
 
 }  // namespace cgg

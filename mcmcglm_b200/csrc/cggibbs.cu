@@ -446,7 +446,8 @@ __global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, con
 }
 
 // Diagnostic (cgg_debug_jet): evaluate the enclosure of chain c's current jet sums at K candidates.
-__global__ void jet_debug_kernel(Dev d, int c, int j, int K, const double *cand, double *out /* [K] value, [K] bound, [NV] sums */) {
+__global__ void jet_debug_kernel(Dev d, int c, int j, int K, int light, double fmag_light, const double *cand,
+                                 double *out /* [K] value, [K] bound, [NV] sums */) {
     const int lane = threadIdx.x;
     double m[NV];
     const double mv = (lane < NV) ? d.xbuf[c * NV + lane] : 0.0;
@@ -455,9 +456,10 @@ __global__ void jet_debug_kernel(Dev d, int c, int j, int K, const double *cand,
     const double x0 = d.beta[(int64_t)c * d.p + j];
     if (lane < K) {
         double B;
-        const double f = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, (double)d.n, d.inv_sd, __dadd_rn(cand[lane], -x0), B);
-        out[lane] = f + d.ll_const;
-        out[K + lane] = B * d.jet_bscale + 4.0 * JET_EPS * fabs(f);
+        const double fmag = light ? fmag_light : fabs(m[0]);
+        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, (double)d.n, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B);
+        out[lane] = light ? dl : (m[0] + dl) + d.ll_const;
+        out[K + lane] = B * d.jet_bscale + 8.0 * JET_EPS * (fmag + fabs(dl));
     }
     if (lane < NV) out[2 * K + lane] = m[lane];
 }
@@ -613,6 +615,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     d.coarse_theta = getenv("CGG_COARSE_THETA") ? atof(getenv("CGG_COARSE_THETA")) : 0.4;
     d.jet = !d.sharded && !(cfg->flags & CGG_FLAG_NO_JET);
     d.jet_bscale = (cfg->jet_bound_scale > 0.0) ? cfg->jet_bound_scale : 1.0;
+    d.jet_light = d.jet && !(cfg->flags & CGG_FLAG_NO_JET_LIGHT);
     d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
     d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
     if (cfg->prior == CGG_PRIOR_NORMAL) d.prior.c0 = -(kLnSqrt2Pi + log(cfg->prior_sigma));
@@ -958,7 +961,7 @@ extern "C" int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plu
     return CGG_OK;
 }
 
-extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const double *cand_host,
+extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, int32_t light, const double *cand_host,
                              double *value_host, double *bound_host, double *sums_host) {
     int rc = check_chain(h, chain, "cgg_debug_jet", true);
     if (rc) return rc;
@@ -970,7 +973,16 @@ extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K,
     std::vector<Ctl> ctl(d.C), saved(d.C);
     memset(ctl.data(), 0, sizeof(Ctl) * d.C);
     for (int c = 0; c < d.C; ++c) ctl[c].commit_j = -1;
-    ctl[chain].j = (int32_t)j; ctl[chain].ncand = 0; ctl[chain].coarse_mask = (int32_t)JET_BIT;
+    const bool lt = light && d.family == CGG_BINOMIAL;
+    double fmag_light = 1.0;
+    if (lt) {      // the magnitude a chain would carry: |f(x0)|
+        rc = ensure_fx(h, chain);
+        if (rc) return rc;
+        ChainState cs1;
+        CK(cudaMemcpy(&cs1, d.cs + chain, sizeof cs1, cudaMemcpyDeviceToHost));
+        fmag_light = fabs(cs1.fx0) + 1.0;
+    }
+    ctl[chain].j = (int32_t)j; ctl[chain].ncand = 0; ctl[chain].coarse_mask = (int32_t)(JET_BIT | (lt ? 0u : JET_FULL));
     CK(cudaMemcpyAsync(&ctl[chain].cscale, h->colstat_dev + j * CS_STRIDE, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpyAsync(saved.data(), d.ctl, sizeof(Ctl) * d.C, cudaMemcpyDeviceToHost, h->stream));
@@ -979,7 +991,7 @@ extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K,
     CK(cudaMemsetAsync(&d.hdr->done, 0, sizeof(int32_t), h->stream));
     rc = launch_pass(h, 1);
     if (rc) return rc;
-    jet_debug_kernel<<<1, 32, 0, h->stream>>>(d, chain, (int)j, K, h->scratch_dev, h->scratch_dev + KMAX);
+    jet_debug_kernel<<<1, 32, 0, h->stream>>>(d, chain, (int)j, K, lt ? 1 : 0, fmag_light, h->scratch_dev, h->scratch_dev + KMAX);
     CK(cudaGetLastError());
     std::vector<double> out(2 * K + NV);
     CK(cudaMemcpyAsync(out.data(), h->scratch_dev + KMAX, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, h->stream));
@@ -1079,7 +1091,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         cs[c].phase = PH_START; cs[c].status = CGG_OK; cs[c].iter = 0; cs[c].j = 0;
         cs[c].updates = cs[c].chain_passes = cs[c].commit_passes = cs[c].cand_evals = 0;
         cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = cs[c].coarse_evals = cs[c].coarse_undecided = 0;
-        cs[c].jet_passes = cs[c].jet_fallbacks = 0;
+        cs[c].jet_passes = cs[c].jet_fallbacks = cs[c].jet_retries = 0;
         cs[c].fine_next = 0;
         ctl[c].commit_j = -1;
     }
@@ -1155,10 +1167,11 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         st.updates += cs[c].updates; st.chain_passes += cs[c].chain_passes; st.commit_passes += cs[c].commit_passes;
         st.cand_evals += cs[c].cand_evals; st.ref_evals += cs[c].ref_evals; st.stepouts += cs[c].stepouts; st.shrinks += cs[c].shrinks;
         st.passes += cs[c].passes; st.coarse_evals += cs[c].coarse_evals; st.coarse_undecided += cs[c].coarse_undecided;
-        st.jet_passes += cs[c].jet_passes; st.jet_fallbacks += cs[c].jet_fallbacks;
+        st.jet_passes += cs[c].jet_passes; st.jet_fallbacks += cs[c].jet_fallbacks; st.jet_retries += cs[c].jet_retries;
         if (u_consumed) u_consumed[c] = cs[c].cursor;
         if (cs[c].status != CGG_OK && bad == CGG_OK) { bad = cs[c].status; bad_chain = c; }
     }
+    if (d.jet_light && d.family == CGG_BINOMIAL) std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);   // carried f(x0) is a surrogate value
     st.launches = launches; st.sweep_ms = ms;
     st.algorithmic_bytes = 8.0 * (double)d.n * (3.0 * (double)st.chain_passes + 2.0 * (double)st.commit_passes);
     if (stats) *stats = st;

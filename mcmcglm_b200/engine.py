@@ -33,7 +33,7 @@ class Engine:
     def __init__(self, n, p, family="gaussian", link=None, sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0,
                  prior_df=1.0, w=0.5, max_steps=-1, n_chains=1, K=8, device=0, driver="persistent", seed=0,
                  chain_offset=0, spec_tau=0.12, rows_per_cta_min=0, row_sharded=False, prefilter=True, jet=True,
-                 jet_bound_scale=1.0):
+                 jet_light=True, jet_bound_scale=1.0):
         self._h = None
         self._lib = L.load()
         if family not in FAMILIES:
@@ -54,7 +54,8 @@ class Engine:
                        prior_df=prior_df, w=w, max_steps=int(max_steps), K=K, driver=DRIVERS[driver],
                        mode=L.MODE_ROW_SHARDED if row_sharded else L.MODE_CHAINS, chain_offset=chain_offset,
                        seed=seed, spec_tau=spec_tau, rows_per_cta_min=rows_per_cta_min,
-                       flags=(0 if prefilter else L.FLAG_NO_PREFILTER) | (0 if jet else L.FLAG_NO_JET),
+                       flags=((0 if prefilter else L.FLAG_NO_PREFILTER) | (0 if jet else L.FLAG_NO_JET)
+                              | (0 if jet_light else L.FLAG_NO_JET_LIGHT)),
                        jet_bound_scale=jet_bound_scale)
         h = C.c_void_p()
         L.check(self._lib.cgg_create(C.byref(cfg), C.byref(h)))
@@ -116,11 +117,12 @@ class Engine:
         L.check(self._lib.cgg_log_potential(self._h, chain, j, c.size, c.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
         return out
 
-    def debug_jet(self, chain, j, cands):
-        """One jet pass along column j (no state change): (surrogate log-likelihood, error bound, raw sums)."""
+    def debug_jet(self, chain, j, cands, light=False):
+        """One jet pass along column j (no state change): (surrogate log-likelihood, error bound, raw sums);
+        light=True (binomial): the log-likelihood difference to the current point instead."""
         c = np.atleast_1d(_f64(cands))
         val, bnd, sums = np.empty_like(c), np.empty_like(c), np.empty(L.JET_NV)
-        L.check(self._lib.cgg_debug_jet(self._h, chain, j, c.size, c.ctypes.data_as(_dp), val.ctypes.data_as(_dp),
+        L.check(self._lib.cgg_debug_jet(self._h, chain, j, c.size, int(bool(light)), c.ctypes.data_as(_dp), val.ctypes.data_as(_dp),
                                         bnd.ctypes.data_as(_dp), sums.ctypes.data_as(_dp)))
         return val, bnd, sums
 

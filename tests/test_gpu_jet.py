@@ -64,6 +64,19 @@ def test_enclosure_contains_the_exact_value(family):
             # tight where the slice lives: |x delta| <= ~0.05 => far below any realistic |f - level|
             assert np.all(bnd[:3] < 1e-9), bnd[:3]
             assert np.all(bnd[:5] < 1e-4), bnd[:5]
+            if family == "binomial":
+                # light pass: no M_0; the enclosure is of the DIFFERENCE f(cand) - f(x0) of two exact evaluations
+                dval, dbnd, dsums = e.debug_jet(0, j, cands, light=True)
+                assert dsums[0] == 0.0
+                base = _loglik_mp(family, y, eta, X[:, j], 0.0, sd)
+                for k, dlt in enumerate(cands - beta[j]):
+                    truth = _loglik_mp(family, y, eta, X[:, j], dlt, sd) - base
+                    assert np.isfinite(dbnd[k]) and abs(mp.mpf(float(dval[k])) - truth) <= dbnd[k], (j, k)
+                    # against the difference of the engine's own two exact evaluations (cands[0] is the current point)
+                    pk = oracle.log_prior_density(m, np.r_[beta[:j], cands[k], beta[j + 1:]])
+                    ex_diff = (f_ex[k] - pk) - (f_ex[0] - oracle.log_prior_density(m, beta))
+                    assert abs(dval[k] - ex_diff) <= dbnd[k] + 16 * np.spacing(abs(f_ex[k])), (j, k)
+                assert np.all(dbnd[:3] < 1e-9) and np.all(dbnd[:5] < 1e-4)
 
 
 def _run(family, prior, X, y, beta0, iters, U=None, **kw):
@@ -101,16 +114,21 @@ def test_jet_chain_is_bit_identical_to_the_exact_chain(family, prior, w, max_ste
     for replay in (U, None):
         kw = dict(w=w, max_steps=max_steps, K=6, spec_tau=0.4, driver=driver, seed=77, chain_offset=10)
         exact = _run(family, prior, X, y, beta0, iters, replay, jet=False, **kw)
-        jet = _run(family, prior, X, y, beta0, iters, replay, jet=True, **kw)
-        _same_chain(exact, jet)
         assert exact[1]["jet_passes"] == 0
-        assert jet[1]["jet_passes"] >= jet[1]["updates"] - jet[1]["jet_fallbacks"] > 0
-        # inflated bounds: ~1 log unit (some comparisons undecided mid-sequence) and enormous (every one undecided)
-        for scale in (1e9, 1e30):
-            forced = _run(family, prior, X, y, beta0, iters, replay, jet=True, jet_bound_scale=scale, **kw)
-            _same_chain(exact, forced)
-            if scale == 1e30:
-                assert forced[1]["jet_fallbacks"] == forced[1]["updates"]
+        for light in (True, False):      # binomial: light passes (no M_0) by default; full passes on request
+            jet = _run(family, prior, X, y, beta0, iters, replay, jet=True, jet_light=light, **kw)
+            _same_chain(exact, jet)
+            assert jet[1]["jet_passes"] >= jet[1]["updates"] - jet[1]["jet_fallbacks"] > 0
+            if not (light and family == "binomial"):
+                assert jet[1]["jet_retries"] == 0
+            # inflated bounds: ~1 log unit (some comparisons undecided mid-sequence) and enormous (every one undecided)
+            for scale in (1e9, 1e30):
+                forced = _run(family, prior, X, y, beta0, iters, replay, jet=True, jet_light=light, jet_bound_scale=scale, **kw)
+                _same_chain(exact, forced)
+                if scale == 1e30:
+                    assert forced[1]["jet_fallbacks"] == forced[1]["updates"]
+                    if light and family == "binomial":
+                        assert forced[1]["jet_retries"] == forced[1]["updates"]
 
 
 def test_jet_is_one_pass_per_update_at_scale():
@@ -120,8 +138,8 @@ def test_jet_is_one_pass_per_update_at_scale():
     beta0 = np.tile(bt, (C, 1))
     S, st, _ = _run("binomial", "laplace", X, y, beta0, 25, None, w=0.5, seed=5)
     assert st["updates"] == C * 25 * p
-    assert st["jet_fallbacks"] <= 2
-    assert st["chain_passes"] <= st["updates"] + 8 * st["jet_fallbacks"] + C
+    assert st["jet_fallbacks"] <= 2 and st["jet_retries"] <= 4
+    assert st["chain_passes"] <= st["updates"] + 8 * st["jet_fallbacks"] + st["jet_retries"] + C
     exact = _run("binomial", "laplace", X, y, beta0, 25, None, w=0.5, seed=5, jet=False)
     assert np.array_equal(S, exact[0])
 
