@@ -99,6 +99,7 @@ struct Dev {
     double *eta, *beta, *shat, *samples, *xbuf;
     const double *replay;
     const double *colstat;     // [p][CS_STRIDE] per-column scale and absolute moments (jet passes)
+    double *slots;             // [C][G][NV] per-CTA partial sums of the pass in flight (persistent driver)
     Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
     unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
     int64_t n, p, ldx, lde, n_tiles, n_iter;
@@ -384,11 +385,14 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
 // next_cw: the control block of the chain this warp will stream next if its decision is already published
 // (else nullptr); its first ring stages are then issued as soon as this chain's tiles are consumed, so the
 // loads are in flight during the reduction and delivery below.  `prefetched` is updated accordingly.
-template <int FAMILY>
+// No look-ahead (stepwise driver: every launch starts from scratch).
+struct NoLookAhead { __device__ __forceinline__ const double *poll(const Dev &, int) { return nullptr; } };
+
+template <int FAMILY, class LA>
 __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw /* the CTA's shared copy of ctl[c] */,
                                            long long wid, long long W, int lane, uint32_t ring, const double2 *tab,
                                            double *sacc, double (&acc)[NV], int &j_out, bool &prefetched,
-                                           int next_c, const double *next_cw, long long *t_tiles = nullptr) {
+                                           int next_c, LA *la, long long *t_tiles = nullptr) {
     const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
     const int j = (int)(w0 & 0xffffffffLL), nc = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
     const unsigned cmask = (unsigned)(w1 >> 32);
@@ -404,7 +408,7 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
             else warp_pass_jet<FAMILY, false>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
             if (t_tiles) *t_tiles += clock64() - t0;
         }
-        if (next_cw) {
+        if (const double *next_cw = la->poll(d, lane)) {
             const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
             const long long nw0 = __double_as_longlong(next_cw[0]);
             const int nj = (int)(nw0 & 0xffffffffLL);
@@ -423,7 +427,7 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
         warp_pass_chain<FAMILY>(d, cs, cw[2], cw + 3, lane, tab, sacc, was_prefetched, cmask, bE, bX, nearmask);
         if (t_tiles) *t_tiles += clock64() - t0;
     }
-    if (next_cw) {
+    if (const double *next_cw = la->poll(d, lane)) {
         const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
         const long long nw0 = __double_as_longlong(next_cw[0]);
         const int nj = (int)(nw0 & 0xffffffffLL);
@@ -439,6 +443,10 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
 #pragma unroll
     for (int k = 0; k < NV; ++k) { if (k == nc) acc[k] = sE; if (k == nc + 1) acc[k] = sX; }
     nearmask = __reduce_or_sync(0xffffffffu, nearmask);
+    if (nearmask) {                // ... and as a NaN bound sum, which travels with the values themselves (slot delivery)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) if (k == nc) acc[k] = NAN;
+    }
     if (nearmask && lane == 0) {   // a row sat on the |eta| = 30 clamp discontinuity: the bound does not hold
         for (int k = 0; k < nc; ++k)
             if ((nearmask >> k) & 1u) atomicOr(&d.acc[c * NV + k].flags, 8u);
@@ -472,6 +480,41 @@ struct CtaShared {                       // views into dynamic shared memory, si
     }
 };
 
+// Persistent driver: at the END of a chain's pass (tiles consumed, sums not yet reduced) look whether the next chain's
+// decision is published; if so bring its control block into shared memory (one elected warp per CTA, everybody else
+// only reads shared memory) so that its first tiles can be requested before this chain's sums are reduced and
+// delivered, and nobody has to fetch the block from global memory at the top of the next pass.  Decisions are
+// published roughly one pass before they are needed, so a look at the start of the pass would be too early.
+struct LookAhead {
+    CtaShared *sh; const ChainSync *sync; const Ctl *ctl;
+    int nxt; unsigned long long nround;
+    long long n_look, n_ok;
+    __device__ __forceinline__ const double *poll(const Dev &d, int lane) {
+        if (nxt < 0) return nullptr;
+        volatile unsigned long long *sv = &sh->ver[nxt];
+        if (*sv < nround) {
+            int got = 0;
+            if (lane == 0) got = (atomicCAS_block(&sh->lock[nxt], 0, 1) == 0);
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (got) {
+                unsigned long long v = 0;
+                if (lane == 0) v = ld_acquire_u64(&sync[nxt].version);
+                v = __shfl_sync(0xffffffffu, v, 0);
+                ++n_look; if (v >= nround) ++n_ok;
+                if (v >= nround && v > *sv) {
+                    if (lane < CTL_WORDS) sh->ctl[nxt * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(ctl + nxt) + lane);
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); *sv = v; }
+                }
+                if (lane == 0) { __threadfence_block(); atomicExch_block(&sh->lock[nxt], 0); }
+                __syncwarp();
+            }
+        }
+        // the shared control block of `nxt` belongs to version ver[nxt]: usable only if that is exactly the pass we will run
+        return (*sv == nround) ? sh->ctl + nxt * CTL_WORDS : nullptr;
+    }
+};
+
 // Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
 // has folded the CTA's NWARPS partials -- summed in warp order, so the value is reproducible -- into the
 // chain's exact accumulators; the other warps return at once and move on to their next chain.
@@ -498,6 +541,88 @@ __device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, 
     if (lane == 0) sh.cnt[c] = 0;
     __syncwarp();
     return true;
+}
+
+// Persistent driver: the same CTA-level fold, but the CTA's sums go to the CTA's own slot of the chain as 16-byte
+// {value, stamp} pairs (stamp = number of the pass + 1), written by ONE lane with plain vector stores: no atomic, no
+// fence, nothing to wait for -- the warp moves on to its next chain at once.  A 16-byte aligned store / load is a
+// single memory transaction, so a pair is never torn; the decider polls the stamps and only uses a value whose own
+// stamp is the expected one (the protocol of NCCL's low-latency paths).  With atomics on shared accumulators -- and
+// still with a release-increment of an arrival counter, whose implied membar costs microseconds under load -- the last
+// warp of every CTA fell behind, was therefore last again, and paced the whole grid.  Entry 0 is always written (an
+// idle pass delivers nothing else).  The decider adds the G slots in CTA order: reproducible.
+struct __align__(16) SlotEntry { double v; unsigned long long stamp; };
+__device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers,
+                                                  unsigned long long stamp, const double (&acc)[NV]) {
+    // Shared-memory hand-over without a MEMBAR: the partials are written with volatile stores and the counter is bumped by
+    // the same thread afterwards; shared-memory operations of a thread are performed in program order by the SM's
+    // one shared-memory pipe, and the reader's loads depend on the value its own atomic returned.  (A __threadfence_block()
+    // here is a MEMBAR.SC.CTA that also waits for the warp's outstanding global traffic -- the eta stores and the next
+    // chain's prefetch just issued -- i.e. for a microsecond or two.)
+    int last = 0;
+    if (lane == 0) {
+        volatile double *pw = sh.part + ((size_t)c * NWARPS + warp) * NV;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            if (k < nc) pw[k] = acc[k];
+#ifdef CGG_CTA_FENCE
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+        last = (atomicAdd_block(&sh.cnt[c], 1) == nworkers - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+#ifdef CGG_CTA_FENCE
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
+    // three lanes per value, each adding every third warp's partial, then two fixed-order adds
+    static_assert(3 * NV <= 32, "three lanes per value");
+    const int k0 = lane % NV, g0 = lane / NV;
+    double v = 0.0;
+    if (g0 < 3 && k0 < nc) {
+#pragma unroll
+        for (int w = 0; w < NWARPS; w += 3)
+            if (w + g0 < nworkers) v += const_cast<volatile double *>(sh.part)[((size_t)c * NWARPS + w + g0) * NV + k0];
+    }
+    v = (v + __shfl_down_sync(0xffffffffu, v, NV)) + __shfl_down_sync(0xffffffffu, v, 2 * NV);   // valid in lanes < NV
+    if (lane == 0) sh.cnt[c] = 0;
+    if (lane < NV && (lane < nc || lane == 0)) {
+        SlotEntry *dst = reinterpret_cast<SlotEntry *>(d.slots) + ((size_t)c * d.G + blockIdx.x) * NV + lane;
+        asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(v)), "l"(stamp) : "memory");   // ONE 16-byte store
+    }
+    __syncwarp();
+}
+
+// Decider side: has every CTA delivered pass `stamp - 1` of chain c?  (entry 0 of each slot; the other entries are
+// validated when they are read)
+__device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long long stamp, int lane) {
+    const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
+    bool ok = true;
+    for (int g = lane; g < d.G; g += 32) ok = ok && (__ldcg(&base[(size_t)g * NV].stamp) == stamp);
+    return __all_sync(0xffffffffu, ok);
+}
+
+// Value k of chain c's finished pass = the G slots added in CTA order (lane l takes CTAs l, l + 32, ..., then a
+// butterfly: the same bits in every lane and on every run).  Returns false if some entry does not carry the stamp yet.
+__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
+    const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
+    double part[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[k] = 0.0;
+    bool ok = true;
+    for (int g = lane; g < d.G; g += 32) {
+        const int4 *src = reinterpret_cast<const int4 *>(base + (size_t)g * NV);
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            if (k < nvals) {
+                const int4 t = __ldcg(src + k);                       // one 16-byte load: {value, stamp}
+                part[k] += __hiloint2double(t.y, t.x);
+                ok = ok && ((((unsigned long long)(unsigned)t.w << 32) | (unsigned)t.z) == stamp);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) out[k] = (k < nvals) ? warp_sum(part[k]) : 0.0;
+    return __all_sync(0xffffffffu, ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -822,7 +947,10 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
 // Returns true when the chain is finished (or failed) after this decision.
 // The parameter block is taken by pointer -- the kernels pass the address of their __grid_constant__
 // parameter -- so this cold, register-hungry routine stays out of line and off the hot loop's registers.
-__device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_hint, bool from_xbuf) {
+enum SumSource : int { SRC_ACC = 0, SRC_XBUF = 1, SRC_SLOTS = 2 };
+enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
+__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, unsigned long long stamp = 0) {
+    const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
     // ---- one batched round of loads: control block, state, accumulators, beta/shat of j and j+1
     if (j_hint < 0) j_hint = __ldcg(&d.ctl[c].j);
@@ -833,12 +961,15 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     const double shat_j = __ldcg(sp + jq), shat_n = __ldcg(sp + jn);
     Ctl ct = d.ctl[c];
     ChainState s = d.cs[c];
-    if (s.phase == PH_FINISHED || s.status != CGG_OK) return true;
+    if (s.phase == PH_FINISHED || s.status != CGG_OK) return DEC_FINISHED;
     const bool jetpass = ((unsigned)ct.coarse_mask & JET_BIT) != 0u && s.phase == PH_JET;
     const int nc = jetpass ? 0 : ct.ncand;
     const unsigned cmask = jetpass ? 0u : (unsigned)ct.coarse_mask;
-    double jm[NV];
-    if (jetpass) {
+    double jm[NV];        // the pass's sums, identical in every lane (slots source: all of them; else only for a jet pass)
+    if (src == SRC_SLOTS) {
+        const int nvals = jetpass ? NV : (cmask ? nc + 2 : nc);
+        if (!slots_sum(d, c, nvals, stamp, lane, jm)) return DEC_NOT_READY;      // some value is still on its way: nothing was changed
+    } else if (jetpass) {
         const double mv = (lane < NV) ? (from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
@@ -846,8 +977,16 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
     unsigned int aflags = 0;
+    auto pick = [&](int idx) { double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v = (k == idx) ? jm[k] : v;
+        return v; };
     if (lane < nc) {
-        const double ll = from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
+        double ll;
+        if (src == SRC_SLOTS) {
+            ll = pick(lane) + d.ll_const;
+            if (cmask) { aflags = __ldcg(&d.acc[c * NV + lane].flags); d.acc[c * NV + lane].flags = 0u; }   // clamp-proximity flag of the pre-filter
+        } else ll = from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
         f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));
     }
     int stop_at = nc;
@@ -855,8 +994,9 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
         // pre-filtered candidates: |f32 sum - exact| <= B.  The candidate is outside the slice for certain iff
         // f + B < ylev; anything else (including a row on the clamp discontinuity, or NaN) stays undecided.
         double bsum = 0.0;
-        if (lane == nc || lane == nc + 1) bsum = acc_take(d.acc + c * NV + lane);
-        const double sE = __shfl_sync(0xffffffffu, bsum, nc), sX = __shfl_sync(0xffffffffu, bsum, nc + 1);
+        if (src != SRC_SLOTS && (lane == nc || lane == nc + 1)) bsum = acc_take(d.acc + c * NV + lane);
+        const double sE = (src == SRC_SLOTS) ? pick(nc) : __shfl_sync(0xffffffffu, bsum, nc);
+        const double sX = (src == SRC_SLOTS) ? pick(nc + 1) : __shfl_sync(0xffffffffu, bsum, nc + 1);
         bool undecided = false;
         if (lane < nc && ((cmask >> lane) & 1u)) {
             const double B = 1.01 * ((2.384185791015625e-07 + (double)kCoarseKappa) * (sE + fabs(s.cand[lane] - s.x0) * sX)
@@ -945,7 +1085,7 @@ __device__ __noinline__ bool decide_chain(const Dev *dp, int c, int lane, int j_
     fin = __shfl_sync(0xffffffffu, (int)fin, 0);
     fence_gpu();       // every lane: its accumulator clears must be visible before the version is released
     __syncwarp();
-    return fin;
+    return fin ? DEC_FINISHED : DEC_CONTINUE;
 }
 
 }  // namespace cgg

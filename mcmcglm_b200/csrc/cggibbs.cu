@@ -48,18 +48,22 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
     for (;;) {
         bool all_fin = true, progressed = false;
         for (int c = first_chain; c < d.C; c += stride) {
-            unsigned long long v = 0, a = 0;
-            if (lane == 0) { v = __ldcg(&d.sync[c].version); if (v < VERSION_FINISHED) a = ld_acquire_u64(&d.sync[c].arrive); }
+            unsigned long long v = 0;
+            if (lane == 0) v = __ldcg(&d.sync[c].version);
             v = __shfl_sync(0xffffffffu, v, 0);
             if (v >= VERSION_FINISHED) continue;
             all_fin = false;
-            a = __shfl_sync(0xffffffffu, a, 0);
-            if (a < (v + 1) * (unsigned long long)d.G) continue;   // pass #v still has CTAs streaming
-            fence_gpu();
+            if (!slots_arrived(d, c, v + 1, lane)) continue;       // pass #v still has CTAs streaming
+            const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
             const long long td0 = d.prof ? clock64() : 0;
-            const bool fin = decide_chain(dp, c, lane, -1, false);
+            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, v + 1);
+            if (oc == DEC_NOT_READY) continue;
+            const bool fin = oc == DEC_FINISHED;
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
-            if (d.prof && lane == 0) { atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL); }
+            if (d.prof && lane == 0) {
+                atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL);
+                if (v < 128) { d.prof[16 + 4096 + (c * 128 + v) * 4 + 0] = tg0; d.prof[16 + 4096 + (c * 128 + v) * 4 + 1] = globaltimer_ns(); }
+            }
             progressed = true;
         }
         if (all_fin) break;
@@ -81,17 +85,20 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     for (int i = threadIdx.x; i < d.C; i += THREADS) { sh.ver[i] = 0ULL; sh.cnt[i] = 0; sh.lock[i] = 0; }
     for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
     __syncthreads();
-    // decider warps: the last warp of the first ND CTAs
-    const int ND = d.C < d.G ? d.C : d.G;
-    const bool decider_cta = (int)blockIdx.x < ND;
-    if (decider_cta && warp == NWARPS - 1) { decider_loop(&d, (int)blockIdx.x, ND, lane); return; }
-    const int nworkers = NWARPS - (decider_cta ? 1 : 0);
-    const long long wid = (long long)blockIdx.x * NWARPS + warp - ((int)blockIdx.x < ND ? (int)blockIdx.x : ND);
-    const long long W = (long long)d.G * NWARPS - ND;
+    // The deciders have a CTA (an SM) of their own, the one after the d.G worker CTAs: warp w decides chains w, w + NWARPS, ...
+    // Next to fifteen workers that saturate the fp64 pipe a decision took ~25 us, and the decision sits on every
+    // chain's critical cycle (pass -> decision -> next pass).
+    if ((int)blockIdx.x == d.G) {
+        if (warp < d.C) decider_loop(&d, warp, NWARPS, lane);
+        return;
+    }
+    const int nworkers = NWARPS;
+    const long long wid = (long long)blockIdx.x * NWARPS + warp;
+    const long long W = (long long)d.G * NWARPS;
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
     double acc[NV];
     bool prefetched = false;
-    long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0;
+    long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0, n_notready = 0, n_look = 0, n_look_ok = 0;
     const bool prof = d.prof != nullptr;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
@@ -100,6 +107,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             // time polls the flag for the whole CTA and, when it has advanced, fetches the chain's control
             // block with one coalesced request into shared memory; the other warps only watch shared memory.
             long long tA = prof ? clock64() : 0;
+            if (prof && lane == 0 && round >= 1 && round <= 128) {
+                if (blockIdx.x == 20 && warp == 0) d.prof[16 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
+            }
             {
                 volatile unsigned long long *sv = &sh.ver[c];
                 if (*sv < round) {
@@ -114,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                             unsigned long long v = 0;
                             if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
                             v = __shfl_sync(0xffffffffu, v, 0);
+                            if (v < round) ++n_notready;
                             if (v >= round && v > *sv) {
                                 if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
                                 __syncwarp();
@@ -135,39 +146,23 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             int j = -1;
             const int nxt = (c + 1 == d.C) ? 0 : c + 1;
             const unsigned long long nround = (c + 1 == d.C) ? round + 1 : round;
-            if (d.C > 1 && *(volatile unsigned long long *)&sh.ver[nxt] < nround) {
-                // one non-blocking look at the next chain's flag (same election as the wait loop above)
-                int got = 0;
-                if (lane == 0) got = (atomicCAS_block(&sh.lock[nxt], 0, 1) == 0);
-                got = __shfl_sync(0xffffffffu, got, 0);
-                if (got) {
-                    unsigned long long v = 0;
-                    if (lane == 0) v = ld_acquire_u64(&d.sync[nxt].version);
-                    v = __shfl_sync(0xffffffffu, v, 0);
-                    if (v >= nround && v > *(volatile unsigned long long *)&sh.ver[nxt]) {
-                        if (lane < CTL_WORDS) sh.ctl[nxt * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + nxt) + lane);
-                        __syncwarp();
-                        if (lane == 0) { __threadfence_block(); *(volatile unsigned long long *)&sh.ver[nxt] = v; }
-                    }
-                    if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[nxt], 0); }
-                    __syncwarp();
-                }
-            }
-            const bool nready = (d.C > 1) && (*(volatile unsigned long long *)&sh.ver[nxt] >= nround) &&
-                                (*(volatile unsigned long long *)&sh.ver[nxt] < VERSION_FINISHED);
-            // the shared control block of `nxt` belongs to version sh.ver[nxt]: usable only if that is exactly the pass we will run
-            const bool nexact = nready && (*(volatile unsigned long long *)&sh.ver[nxt] == nround);
+            LookAhead la{&sh, d.sync, d.ctl, d.C > 1 ? nxt : -1, nround, 0, 0};
             const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
-                                               acc, j, prefetched, nxt, nexact ? sh.ctl + nxt * CTL_WORDS : nullptr, prof ? &t_tiles : nullptr);
+                                               acc, j, prefetched, nxt, &la, prof ? &t_tiles : nullptr);
+            n_look += la.n_look; n_look_ok += la.n_ok;
             if (nc < 0) continue;
             any = true;
             n_pref += prefetched ? 1 : 0;
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
-            if (cta_deliver(d, sh, c, nc, warp, lane, nworkers, acc) && lane == 0) {
-                fence_gpu();
-                atomicAdd(&d.sync[c].arrive, 1ULL);
+            cta_deliver_slots(d, sh, c, nc, warp, lane, nworkers, round + 1, acc);
+            if (prof && lane == 0 && round == 60 && c == 0)
+                d.prof[16 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
+            if (prof && lane == 0 && round < 128) {     // arrival spread of the warps for pass #round of chain c
+                const unsigned long long tn = globaltimer_ns();
+                atomicMin(d.prof + 16 + 4096 + (c * 128 + round) * 4 + 2, tn);
+                atomicMax(d.prof + 16 + 4096 + (c * 128 + round) * 4 + 3, tn);
             }
             if (prof) t_arrive += clock64() - tC;
         }
@@ -178,6 +173,15 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         atomicAdd(d.prof + 2, (unsigned long long)t_arrive); atomicAdd(d.prof + 5, (unsigned long long)n_slow);
         atomicAdd(d.prof + 3, (unsigned long long)t_tiles); atomicAdd(d.prof + 4, (unsigned long long)n_pref);
         atomicAdd(d.prof + 6, 1ULL);
+        atomicAdd(d.prof + 9, (unsigned long long)n_notready); atomicAdd(d.prof + 10, (unsigned long long)n_look); atomicAdd(d.prof + 11, (unsigned long long)n_look_ok);
+        // per-CTA view (who waits, who never does): [16 + 4 * cta + {wait, tiles, rows, smid}]
+        unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 0, (unsigned long long)t_wait);
+        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 1, (unsigned long long)t_tiles);
+        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 2, (unsigned long long)t_rows);
+        d.prof[16 + 4 * blockIdx.x + 3] = smid;
+        // per-warp view: [16 + 4096 + 32*128*4 + (cta * NWARPS + warp) * 2 + {wait, tiles}]
+        d.prof[16 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 0] = (unsigned long long)t_wait;
     }
 }
 
@@ -202,8 +206,9 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     for (int c = 0; c < d.C; ++c) {
         int j;
         bool prefetched = false;
+        NoLookAhead nola;
         const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
-                                           acc, j, prefetched, 0, nullptr);
+                                           acc, j, prefetched, 0, &nola);
         if (nc > 0) cta_deliver(d, sh, c, nc, warp, lane, NWARPS, acc);
     }
     __syncthreads();
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     if (!s_flag) return;
     __threadfence();
     for (int c = warp; c < d.C; c += NWARPS) {
-        if (mode == 0) decide_chain(&d, c, lane, -1, false);
+        if (mode == 0) decide_chain(&d, c, lane, -1, SRC_ACC);
         else {
             const bool jet = ((unsigned)d.ctl[c].coarse_mask & JET_BIT) != 0u;
             const int nc = jet ? NV : d.ctl[c].ncand;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
 __global__ void __launch_bounds__(THREADS, 1) decide_kernel(const __grid_constant__ Dev d) {
     if (d.hdr->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < d.C; c += NWARPS) decide_chain(&d, c, lane, -1, true);
+    for (int c = warp; c < d.C; c += NWARPS) decide_chain(&d, c, lane, -1, SRC_XBUF);
     __syncthreads();
     if (threadIdx.x == 0) {
         int done = 1;
@@ -532,7 +537,7 @@ struct cgg_handle {
     unsigned long long *prof_dev = nullptr;
     Hdr *hdr_pinned = nullptr;
     bool has_data = false;
-    std::vector<char> chain_init, fx_valid;
+    std::vector<char> chain_init, fx_valid, fx_mag;   // fx_mag: the carried f(x0) is at least a valid magnitude (light jet passes)
     int num_sms = 0, max_grid = 0;
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
     ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr;
@@ -646,7 +651,9 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     int64_t tmin = cfg->rows_per_cta_min > 0 ? cfg->rows_per_cta_min / (TILE_ROWS * NWARPS) : 1;
     if (tmin < 1) tmin = 1;
     int64_t G = (d.n_tiles + NWARPS * tmin - 1) / (NWARPS * tmin);
-    if (G > h->max_grid) G = h->max_grid;
+    const int64_t gmax = h->max_grid - (cfg->driver == CGG_DRIVER_PERSISTENT ? 1 : 0);   // persistent driver: one more CTA hosts the deciders
+    if (gmax < 1) { delete h; return fail(CGG_E_CUDA, "cgg_create: the device cannot co-schedule a worker CTA and the decider CTA"); }
+    if (G > gmax) G = gmax;
     if (G < 1) G = 1;
     d.G = (int)G;
     d.lde = (d.n + 31) / 32 * 32;
@@ -659,6 +666,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.sync, sizeof(ChainSync) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * NV);
+    if (e == cudaSuccess) e = A((void **)&d.slots, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G);
     if (e == cudaSuccess) e = A((void **)&d.ctl, sizeof(Ctl) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.cs, sizeof(ChainState) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.hdr, sizeof(Hdr));
@@ -684,6 +692,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     CK(cudaStreamSynchronize(h->stream));
     h->chain_init.assign(C, 0);
     h->fx_valid.assign(C, 0);
+    h->fx_mag.assign(C, 0);
     d.colstat = h->colstat_dev;
     *out = h;
     return CGG_OK;
@@ -695,7 +704,7 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     Dev &d = h->d;
     cudaFree(d.eta); cudaFree(d.beta); cudaFree(d.shat); cudaFree(d.acc); cudaFree(d.sync); cudaFree(d.xbuf);
-    cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr);
+    cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr); cudaFree(d.slots);
     cudaFree(h->scratch_dev); cudaFree(h->prof_dev); cudaFree(h->colstat_dev);
     if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
@@ -740,6 +749,7 @@ static int finish_set_data(cgg_handle *h) {
     h->has_data = true;
     std::fill(h->chain_init.begin(), h->chain_init.end(), 0);
     std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);
+    std::fill(h->fx_mag.begin(), h->fx_mag.end(), 0);
     return CGG_OK;
 }
 
@@ -793,7 +803,7 @@ extern "C" int cgg_init_chain(cgg_handle *h, int32_t chain, const double *beta0_
     CK(cudaMemcpyAsync(d.cs + chain, &cs, sizeof cs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->chain_init[chain] = 1;
-    h->fx_valid[chain] = 0;
+    h->fx_valid[chain] = 0; h->fx_mag[chain] = 0;
     return CGG_OK;
 }
 
@@ -811,7 +821,7 @@ extern "C" int cgg_set_state(cgg_handle *h, int32_t chain, const double *beta_ho
     CK(cudaMemcpyAsync(d.cs + chain, &cs, sizeof cs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->chain_init[chain] = 1;
-    h->fx_valid[chain] = 0;
+    h->fx_valid[chain] = 0; h->fx_mag[chain] = 0;
     return CGG_OK;
 }
 
@@ -908,7 +918,7 @@ extern "C" int cgg_update_eta(cgg_handle *h, int32_t chain, int64_t j, double ne
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(d.beta + (int64_t)chain * d.p + j, &new_beta_j, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->fx_valid[chain] = 0;
+    h->fx_valid[chain] = 0; h->fx_mag[chain] = 0;
     return CGG_OK;
 }
 
@@ -1038,7 +1048,7 @@ extern "C" void *cgg_stream(cgg_handle *h) { return h ? (void *)h->stream : null
 
 extern "C" int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads) {
     if (!h) return fail(CGG_E_ARG, "cgg_launch_shape: NULL handle");
-    if (ctas) *ctas = h->d.G;
+    if (ctas) *ctas = h->d.G + (h->cfg.driver == CGG_DRIVER_PERSISTENT ? 1 : 0);   // + the decider CTA
     if (threads) *threads = THREADS;
     return CGG_OK;
 }
@@ -1054,9 +1064,12 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         if (!h->chain_init[c]) return fail(CGG_E_STATE, "cgg_run: chain %d not initialised (cgg_init_chain)", c);
     if (d.sharded && !h->xfn && !h->comm) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
     CK(cudaSetDevice(h->cfg.device));
+    const bool light = d.jet_light && d.family == CGG_BINOMIAL;
     for (int c = 0; c < C; ++c) {
+        if (light && h->fx_mag[c]) continue;     // light passes only use |f(x0)| as a magnitude: the carried value will do
         int rc = ensure_fx(h, c);
         if (rc) return rc;
+        h->fx_mag[c] = 1;
     }
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_iter == 0) return CGG_OK;
@@ -1103,10 +1116,17 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemcpyAsync(d.hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * NV, h->stream));
     CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
+    CK(cudaMemsetAsync(d.slots, 0, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G, h->stream));   // stamps restart with the versions
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
     if (want_prof) {
-        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 128));
-        CK(cudaMemsetAsync(h->prof_dev, 0, 128, h->stream));
+        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 8 * (16 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128)));
+        CK(cudaMemsetAsync(h->prof_dev, 0, 8 * (16 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128), h->stream));
+        {   // arrival minima start at +inf
+            std::vector<unsigned long long> init((size_t)32 * 128 * 4, 0ULL);
+            for (size_t i = 2; i < init.size(); i += 4) init[i] = ~0ULL;
+            CK(cudaMemcpyAsync(h->prof_dev + 16 + 4096, init.data(), 8 * init.size(), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
     }
     d.prof = want_prof ? h->prof_dev : nullptr;
 
@@ -1115,7 +1135,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     if (h->cfg.driver == CGG_DRIVER_PERSISTENT) {
         Dev dd = d;
         void *args[] = {&dd};
-        CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G), dim3(THREADS), args, h->smem, h->stream));
+        CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G + 1), dim3(THREADS), args, h->smem, h->stream));
         launches = 1;
     } else {
         const int batch = (d.sharded && !h->comm) ? 1 : 32;   // host callbacks are synchronous; NCCL and kernels queue up
@@ -1154,7 +1174,40 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         const double nw = pr[6] ? (double)pr[6] : 1.0;
         fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-passes/worker %.1f workers %llu\n",
                 ms, pr[0] / nw, pr[1] / nw, pr[3] / nw, pr[2] / nw, pr[5] / nw, pr[4] / nw, pr[6]);
-        fprintf(stderr, "[cgg profile] decisions %llu, mean cycles per decision %.0f\n", pr[8], pr[8] ? (double)pr[7] / (double)pr[8] : 0.0);
+        fprintf(stderr, "[cgg profile] decisions %llu, mean cycles per decision %.0f | polls that found the decision not yet published %llu, look-aheads %llu (published: %llu)\n",
+                pr[8], pr[8] ? (double)pr[7] / (double)pr[8] : 0.0, pr[9], pr[10], pr[11]);
+        if (getenv("CGG_PROFILE_TRACE")) {
+            std::vector<unsigned long long> tr((size_t)d.C * 128 * 4);
+            CK(cudaMemcpy(tr.data(), h->prof_dev + 16 + 4096, 8 * tr.size(), cudaMemcpyDeviceToHost));
+            const unsigned long long t0 = tr[(0 * 128 + 0) * 4 + 0];
+            std::vector<unsigned long long> need((size_t)32 * 128);
+            CK(cudaMemcpy(need.data(), h->prof_dev + 16 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32, 8 * need.size(), cudaMemcpyDeviceToHost));
+            for (int v = 40; v < 44; ++v)
+                for (int c = 0; c < d.C; ++c) {
+                    const unsigned long long *q = &tr[((size_t)c * 128 + v) * 4];
+                    fprintf(stderr, "[cgg trace] pass %d chain %d: first warp done %.1f us, last warp done %.1f us, decider saw it %.1f us, decision published %.1f us | a leader warp needed it at %.1f us\n",
+                            v, c, (q[2] - t0) * 1e-3, (q[3] - t0) * 1e-3, (q[0] - t0) * 1e-3, (q[1] - t0) * 1e-3, (need[(size_t)c * 128 + v] - t0) * 1e-3);
+                }
+        }
+        if (getenv("CGG_PROFILE_WARPS")) {
+            std::vector<unsigned long long> pw(2 * (size_t)d.G * NWARPS);
+            CK(cudaMemcpy(pw.data(), h->prof_dev + 16 + 4096 + 32 * 128 * 4, 8 * pw.size(), cudaMemcpyDeviceToHost));
+            for (int b = 0; b < d.G; b += 1) {
+                fprintf(stderr, "[cgg warps] cta %3d wait(k cycles):", b);
+                for (int w = 0; w < NWARPS; ++w) fprintf(stderr, " %5.0f", pw[2 * ((size_t)b * NWARPS + w)] * 1e-3);
+                fprintf(stderr, " | finish of (chain 0, pass 60), us after the first:");
+                unsigned long long tmin = ~0ULL;
+                for (size_t i = 1; i < pw.size(); i += 2) if (pw[i] && pw[i] < tmin) tmin = pw[i];
+                for (int w = 0; w < NWARPS; ++w) fprintf(stderr, " %4.1f", (pw[2 * ((size_t)b * NWARPS + w) + 1] - tmin) * 1e-3);
+                fprintf(stderr, "\n");
+            }
+        }
+        if (getenv("CGG_PROFILE_CTAS")) {
+            std::vector<unsigned long long> pc(4 * (size_t)d.G);
+            CK(cudaMemcpy(pc.data(), h->prof_dev + 16, 8 * pc.size(), cudaMemcpyDeviceToHost));
+            for (int b = 0; b < d.G; ++b)
+                fprintf(stderr, "[cgg cta] %3d sm %3llu wait %.3g tiles %.3g rows %.3g\n", b, pc[4 * b + 3], (double)pc[4 * b] / NWARPS, (double)pc[4 * b + 1] / NWARPS, (double)pc[4 * b + 2] / NWARPS);
+        }
     }
 
     CK(cudaMemcpy(&hdr, d.hdr, sizeof hdr, cudaMemcpyDeviceToHost));

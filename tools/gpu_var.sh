@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-( timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/gpu_tests.log 2>&1
-cat gpurun_out/gpu_tests.log
-unset CGG_PROFILE
-CMD2="python bench.py --workload cfg3 --cols 100 --steps 1 --warmup 1 --burnin-iters 30 --no-e2e --no-cpu"
-$CMD2 > gpurun_out/plain_p100.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_persistent -s 2 -c 1 -f -o gpurun_out/prof_binom_light $CMD2 > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+B="python bench.py --no-e2e --no-cpu --steps 2 --warmup 1"
+export CGG_PROFILE=1
+( timeout 600 python -m pytest tests/test_gpu_jet.py -x -q 2>&1 | tail -2
+echo "== nofence full"; timeout 600 $B 2>&1 | grep -v "slice-width\|trace" | cut -c1-300 | tail -3
+echo "== fence.acq_rel.cta full"; CGG_LIB=$PWD/tools/var/lib_fence.so timeout 600 $B 2>&1 | grep -v "slice-width\|trace" | cut -c1-300 | tail -3 ) > gpurun_out/var.log 2>&1
+cat gpurun_out/var.log
