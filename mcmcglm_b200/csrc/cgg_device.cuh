@@ -78,7 +78,7 @@ struct __align__(16) ChainState {
     int32_t npass;      // passes spent on this update (non-termination guard)
     int32_t j;
     int32_t fine_next;  // the previous pass left a pre-filtered candidate undecided: score everything in fp64 next
-    int32_t pad;
+    int32_t jet_skip;   // a jet pass of this sweep met rows within reach of a clamp: exact passes until the sweep ends
     int64_t iter;       // iterations completed in this run
     uint64_t cursor;    // uniforms consumed before this update
     uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
@@ -829,6 +829,9 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     if (!light) {
         if (!(fabs(m[0]) < INFINITY)) { s.status = CGG_E_NAN; return JET_EXACT; }     // f(x0) itself is not finite
         s.fx0 = (m[0] + d.ll_const) + s.prior_sum;   // the reference's first evaluation, f(x0), at the committed eta
+        // rows within reach of a link clamp (a chain still far from its stationary region): no enclosure will apply
+        // until eta has moved, so do not spend jet passes on the rest of this sweep (a cost decision only)
+        if (d.family != CGG_GAUSSIAN && m[9] != 0.0) s.jet_skip = 1;
     }
     const double fmag = light ? fabs(s.fx0) + 1.0 : fabs(m[0]);
     const double *cst = d.colstat + (int64_t)s.j * CS_STRIDE;
@@ -1044,7 +1047,9 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         v = warp_sum(v);
         s.prior_sum = v;
     }
-    if (status == CGG_OK && d.jet && (phase == PH_START || retry_full)) {
+    const int jskip = __shfl_sync(0xffffffffu, (j == 0 && phase == PH_START) ? 0 : s.jet_skip, 0);   // a new sweep tries again
+    if (lane == 0) s.jet_skip = jskip;
+    if (status == CGG_OK && d.jet && ((phase == PH_START && !jskip) || retry_full)) {
         // jet mode: the next pass of this chain applies the pending eta update and delivers the derivative moments along
         // the new column (and the exact f(x0) if it is a full pass); the whole update is then decided from them
         if (lane == 0) {

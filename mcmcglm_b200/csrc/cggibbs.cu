@@ -1105,7 +1105,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         cs[c].updates = cs[c].chain_passes = cs[c].commit_passes = cs[c].cand_evals = 0;
         cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = cs[c].coarse_evals = cs[c].coarse_undecided = 0;
         cs[c].jet_passes = cs[c].jet_fallbacks = cs[c].jet_retries = 0;
-        cs[c].fine_next = 0;
+        cs[c].fine_next = 0; cs[c].jet_skip = 0;
         ctl[c].commit_j = -1;
     }
     Hdr hdr;
