@@ -15,10 +15,13 @@ namespace cgg {
 constexpr int KMAX = CGG_KMAX;
 constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate sums + the two error-bound sums of the pre-filter
 #ifndef CGG_THREADS
-#define CGG_THREADS 512
+#define CGG_THREADS 256     // 8 warps per SM: measured best (16 warps: more per-pass overhead than latency hiding gained)
 #endif
 #ifndef CGG_RING_D
 #define CGG_RING_D 4
+#endif
+#ifndef CGG_JET_TPI
+#define CGG_JET_TPI 2        // tiles a warp scores per iteration of the jet loop (1 or 2)
 #endif
 constexpr int THREADS = CGG_THREADS;   // one CTA per SM, THREADS/32 warp-workers each
 constexpr int NWARPS = THREADS / 32;
@@ -346,24 +349,47 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
         unsigned stage = 0;
         const int64_t step = cs.W * TILE_ROWS;
         const int64_t i0 = cs.vw * TILE_ROWS + 2 * lane;
-        const double *pe = eta + i0 + (RING_D - 1) * step, *py = cs.y + i0 + (RING_D - 1) * step;
+        const double *pe = eta + i0 + (RING_D - 1) * step, *py = cs.y + i0 + (RING_D - 1) * step;     // not const: issue_next advances them
         const double *px = cs.xj + i0 + (RING_D - 1) * step, *pc = cs.xc + i0 + (RING_D - 1) * step;
         const double *const pe_last = eta + (n - 1);                   // a pair at p is inside the matrix iff p < pe_last
         const double *const pe_end = eta + cs.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
         const uint32_t sbase = cs.slot0;
-        for (; pe < pe_end; pe += step, py += step, px += step, pc += step) {
+        auto issue_next = [&](unsigned st) {       // the tile at the running pointers goes to ring stage st
             if (pe < pe_last) {
-                const uint32_t sa = sbase + ((stage + RING_D - 1) & (RING_D - 1)) * (RING_OPS * 512u);
+                const uint32_t sa = sbase + st * (RING_OPS * 512u);
                 cp_async16(sa, pe);
                 cp_async16(sa + 512u, py); cp_async16(sa + 1024u, px);
                 if (cj >= 0) cp_async16(sa + 1536u, pc);
             }
             cp_async_commit();
+            pe += step; py += step; px += step; pc += step;
+        };
+#if CGG_JET_TPI == 2
+        // Two tiles (four rows per lane) per iteration: with 2 warps per scheduler the loop is bound by the dependency
+        // latency of a row's exp -> reciprocal -> moments chain, and the second tile's chain fills the gaps.
+        static_assert(RING_D >= 4, "two tiles per iteration need a ring of at least 4 stages");
+        for (; pe < pe_end; ) {
+            issue_next((stage + RING_D - 1) & (RING_D - 1));
+            cp_async_wait<RING_D - 2>();
+            double *e0 = const_cast<double *>(pe) - RING_D * step, *e1 = e0 + step;
+            if (e1 < pe_last) {
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk);
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)((stage + 1) & (RING_D - 1)), e1, tab, m, risk);
+            } else if (e0 < pe_last) {
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk);
+            }
+            issue_next(stage);
+            stage = (stage + 2) & (RING_D - 1);
+        }
+#else
+        for (; pe < pe_end; ) {
+            issue_next((stage + RING_D - 1) & (RING_D - 1));
             cp_async_wait<RING_D - 1>();
-            double *ecur = const_cast<double *>(pe) - (RING_D - 1) * step;
+            double *ecur = const_cast<double *>(pe) - RING_D * step;
             if (ecur < pe_last) jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk);
             stage = (stage + 1) & (RING_D - 1);
         }
+#endif
     }
     cp_async_wait<0>();
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar

@@ -11,3 +11,5 @@ echo "== cfg4 p=100"; timeout 300 $B --workload cfg4 --cols 100 2>&1 | grep -v "
 echo "== cfg2"; timeout 300 $B --workload cfg2 2>&1 | grep -v "slice-width" | cut -c1-300| tail -3
 echo "== cfg3 p=100 C=1"; timeout 300 $B --workload cfg3 --cols 100 --chains 1 2>&1 | grep -v "slice-width\|trace" | cut -c1-300| tail -3 ) > gpurun_out/var.log 2>&1
 cat gpurun_out/var.log
+( echo "== cfg3 full no-jet"; timeout 600 $B --steps 2 --warmup 1 --no-jet 2>&1 | grep -v "slice-width\|trace" | cut -c1-300 | tail -3 ) >> gpurun_out/var.log 2>&1
+tail -4 gpurun_out/var.log
