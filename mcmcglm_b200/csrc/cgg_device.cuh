@@ -108,7 +108,7 @@ struct Dev {
     int64_t n, p, ldx, lde, n_tiles, n_iter;
     uint64_t n_u, seed;
     int64_t max_steps;
-    double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale;
+    double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds)
     PriorParams prior;
     int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, pad_;
 };
@@ -852,9 +852,10 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     s.npass++; s.jet_passes++;
     if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
     ct.coarse_mask = 0;
+    const double llc = d.sharded ? 0.0 : d.ll_const;   // row-sharded: every shard's constant is already inside the exchanged M_0
     if (!light) {
         if (!(fabs(m[0]) < INFINITY)) { s.status = CGG_E_NAN; return JET_EXACT; }     // f(x0) itself is not finite
-        s.fx0 = (m[0] + d.ll_const) + s.prior_sum;   // the reference's first evaluation, f(x0), at the committed eta
+        s.fx0 = (m[0] + llc) + s.prior_sum;          // the reference's first evaluation, f(x0), at the committed eta
         // rows within reach of a link clamp (a chain still far from its stationary region): no enclosure will apply
         // until eta has moved, so do not spend jet passes on the rest of this sweep (a cost decision only)
         if (d.family != CGG_GAUSSIAN && m[9] != 0.0) s.jet_skip = 1;
@@ -883,7 +884,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     // verdict on candidate v; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
     auto verdict = [&](double v, bool &in, bool &out, double &fnew) {
         double B;
-        const double dl = jet_eval(d.family, m, cst, (double)d.n, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B);
+        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B);
         B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
         if (light) {
             const double t = dl + (prior_logdens(d.prior, v) - prior_x0);
@@ -894,8 +895,8 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
             // same expression order as the exact path: (ll + ll_const) + (prior_rest + prior(v)), monotone in ll
             const double ll = m[0] + dl;
             const double pr = s.prior_rest + prior_logdens(d.prior, v);
-            const double flo = ((ll - B) + d.ll_const) + pr, fhi = ((ll + B) + d.ll_const) + pr;
-            fnew = (ll + d.ll_const) + pr;
+            const double flo = ((ll - B) + llc) + pr, fhi = ((ll + B) + llc) + pr;
+            fnew = (ll + llc) + pr;
             in = s.ylev < flo;
             out = fhi <= s.ylev;
         }

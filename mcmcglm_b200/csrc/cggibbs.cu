@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
         else {
             const bool jet = ((unsigned)d.ctl[c].coarse_mask & JET_BIT) != 0u;
             const int nc = jet ? NV : d.ctl[c].ncand;
-            if (lane < NV) d.xbuf[c * NV + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + (jet ? 0.0 : d.ll_const) : 0.0;
+            if (lane < NV) d.xbuf[c * NV + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + ((jet && !(d.sharded && lane == 0)) ? 0.0 : d.ll_const) : 0.0;
         }
     }
     __syncthreads();
@@ -382,18 +382,25 @@ __global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial,
     }
 }
 
-// Per-column statistics for the jet passes (cgg_jet.cuh), one CTA per column: cs = 2^-e with max|x| * cs in [0.5, 1)
-// (exact scaling), S_k = sum_i |x_i cs|^k for k = 1..8 rounded UP (they enter error bounds), max|x|, and for the
-// binomial family C1 = sum_i x_i cs (y_i - 1/2) with compensated (two-sum) accumulation.
+// Per-column statistics for the jet passes (cgg_jet.cuh), one CTA per column, in two steps so that a row-sharded
+// handle can reduce them over the ranks in between:
+//   col_max_kernel   the binary exponent e of max|x| (frexp), as a one-hot entry of a small histogram per column
+//                    (bins for e in [-CS_EMAX, CS_EMAX]; anything outside, or a non-finite entry, goes to the two edge
+//                    bins = "this column cannot be scaled").  Histograms ADD across ranks; the top non-empty bin is the
+//                    global exponent, so a sum-only exchange is enough.
+//   col_sums_kernel  cs = 2^-e (max|x| * cs in [0.5, 1): exact scaling), S_k = sum_i |x_i cs|^k for k = 1..8 and, for the
+//                    binomial family, C1 = sum_i x_i cs (y_i - 1/2) with compensated (two-sum) accumulation.  S_k and C1
+//                    add across ranks; col_finish_kernel rounds S_k UP (they enter error bounds).
+constexpr int CS_EMAX = 64;
+constexpr int CS_BINS = 2 * CS_EMAX + 1;
 __device__ __forceinline__ void two_sum_acc(double &s, double &c, double v) {
     const double t = s + v;
     const double bp = t - s;
     c += (s - (t - bp)) + (v - bp);
     s = t;
 }
-__global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, const double *y, int family, int64_t n, int64_t ldx, int64_t p, double *out) {
-    __shared__ double s_red[NWARPS][10];
-    __shared__ double s_cs;
+__global__ void __launch_bounds__(THREADS) col_max_kernel(const double *X, int64_t n, int64_t ldx, int64_t p, double *hist /* [p][CS_BINS], zeroed */) {
+    __shared__ double s_red[NWARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {
         const double *x = X + j * ldx;
@@ -401,20 +408,37 @@ __global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, con
         for (int64_t i = threadIdx.x; i < n; i += THREADS) { const double a = fabs(x[i]); mx = (a > mx || a != a) ? a : mx; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); mx = (t > mx || t != t) ? t : mx; }
-        if (lane == 0) s_red[warp][0] = mx;
+        if (lane == 0) s_red[warp] = mx;
         __syncthreads();
         if (threadIdx.x == 0) {
             double m = 0.0;
-            for (int w = 0; w < NWARPS; ++w) { const double t = s_red[w][0]; m = (t > m || t != t) ? t : m; }
-            int e = 0;
-            double cs = 1.0;
-            if (m > 0.0 && m < INFINITY) { frexp(m, &e); cs = ldexp(1.0, -e); }
-            if (!(cs > 0.0) || !(cs < INFINITY)) cs = 1.0;      // subnormal / huge columns: no scaling (the bounds then simply fail to decide)
-            s_cs = cs;
-            out[j * CS_STRIDE + 0] = cs; out[j * CS_STRIDE + 1] = 1.0 / cs; out[j * CS_STRIDE + 10] = m;
+            for (int w = 0; w < NWARPS; ++w) { const double t = s_red[w]; m = (t > m || t != t) ? t : m; }
+            int bin = CS_EMAX;                                // an all-zero column: exponent 0, cs = 1
+            if (m > 0.0 && m < INFINITY) {
+                int e = 0;
+                frexp(m, &e);
+                bin = (e < -CS_EMAX + 1 || e > CS_EMAX - 1) ? (e < 0 ? 0 : CS_BINS - 1) : e + CS_EMAX;
+            } else if (m != 0.0) bin = CS_BINS - 1;           // Inf / NaN
+            hist[j * CS_BINS + bin] += 1.0;
         }
         __syncthreads();
-        const double cs = s_cs;
+    }
+}
+// cs of column j from its (globally summed) exponent histogram; 0 = the column cannot be scaled
+__device__ __forceinline__ double col_scale(const double *hist, int64_t j) {
+    int top = -1;
+    for (int b = CS_BINS - 1; b >= 0; --b) if (hist[j * CS_BINS + b] != 0.0) { top = b; break; }
+    if (top <= 0 || top == CS_BINS - 1) return 0.0;
+    return ldexp(1.0, -(top - CS_EMAX));
+}
+__global__ void __launch_bounds__(THREADS) col_sums_kernel(const double *X, const double *y, int family, int64_t n, int64_t ldx, int64_t p,
+                                                           const double *hist, double *sums /* [p][10]: S_1..S_8, C1 sum, C1 compensation */) {
+    __shared__ double s_red[NWARPS][10];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {
+        const double *x = X + j * ldx;
+        double cs = col_scale(hist, j);
+        if (cs == 0.0) cs = 1.0;
         double S[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         double c1s = 0.0, c1c = 0.0;
         for (int64_t i = threadIdx.x; i < n; i += THREADS) {
@@ -438,16 +462,32 @@ __global__ void __launch_bounds__(THREADS) col_stats_kernel(const double *X, con
         if (threadIdx.x < 8) {
             double v = 0.0;
             for (int w = 0; w < NWARPS; ++w) v += s_red[w][threadIdx.x];
-            // fp64 summation of n non-negative terms: relative error <= n * 2^-53; inflate so the value is an upper bound
-            out[j * CS_STRIDE + 2 + threadIdx.x] = v * (1.0 + 4.0 * (double)n * 1.1102230246251565e-16 + 1e-12);
+            sums[j * 10 + threadIdx.x] = v;
         }
         if (threadIdx.x == 8) {
             double ss = 0.0, cc = 0.0;
             for (int w = 0; w < NWARPS; ++w) { cc += s_red[w][9]; two_sum_acc(ss, cc, s_red[w][8]); }
-            out[j * CS_STRIDE + 11] = ss + cc;
+            sums[j * 10 + 8] = ss; sums[j * 10 + 9] = cc;
         }
         __syncthreads();
     }
+}
+__global__ void col_finish_kernel(const double *hist, const double *sums, int64_t p, double n_total, double *out /* [p][CS_STRIDE] */) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    const double cs = col_scale(hist, j);
+    double *o = out + j * CS_STRIDE;
+    if (cs == 0.0) {            // not scalable: bounds that never decide
+        o[0] = 1.0; o[1] = 1.0;
+        for (int k = 0; k < 8; ++k) o[2 + k] = INFINITY;
+        o[10] = INFINITY; o[11] = 0.0;
+        return;
+    }
+    o[0] = cs; o[1] = 1.0 / cs;
+    // fp64 summation of n non-negative terms (and of the per-rank partial sums): relative error <= ~n * 2^-53; inflate
+    for (int k = 0; k < 8; ++k) o[2 + k] = sums[j * 10 + k] * (1.0 + 4.0 * n_total * 1.1102230246251565e-16 + 1e-12);
+    o[10] = 1.0 / cs;           // >= max|x|
+    o[11] = sums[j * 10 + 8] + sums[j * 10 + 9];
 }
 
 // Diagnostic (cgg_debug_jet): evaluate the enclosure of chain c's current jet sums at K candidates.
@@ -462,8 +502,8 @@ __global__ void jet_debug_kernel(Dev d, int c, int j, int K, int light, double f
     if (lane < K) {
         double B;
         const double fmag = light ? fmag_light : fabs(m[0]);
-        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, (double)d.n, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B);
-        out[lane] = light ? dl : (m[0] + dl) + d.ll_const;
+        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, d.n_total, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B);
+        out[lane] = light ? dl : (m[0] + dl) + (d.sharded ? 0.0 : d.ll_const);
         out[K + lane] = B * d.jet_bscale + 8.0 * JET_EPS * (fmag + fabs(dl));
     }
     if (lane < NV) out[2 * K + lane] = m[lane];
@@ -536,11 +576,11 @@ struct cgg_handle {
     size_t smem = 0;
     unsigned long long *prof_dev = nullptr;
     Hdr *hdr_pinned = nullptr;
-    bool has_data = false;
+    bool has_data = false, jet_wanted = false;
     std::vector<char> chain_init, fx_valid, fx_mag;   // fx_mag: the carried f(x0) is at least a valid magnitude (light jet passes)
     int num_sms = 0, max_grid = 0;
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
-    ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr;
+    ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr; size_t gather_cap = 0;
     double local_ll_const = 0.0;
 };
 
@@ -559,20 +599,25 @@ static void *kernel_ptr(int family, int which) {
 }
 
 // Row-sharded mode: turn the local per-candidate sums in d.xbuf into global sums, identical on every rank.
-static int exchange(cgg_handle *h) {
-    Dev &d = h->d;
-    const int count = d.C * NV;
+// Row-sharded mode: turn a device buffer of local sums into global sums, identical on every rank.
+static int exchange_buf(cgg_handle *h, double *buf, int64_t count) {
     if (h->comm) {
-        ncclResult_t r = g_nccl.AllGather(d.xbuf, h->gather_dev, (size_t)count, ncclDouble, h->comm, h->stream);
+        if ((size_t)count > h->gather_cap) {
+            cudaFree(h->gather_dev); h->gather_dev = nullptr; h->gather_cap = 0;
+            CK(cudaMalloc((void **)&h->gather_dev, sizeof(double) * (size_t)h->world * (size_t)count));
+            h->gather_cap = (size_t)count;
+        }
+        ncclResult_t r = g_nccl.AllGather(buf, h->gather_dev, (size_t)count, ncclDouble, h->comm, h->stream);
         if (r != ncclSuccess) return fail(CGG_E_COMM, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
-        rank_sum_kernel<<<(count + 127) / 128, 128, 0, h->stream>>>(h->gather_dev, h->world, count, d.xbuf);
+        rank_sum_kernel<<<(int)((count + 127) / 128), 128, 0, h->stream>>>(h->gather_dev, h->world, (int)count, buf);
         CK(cudaGetLastError());
         return CGG_OK;
     }
     if (!h->xfn) return fail(CGG_E_STATE, "row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
-    if (h->xfn(h->xuser, d.xbuf, (int64_t)count, (void *)h->stream) != 0) return fail(CGG_E_COMM, "exchange callback failed");
+    if (h->xfn(h->xuser, buf, count, (void *)h->stream) != 0) return fail(CGG_E_COMM, "exchange callback failed");
     return CGG_OK;
 }
+static int exchange(cgg_handle *h) { return exchange_buf(h, h->d.xbuf, (int64_t)h->d.C * NV); }
 
 static int launch_pass(cgg_handle *h, int mode) {
     Dev d = h->d;
@@ -611,14 +656,15 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     memset(&h->d, 0, sizeof(Dev));
     Dev &d = h->d;
     const int C = cfg->n_chains;
-    d.n = cfg->n; d.p = cfg->p; d.C = C; d.K = cfg->K; d.family = cfg->family;
+    d.n = cfg->n; d.p = cfg->p; d.C = C; d.K = cfg->K; d.family = cfg->family; d.n_total = (double)cfg->n;
     d.inv_sd = 1.0 / (cfg->family == CGG_GAUSSIAN ? cfg->sd : 1.0);
     d.w = cfg->w; d.max_steps = cfg->max_steps < 0 ? -1 : cfg->max_steps;
     d.seed = cfg->seed; d.chain_offset = cfg->chain_offset; d.tau = cfg->spec_tau;
     d.sharded = cfg->mode == CGG_MODE_ROW_SHARDED;
     d.coarse = (cfg->family == CGG_BINOMIAL) && !d.sharded && !(cfg->flags & CGG_FLAG_NO_PREFILTER);
     d.coarse_theta = getenv("CGG_COARSE_THETA") ? atof(getenv("CGG_COARSE_THETA")) : 0.4;
-    d.jet = !d.sharded && !(cfg->flags & CGG_FLAG_NO_JET);
+    h->jet_wanted = !(cfg->flags & CGG_FLAG_NO_JET);
+    d.jet = h->jet_wanted && !d.sharded;     // row-sharded: decided at cgg_set_data (needs the exchange for the column statistics)
     d.jet_bscale = (cfg->jet_bound_scale > 0.0) ? cfg->jet_bound_scale : 1.0;
     d.jet_light = d.jet && !(cfg->flags & CGG_FLAG_NO_JET_LIGHT);
     d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
@@ -740,11 +786,42 @@ static int finish_set_data(cgg_handle *h) {
     if (d.family == CGG_GAUSSIAN) d.ll_const = -(double)d.n * (kLnSqrt2Pi + log(h->cfg.sd));
     else if (d.family == CGG_POISSON) d.ll_const = -(double)s;
     else d.ll_const = 0.0;
+    if (h->jet_wanted) {
+        // column statistics of the jet passes; a row-sharded handle reduces them over the ranks (needs its exchange now)
+        d.jet = (!d.sharded || h->comm || h->xfn) ? 1 : 0;
+        d.jet_light = d.jet && !(h->cfg.flags & CGG_FLAG_NO_JET_LIGHT);
+    }
     if (d.jet) {
         const int grid = (int)std::min<int64_t>(d.p, 4 * (int64_t)h->num_sms);
-        col_stats_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.y, d.family, d.n, d.ldx, d.p, h->colstat_dev);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(h->stream));
+        double *hist = nullptr, *sums = nullptr;
+        CK(cudaMalloc((void **)&hist, sizeof(double) * (size_t)d.p * CS_BINS));
+        CK(cudaMalloc((void **)&sums, sizeof(double) * (size_t)d.p * 10));
+        int rc = CGG_OK;
+        cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(double) * (size_t)d.p * CS_BINS, h->stream);
+        if (e == cudaSuccess) { col_max_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.n, d.ldx, d.p, hist); e = cudaGetLastError(); }
+        if (e == cudaSuccess && d.sharded) rc = exchange_buf(h, hist, d.p * CS_BINS);
+        if (e == cudaSuccess && rc == CGG_OK) { col_sums_kernel<<<grid, THREADS, 0, h->stream>>>(d.X, d.y, d.family, d.n, d.ldx, d.p, hist, sums); e = cudaGetLastError(); }
+        double n_total[1] = {(double)d.n};
+        if (e == cudaSuccess && rc == CGG_OK && d.sharded) {
+            rc = exchange_buf(h, sums, d.p * 10);
+            // the global row count (for the rounding allowance of the sums) travels the same way
+            if (rc == CGG_OK) {
+                e = cudaMemcpyAsync(h->scratch_dev, n_total, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+                if (e == cudaSuccess) rc = exchange_buf(h, h->scratch_dev, 1);
+                if (e == cudaSuccess && rc == CGG_OK) e = cudaMemcpyAsync(n_total, h->scratch_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            }
+        }
+        if (e == cudaSuccess && rc == CGG_OK) {
+            col_finish_kernel<<<(int)((d.p + 127) / 128), 128, 0, h->stream>>>(hist, sums, d.p, n_total[0], h->colstat_dev);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(hist); cudaFree(sums);
+        if (rc != CGG_OK) return rc;
+        CK(e);
+        d.n_total = n_total[0];
     }
     h->has_data = true;
     std::fill(h->chain_init.begin(), h->chain_init.end(), 0);
@@ -1041,6 +1118,7 @@ extern "C" int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, co
     if (r != ncclSuccess) { h->comm = nullptr; return fail(CGG_E_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
     h->world = world; h->rank = rank;
     CK(cudaMalloc((void **)&h->gather_dev, sizeof(double) * (size_t)world * h->d.C * NV));
+    h->gather_cap = (size_t)h->d.C * NV;
     return CGG_OK;
 }
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _run_two_shards_one_gpu(family, prior, X, y, beta0, w, iters, replay_u=None, seed=0, sd=1.0):
+def _run_two_shards_one_gpu(family, prior, X, y, beta0, w, iters, replay_u=None, seed=0, sd=1.0, **ekw):
     import torch
     world = 2
     n, p = X.shape
@@ -28,7 +28,7 @@ def _run_two_shards_one_gpu(family, prior, X, y, beta0, w, iters, replay_u=None,
         try:
             lo, hi = shard_rows(n, world, r)
             e = Engine(hi - lo, p, family=family, sd=sd, w=w, n_chains=1, K=6, driver="stepwise", row_sharded=True,
-                       seed=seed, **PRIOR_CASES[prior])
+                       seed=seed, **PRIOR_CASES[prior], **ekw)
 
             def xfn(ptr, count, stream):
                 t = torch.as_tensor(DeviceBuffer(ptr, count), device="cuda")
@@ -65,6 +65,7 @@ def test_readme_chain_row_sharded_in_two():
     for S, st, state, f, (lo, hi) in out:
         assert np.max(np.abs(S - z["samples"][1:201])) <= 1e-9           # every rank holds the reference's chain
         assert st["ref_evals"] > 0
+        assert st["jet_passes"] >= st["updates"] - st["jet_fallbacks"] > 0   # one exchanged pass per update (jet passes)
     assert np.array_equal(out[0][0], out[1][0])                          # ranks took identical branches, bit for bit
     assert out[0][3][0] == out[1][3][0]
     eta_full = np.concatenate([out[0][2][1], out[1][2][1]])
@@ -78,8 +79,15 @@ def test_sharded_matches_oracle(family, prior):
     b0 = np.zeros(4)
     ref = oracle.run_chain(m, X, y, b0, w=0.3, n_iter=25, seed=9, chain=0)
     out = _run_two_shards_one_gpu(family, prior, X, y, b0, 0.3, 25, seed=9)
-    for S, *_ in out:
+    for S, st, *_ in out:
         assert np.max(np.abs(S - ref["samples"])) <= 1e-9
+        assert st["jet_passes"] > 0
+    # and bit for bit the chain of the exact passes (column statistics reduced over the shards, per-shard constants)
+    exact = _run_two_shards_one_gpu(family, prior, X, y, b0, 0.3, 25, seed=9, jet=False)
+    assert exact[0][1]["jet_passes"] == 0
+    assert np.array_equal(out[0][0], exact[0][0]) and np.array_equal(out[1][0], exact[1][0])
+    for k in ("ref_evals", "stepouts", "shrinks", "uniforms_used"):
+        assert out[0][1][k] == exact[0][1][k]
 
 
 def _nccl_worker(rank, world, port, q):
