@@ -102,6 +102,7 @@ struct Dev {
     double *eta, *beta, *shat, *samples, *xbuf;
     const double *replay;
     const double *colstat;     // [p][CS_STRIDE] per-column scale and absolute moments (jet passes)
+    const double *gathered;    // row-sharded over NCCL: [world][C * NV] all-gathered per-rank sums (added in rank order by the decider)
     double *slots;             // [C][G][NV] per-CTA partial sums of the pass in flight (persistent driver)
     Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
     unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
@@ -110,7 +111,7 @@ struct Dev {
     int64_t max_steps;
     double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds)
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, pad_;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -234,9 +235,63 @@ struct ChainStream {
     }
 };
 
+// Scores every live candidate of the chain on NP row pairs (NP tiles of this lane) and adds the terms to the per-lane
+// running sums in shared memory.  Two candidates per loop iteration x NP tiles x two rows: the independent dependency
+// chains a warp needs in flight with 2 warps per scheduler.
+template <int FAMILY, int NP>
+__device__ __forceinline__ void score_pairs(const RowPair<FAMILY> (&rp)[NP], int nc, unsigned cmask, const double *s_dl, double inv_sd,
+                                            const double2 *tab, double *sacc, int lane, float &bE, float &bX, unsigned &nearmask) {
+    const unsigned all = (nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u);
+    unsigned fine = all & ~cmask;
+    if (FAMILY == CGG_BINOMIAL && cmask) {
+        // pre-filter: candidates flagged in cmask are scored in fp32 (hardware ex2/lg2); the sums of
+        // |eta| and |x| over the rows feed the rigorous error bound the decider applies
+        float ef0[NP], ef1[NP], xf0[NP], xf1[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            ef0[q] = (float)rp[q].e0; ef1[q] = (float)rp[q].e1; xf0[q] = (float)rp[q].x0; xf1[q] = (float)rp[q].x1;
+            bE += fabsf(ef0[q]) + fabsf(ef1[q]);
+            bX += fabsf(xf0[q]) + fabsf(xf1[q]);
+        }
+        unsigned cm = cmask & all;
+        while (cm) {
+            const int k0 = __ffs(cm) - 1; cm &= cm - 1;
+            const int k1 = cm ? __ffs(cm) - 1 : k0;
+            if (cm) cm &= cm - 1;
+            const float d0 = (float)s_dl[k0], d1 = (float)s_dl[k1];
+            bool n0 = false, n1 = false;
+            float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                v0 += softplus32(fmaf(xf0[q], d0, ef0[q]), n0) + softplus32(fmaf(xf1[q], d0, ef1[q]), n0);
+                v1 += softplus32(fmaf(xf0[q], d1, ef0[q]), n1) + softplus32(fmaf(xf1[q], d1, ef1[q]), n1);
+            }
+            if (n0) nearmask |= 1u << k0;
+            sacc[k0 * 32 + lane] -= (double)v0;
+            if (k1 != k0) { if (n1) nearmask |= 1u << k1; sacc[k1 * 32 + lane] -= (double)v1; }
+        }
+    }
+    while (fine) {
+        const int k0 = __ffs(fine) - 1; fine &= fine - 1;
+        if (fine) {
+            const int k1 = __ffs(fine) - 1; fine &= fine - 1;
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) { t0 += rp[q].term(s_dl[k0], inv_sd, tab); t1 += rp[q].term(s_dl[k1], inv_sd, tab); }
+            sacc[k0 * 32 + lane] += t0;
+            sacc[k1 * 32 + lane] += t1;
+        } else {
+            double t0 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) t0 += rp[q].term(s_dl[k0], inv_sd, tab);
+            sacc[k0 * 32 + lane] += t0;
+        }
+    }
+}
+
 // One warp, one chain, one pass.  The candidate loop is a run-time loop (trip count nc is warp-uniform) with
 // the per-lane running sums in shared memory: sacc[k * 32 + lane].  s_dl[k] = cand_k - beta_j comes from the
-// CTA's shared control block.  `prefetched`: the prologue of this chain was already issued.
+// CTA's shared control block.  `prefetched`: the prologue of this chain was already issued.  Two tiles per iteration.
 template <int FAMILY>
 __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream &cs, double cdelta, const double *s_dl,
                                                 int lane, const double2 *tab, double *sacc, bool prefetched,
@@ -246,60 +301,43 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
     double *eta = cs.eta;
     if (!prefetched) cs.prologue(lane);
     for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] = 0.0;
-    int stage = 0;
-    for (long long T = cs.vw; T < cs.n_tiles; T += cs.W) {
-        cs.issue(T + (RING_D - 1) * cs.W, (stage + RING_D - 1) % RING_D, lane);
-        cp_async_wait<RING_D - 1>();
-        const int64_t i = T * TILE_ROWS + 2 * lane;
-        if (i + 1 < n) {
-            const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
-            double2 e = lds2(s);
-            if (cj >= 0) {
-                const double2 cv = lds2(s + 1536u);
-                e.x = eta_shift(e.x, cv.x, cdelta);
-                e.y = eta_shift(e.y, cv.y, cdelta);
-                *reinterpret_cast<double2 *>(eta + i) = e;
-            }
+    static_assert(RING_D >= 4 && (RING_D & (RING_D - 1)) == 0, "two tiles per iteration: ring of >= 4 stages, power of two");
+    // the committed (and, if an update is pending, written back) eta of this lane's pair in tile T
+    auto load_eta = [&](unsigned stage, int64_t i) {
+        const uint32_t s = cs.slot0 + stage * (RING_OPS * 512u);
+        double2 e = lds2(s);
+        if (cj >= 0) {
+            const double2 cv = lds2(s + 1536u);
+            e.x = eta_shift(e.x, cv.x, cdelta);
+            e.y = eta_shift(e.y, cv.y, cdelta);
+            *reinterpret_cast<double2 *>(eta + i) = e;
+        }
+        return e;
+    };
+    unsigned stage = 0;
+    for (long long T = cs.vw; T < cs.n_tiles; T += 2 * cs.W) {
+        cs.issue(T + (RING_D - 1) * cs.W, (int)((stage + RING_D - 1) & (RING_D - 1)), lane);
+        cp_async_wait<RING_D - 2>();
+        const unsigned st1 = (stage + 1) & (RING_D - 1);
+        const int64_t i0 = T * TILE_ROWS + 2 * lane, i1 = i0 + cs.W * TILE_ROWS;
+        if (i1 + 1 < n) {
+            const double2 ea = load_eta(stage, i0), eb = load_eta(st1, i1);
             if (nc > 0) {
-                const RowPair<FAMILY> rp(lds2(s + 512u), e, lds2(s + 1024u));
-                // Two candidates per iteration: a warp is bound by the latency of one candidate's dependency chain,
-                // so two independent candidates (x two rows) in flight nearly halve the time per candidate.
-                const unsigned all = (nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u);
-                unsigned fine = all & ~cmask;
-                if (FAMILY == CGG_BINOMIAL && cmask) {
-                    // pre-filter: candidates flagged in cmask are scored in fp32 (hardware ex2/lg2); the sums of
-                    // |eta| and |x| over the rows feed the rigorous error bound the decider applies
-                    const float ef0 = (float)rp.e0, ef1 = (float)rp.e1, xf0 = (float)rp.x0, xf1 = (float)rp.x1;
-                    bE += fabsf(ef0) + fabsf(ef1);
-                    bX += fabsf(xf0) + fabsf(xf1);
-                    unsigned cm = cmask & all;
-                    while (cm) {
-                        const int k0 = __ffs(cm) - 1; cm &= cm - 1;
-                        const int k1 = cm ? __ffs(cm) - 1 : k0;
-                        if (cm) cm &= cm - 1;
-                        const float d0 = (float)s_dl[k0], d1 = (float)s_dl[k1];
-                        bool n0 = false, n1 = false;
-                        const float v0 = softplus32(fmaf(xf0, d0, ef0), n0) + softplus32(fmaf(xf1, d0, ef1), n0);
-                        const float v1 = softplus32(fmaf(xf0, d1, ef0), n1) + softplus32(fmaf(xf1, d1, ef1), n1);
-                        if (n0) nearmask |= 1u << k0;
-                        sacc[k0 * 32 + lane] -= (double)v0;
-                        if (k1 != k0) { if (n1) nearmask |= 1u << k1; sacc[k1 * 32 + lane] -= (double)v1; }
-                    }
-                }
-                while (fine) {
-                    const int k0 = __ffs(fine) - 1; fine &= fine - 1;
-                    if (fine) {
-                        const int k1 = __ffs(fine) - 1; fine &= fine - 1;
-                        const double t0 = rp.term(s_dl[k0], d.inv_sd, tab), t1 = rp.term(s_dl[k1], d.inv_sd, tab);
-                        sacc[k0 * 32 + lane] += t0;
-                        sacc[k1 * 32 + lane] += t1;
-                    } else {
-                        sacc[k0 * 32 + lane] += rp.term(s_dl[k0], d.inv_sd, tab);
-                    }
-                }
+                const uint32_t sa = cs.slot0 + stage * (RING_OPS * 512u), sb = cs.slot0 + st1 * (RING_OPS * 512u);
+                const RowPair<FAMILY> rp[2] = {RowPair<FAMILY>(lds2(sa + 512u), ea, lds2(sa + 1024u)),
+                                               RowPair<FAMILY>(lds2(sb + 512u), eb, lds2(sb + 1024u))};
+                score_pairs<FAMILY, 2>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask);
+            }
+        } else if (i0 + 1 < n) {
+            const double2 ea = load_eta(stage, i0);
+            if (nc > 0) {
+                const uint32_t sa = cs.slot0 + stage * (RING_OPS * 512u);
+                const RowPair<FAMILY> rp[1] = {RowPair<FAMILY>(lds2(sa + 512u), ea, lds2(sa + 1024u))};
+                score_pairs<FAMILY, 1>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask);
             }
         }
-        stage = (stage + 1 == RING_D) ? 0 : stage + 1;
+        cs.issue(T + RING_D * cs.W, (int)stage, lane);
+        stage = (stage + 2) & (RING_D - 1);
     }
     cp_async_wait<0>();
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
@@ -978,6 +1016,13 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
 // The parameter block is taken by pointer -- the kernels pass the address of their __grid_constant__
 // parameter -- so this cold, register-hungry routine stays out of line and off the hot loop's registers.
 enum SumSource : int { SRC_ACC = 0, SRC_XBUF = 1, SRC_SLOTS = 2 };
+// exchanged sum #idx of the row-sharded mode: already reduced in d.xbuf (host hook), or the ranks' parts added in rank order
+__device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
+    if (!d.gathered) return __ldcg(d.xbuf + idx);
+    double v = 0.0;
+    for (int r = 0; r < d.world; ++r) v += __ldcg(d.gathered + (size_t)r * d.C * NV + idx);
+    return v;
+}
 enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
 __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, unsigned long long stamp = 0) {
     const bool from_xbuf = src == SRC_XBUF;
@@ -1000,7 +1045,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         const int nvals = jetpass ? NV : (cmask ? nc + 2 : nc);
         if (!slots_sum(d, c, nvals, stamp, lane, jm)) return DEC_NOT_READY;      // some value is still on its way: nothing was changed
     } else if (jetpass) {
-        const double mv = (lane < NV) ? (from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
+        const double mv = (lane < NV) ? (from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
     }
@@ -1016,7 +1061,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (src == SRC_SLOTS) {
             ll = pick(lane) + d.ll_const;
             if (cmask) { aflags = __ldcg(&d.acc[c * NV + lane].flags); d.acc[c * NV + lane].flags = 0u; }   // clamp-proximity flag of the pre-filter
-        } else ll = from_xbuf ? __ldcg(d.xbuf + c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
+        } else ll = from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
         f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));
     }
     int stop_at = nc;

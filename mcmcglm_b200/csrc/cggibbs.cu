@@ -1223,10 +1223,17 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
                 if (rc) return rc;
                 ++launches;
                 if (d.sharded) {
-                    rc = exchange(h);
-                    if (rc) return rc;
-                    decide_kernel<<<1, THREADS, 0, h->stream>>>(d);
-                    launches += h->comm ? 3 : 1;
+                    Dev dd = d;
+                    if (h->comm) {      // all-gather only: the decider adds the ranks' parts itself, in rank order
+                        ncclResult_t r = g_nccl.AllGather(d.xbuf, h->gather_dev, (size_t)d.C * NV, ncclDouble, h->comm, h->stream);
+                        if (r != ncclSuccess) return fail(CGG_E_COMM, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+                        dd.gathered = h->gather_dev; dd.world = h->world;
+                    } else {
+                        rc = exchange(h);
+                        if (rc) return rc;
+                    }
+                    decide_kernel<<<1, THREADS, 0, h->stream>>>(dd);
+                    launches += h->comm ? 2 : 1;
                 }
             }
             CK(cudaMemcpyAsync(h->hdr_pinned, d.hdr, sizeof(Hdr), cudaMemcpyDeviceToHost, h->stream));
