@@ -406,7 +406,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["desc"], "n": n_total, "rows_per_gpu": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
                            "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver, "jet_passes": not a.no_jet,
-                           "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 8} partial sums per pass, rank-ordered sum)" if sharded
+                           "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 10} partial sums per pass, rank-ordered sum in the decide kernel)" if sharded
                                            else f"chain-parallel x{world} (no collective)"), "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
                            "beta0": "prior draw x %g" % wl["init_scale"], "burnin_iterations": a.burnin_iters},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(agg["launches"]),

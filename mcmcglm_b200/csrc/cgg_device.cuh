@@ -15,7 +15,7 @@ namespace cgg {
 constexpr int KMAX = CGG_KMAX;
 constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate sums + the two error-bound sums of the pre-filter
 #ifndef CGG_THREADS
-#define CGG_THREADS 256     // 8 warps per SM: measured best (16 warps: more per-pass overhead than latency hiding gained)
+#define CGG_THREADS 384     // 12 warps per SM: measured best (16 warps pay more per-pass overhead than the extra latency hiding gains, 8 hide too little)
 #endif
 #ifndef CGG_RING_D
 #define CGG_RING_D 4
