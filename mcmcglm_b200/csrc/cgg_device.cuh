@@ -659,34 +659,112 @@ __device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, i
 
 // Decider side: has every CTA delivered pass `stamp - 1` of chain c?  (entry 0 of each slot; the other entries are
 // validated when they are read)
+constexpr int SLOT_ROUNDS = 5;     // 32 * 5 = 160 >= worker CTAs of a B200: the decider's loads are all issued before any is used
 __device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long long stamp, int lane) {
     const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
     bool ok = true;
-    for (int g = lane; g < d.G; g += 32) ok = ok && (__ldcg(&base[(size_t)g * NV].stamp) == stamp);
+    if (d.G <= 32 * SLOT_ROUNDS) {
+        // a light first look (one load per lane): the deciders share an SM, and a warp that polls with everything it has
+        // slows down the warps that are deciding
+        const bool ok0 = (lane < d.G) ? (__ldcg(&base[(size_t)lane * NV].stamp) == stamp) : true;
+        if (!__all_sync(0xffffffffu, ok0)) return false;
+        unsigned long long st[SLOT_ROUNDS];
+#pragma unroll
+        for (int r = 1; r < SLOT_ROUNDS; ++r) { const int g = lane + 32 * r; st[r] = (g < d.G) ? __ldcg(&base[(size_t)g * NV].stamp) : stamp; }
+#pragma unroll
+        for (int r = 1; r < SLOT_ROUNDS; ++r) ok = ok && (st[r] == stamp);
+    } else {
+        for (int g = lane; g < d.G; g += 32) ok = ok && (__ldcg(&base[(size_t)g * NV].stamp) == stamp);
+    }
     return __all_sync(0xffffffffu, ok);
 }
 
 // Value k of chain c's finished pass = the G slots added in CTA order (lane l takes CTAs l, l + 32, ..., then a
 // butterfly: the same bits in every lane and on every run).  Returns false if some entry does not carry the stamp yet.
-__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
+#ifndef CGG_SLOTSUM_INLINE
+#define CGG_SLOTSUM_INLINE __forceinline__
+#endif
+__device__ CGG_SLOTSUM_INLINE bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
     const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
     double part[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) part[k] = 0.0;
     bool ok = true;
-    for (int g = lane; g < d.G; g += 32) {
-        const int4 *src = reinterpret_cast<const int4 *>(base + (size_t)g * NV);
+    auto take = [&](const int4 &t, int k) {
+        part[k] += __hiloint2double(t.y, t.x);
+        ok = ok && ((((unsigned long long)(unsigned)t.w << 32) | (unsigned)t.z) == stamp);
+    };
+    if (d.G <= 32 * SLOT_ROUNDS) {
+        // five values at a time: their 5 x SLOT_ROUNDS loads are independent and all issued before the first add, so the
+        // decider pays two round trips to L2 instead of one per value (the decision is on every chain's critical cycle)
+#ifndef CGG_SLOT_KB
+#define CGG_SLOT_KB 5
+#endif
+        constexpr int KB = CGG_SLOT_KB;
+        static_assert(NV % KB == 0, "values are read in batches of five");
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
-            if (k < nvals) {
-                const int4 t = __ldcg(src + k);                       // one 16-byte load: {value, stamp}
-                part[k] += __hiloint2double(t.y, t.x);
-                ok = ok && ((((unsigned long long)(unsigned)t.w << 32) | (unsigned)t.z) == stamp);
+        for (int k0 = 0; k0 < NV; k0 += KB) {
+            if (k0 < nvals) {
+                int4 t[KB][SLOT_ROUNDS];
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+                    for (int r = 0; r < SLOT_ROUNDS; ++r) {
+                        const int g = lane + 32 * r;
+                        t[kk][r] = (g < d.G && k0 + kk < nvals) ? __ldcg(reinterpret_cast<const int4 *>(base + (size_t)g * NV) + k0 + kk)
+                                                                : make_int4(0, 0, (int)(unsigned)stamp, (int)(unsigned)(stamp >> 32));
+                    }
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+                    for (int r = 0; r < SLOT_ROUNDS; ++r) take(t[kk][r], k0 + kk);
             }
+        }
+    } else {
+        for (int g = lane; g < d.G; g += 32) {
+            const int4 *src = reinterpret_cast<const int4 *>(base + (size_t)g * NV);
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+                if (k < nvals) take(__ldcg(src + k), k);
+        }
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) out[k] = (k < nvals) ? warp_sum(part[k]) : 0.0;
     return __all_sync(0xffffffffu, ok);
+}
+
+// What the deciding warp of the persistent driver keeps in its CTA's shared memory between two decisions of a chain, so
+// that a decision starts from shared memory instead of a chain of dependent global loads: the chain's state and control
+// block as it left them, and -- fetched right AFTER a decision is published, i.e. off the critical path -- the beta /
+// slice-width entries and column statistics the next decision will need.
+struct DeciderCache {
+    ChainState s;
+    Ctl ct;
+    double cst[CS_STRIDE];      // colstat row of column pref_j
+    double beta_j, shat_j, beta_n, shat_n, cscale_n;
+    int32_t pref_j;             // column the prefetched values belong to (-1: none)
+    int32_t valid;              // s / ct hold the chain's current state
+};
+__device__ __forceinline__ void decider_prefetch(const Dev &d, int c, DeciderCache *dc, int lane) {
+    const int jq = dc->ct.j;
+    if (jq < 0) { if (lane == 0) dc->pref_j = -1; __syncwarp(); return; }
+    const int jn = (jq + 1 == d.p) ? 0 : jq + 1;
+    const double *bp = d.beta + (int64_t)c * d.p, *sp = d.shat + (int64_t)c * d.p;
+    double v = 0.0;
+    if (lane < CS_STRIDE) v = __ldcg(d.colstat + (int64_t)jq * CS_STRIDE + lane);
+    else if (lane == 12) v = __ldcg(bp + jq);
+    else if (lane == 13) v = __ldcg(sp + jq);
+    else if (lane == 14) v = __ldcg(bp + jn);
+    else if (lane == 15) v = __ldcg(sp + jn);
+    else if (lane == 16) v = __ldcg(d.colstat + (int64_t)jn * CS_STRIDE);
+    if (lane < CS_STRIDE) dc->cst[lane] = v;
+    else if (lane == 12) dc->beta_j = v;
+    else if (lane == 13) dc->shat_j = v;
+    else if (lane == 14) dc->beta_n = v;
+    else if (lane == 15) dc->shat_n = v;
+    else if (lane == 16) dc->cscale_n = v;
+    if (lane == 0) dc->pref_j = jq;
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -885,8 +963,15 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
 //   JET_RETRY     (light passes) some test was not certain: the caller discards every change made here and asks for a
 //                 full jet pass of the same coordinate
 enum JetOutcome : int { JET_EXACT = 0, JET_ACCEPTED = 1, JET_RETRY = 2 };
+// per-phase timers of a decision (CGG_PROFILE output): compiled in only with -DCGG_DECIDER_TICKS, they cost ~3 % on the
+// headline workload even when profiling is off
+#ifndef CGG_DECIDER_TICKS
+#define CGG_TICK(slot) do { } while (0)
+#else
+#define CGG_TICK(slot) do { if (d.prof && lane == 0) { const long long t_ = clock64(); atomicAdd(d.prof + (slot), (unsigned long long)(t_ - tick)); tick = t_; } } while (0)
+#endif
 __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV], bool light,
-                                          double x0, double shat_j, double &x1_out, double &shat_out) {
+                                          double x0, double shat_j, const double *cst, double &x1_out, double &shat_out, long long &tick) {
     s.npass++; s.jet_passes++;
     if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
     ct.coarse_mask = 0;
@@ -899,7 +984,6 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
         if (d.family != CGG_GAUSSIAN && m[9] != 0.0) s.jet_skip = 1;
     }
     const double fmag = light ? fabs(s.fx0) + 1.0 : fabs(m[0]);
-    const double *cst = d.colstat + (int64_t)s.j * CS_STRIDE;
     // ---- uniforms: 2 (3 with a finite max) start draws + up to 32 shrink draws
     double uA = 0.5, uB = 0.5;
     const bool okA = draw_uniform(d, c, s.cursor + lane, uA);
@@ -910,6 +994,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     double U3[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) U3[i] = __shfl_sync(0xffffffffu, uA, i);
+    CGG_TICK(14);      // uniforms drawn
     start_coordinate(d, s, x0, U3, nAvail < 3 ? nAvail : 3);
     if (s.status != CGG_OK) return JET_EXACT;
     const double logu = log(U3[0]);
@@ -976,6 +1061,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
         }
         s.phase = PH_SHRINK;
     }
+    CGG_TICK(15);      // stepping out decided
     // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }: the proposals depend on (L, R, x0, u) only
     double l = s.L, r = s.R, xi = 0.0, li = l, ri = r;
     for (int t = 0; t < 32; ++t) {
@@ -984,6 +1070,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
         if (lane == t) { xi = x; li = l; ri = r; }
         if (x < s.x0) l = x; else r = x;
     }
+    CGG_TICK(16);      // proposal sequence generated
     bool in = false, out = false; double fm = 0.0;
     if (us_ok) verdict(xi, in, out, fm);
     const unsigned mout = __ballot_sync(0xffffffffu, out);
@@ -1006,6 +1093,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     s.shrinks++; s.ref_evals++;
     const double x1 = __shfl_sync(0xffffffffu, xi, k), f1 = __shfl_sync(0xffffffffu, fm, k);
     accept_value(d, c, s, ct, x1, f1, shat_j, k + 1, lane == 0, x1_out, shat_out);
+    CGG_TICK(17);      // proposals judged, value accepted
     return JET_ACCEPTED;
 }
 
@@ -1024,18 +1112,26 @@ __device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
     return v;
 }
 enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
-__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, unsigned long long stamp = 0) {
+__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, unsigned long long stamp = 0,
+                                         DeciderCache *dc = nullptr) {
     const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
-    // ---- one batched round of loads: control block, state, accumulators, beta/shat of j and j+1
-    if (j_hint < 0) j_hint = __ldcg(&d.ctl[c].j);
+    // ---- control block, state, beta/shat of j and j+1: from the deciding warp's shared-memory cache if it has them,
+    // else one batched round of global loads
+    const bool cached = dc && dc->valid;
+    if (cached) j_hint = dc->ct.j;
+    else if (j_hint < 0) j_hint = __ldcg(&d.ctl[c].j);
     const int jq = j_hint < 0 ? 0 : j_hint;              // column of the pass that just finished
     const int jn = (jq + 1 == d.p) ? 0 : jq + 1;         // the column an acceptance moves on to
     const double *bp = d.beta + (int64_t)c * d.p, *sp = d.shat + (int64_t)c * d.p;
-    const double beta_j = __ldcg(bp + jq), beta_n = __ldcg(bp + jn);
-    const double shat_j = __ldcg(sp + jq), shat_n = __ldcg(sp + jn);
-    Ctl ct = d.ctl[c];
-    ChainState s = d.cs[c];
+    const bool pref = dc && dc->pref_j == jq;
+    const double beta_j = pref ? dc->beta_j : __ldcg(bp + jq), beta_n = pref ? dc->beta_n : __ldcg(bp + jn);
+    const double shat_j = pref ? dc->shat_j : __ldcg(sp + jq), shat_n = pref ? dc->shat_n : __ldcg(sp + jn);
+    const double *cst_j = pref ? dc->cst : d.colstat + (int64_t)jq * CS_STRIDE;          // statistics of column jq
+    const double cscale_n = pref ? dc->cscale_n : __ldcg(d.colstat + (int64_t)jn * CS_STRIDE);
+    Ctl ct = cached ? dc->ct : d.ctl[c];
+    ChainState s = cached ? dc->s : d.cs[c];
+    long long tick = d.prof ? clock64() : 0;
     if (s.phase == PH_FINISHED || s.status != CGG_OK) return DEC_FINISHED;
     const bool jetpass = ((unsigned)ct.coarse_mask & JET_BIT) != 0u && s.phase == PH_JET;
     const int nc = jetpass ? 0 : ct.ncand;
@@ -1049,6 +1145,8 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
 #pragma unroll
         for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
     }
+    if (s.x0 != s.x0) tick = 0;   // (keeps the state loads above the first timestamp)
+    CGG_TICK(12);      // state loaded, sums read
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
     unsigned int aflags = 0;
@@ -1091,13 +1189,13 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (jetpass) {
         double x1 = 0.0, sh1 = 0.0;
         const bool light = ((unsigned)ct.coarse_mask & JET_FULL) == 0u;
-        const int oc = jet_decide(d, c, lane, s, ct, jm, light, beta_j, shat_j, x1, sh1);
+        const int oc = jet_decide(d, c, lane, s, ct, jm, light, beta_j, shat_j, cst_j, x1, sh1, tick);
         if (oc == JET_ACCEPTED) {
             if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }
         } else if (oc == JET_RETRY) {
             // a light pass left a test undecided: forget everything it changed, keep only the facts of the pass itself
             // (the pending eta update has been applied), and ask for a full jet pass of the same coordinate
-            s = d.cs[c]; ct = d.ctl[c];
+            s = cached ? dc->s : d.cs[c]; ct = cached ? dc->ct : d.ctl[c];
             s.npass++; s.jet_passes++; s.jet_retries++;
             if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
             retry_full = true;
@@ -1127,7 +1225,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (lane == 0) {
             const bool full = retry_full || !d.jet_light || d.family != CGG_BINOMIAL;
             ct.j = s.j; ct.ncand = 0; ct.coarse_mask = (int32_t)(JET_BIT | (full ? JET_FULL : 0u));
-            ct.cscale = __ldcg(d.colstat + (int64_t)s.j * CS_STRIDE);
+            ct.cscale = (s.j == jn) ? cscale_n : ((s.j == jq) ? cst_j[0] : __ldcg(d.colstat + (int64_t)s.j * CS_STRIDE));
             s.phase = PH_JET; s.chain_passes++;
         }
     } else if (status == CGG_OK && (phase == PH_START || phase == PH_SHRINK || phase == PH_STEPOUT)) {
@@ -1158,10 +1256,13 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (fin) ct.j = -1;
         d.cs[c] = s;
         d.ctl[c] = ct;
+        if (dc) { dc->s = s; dc->ct = ct; dc->valid = 1; }
     }
     fin = __shfl_sync(0xffffffffu, (int)fin, 0);
+    CGG_TICK(18);      // next pass set up, state stored
     fence_gpu();       // every lane: its accumulator clears must be visible before the version is released
     __syncwarp();
+    CGG_TICK(19);      // fence
     return fin ? DEC_FINISHED : DEC_CONTINUE;
 }
 

@@ -40,10 +40,13 @@ __device__ __forceinline__ bool wait_timed_out(const Dev &d, unsigned long long 
     return false;
 }
 
-__device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int stride, int lane) {
+// The deciding warp of chains first_chain, first_chain + stride, ...: as soon as every worker CTA's slot of a chain
+// carries the stamp of the pass in flight, decide and publish; then fetch what the chain's next decision will need.
+__device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int stride, int lane, DeciderCache *cache) {
     const Dev &d = *dp;
-    const unsigned long long t_start = globaltimer_ns();
-    unsigned long long t0 = t_start;
+    for (int c = first_chain; c < d.C; c += stride) { if (lane == 0) { cache[c].valid = 0; cache[c].pref_j = -1; } }
+    __syncwarp();
+    unsigned long long t0 = globaltimer_ns();
     unsigned idle = 0;
     for (;;) {
         bool all_fin = true, progressed = false;
@@ -56,13 +59,14 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             if (!slots_arrived(d, c, v + 1, lane)) continue;       // pass #v still has CTAs streaming
             const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
             const long long td0 = d.prof ? clock64() : 0;
-            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, v + 1);
+            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, v + 1, cache + c);
             if (oc == DEC_NOT_READY) continue;
             const bool fin = oc == DEC_FINISHED;
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
+            if (!fin) decider_prefetch(d, c, cache + c, lane);       // after publishing: off the chain's critical path
             if (d.prof && lane == 0) {
                 atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL);
-                if (v < 128) { d.prof[16 + 4096 + (c * 128 + v) * 4 + 0] = tg0; d.prof[16 + 4096 + (c * 128 + v) * 4 + 1] = globaltimer_ns(); }
+                if (v < 128) { d.prof[32 + 4096 + (c * 128 + v) * 4 + 0] = tg0; d.prof[32 + 4096 + (c * 128 + v) * 4 + 1] = globaltimer_ns(); }
             }
             progressed = true;
         }
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     // Next to fifteen workers that saturate the fp64 pipe a decision took ~25 us, and the decision sits on every
     // chain's critical cycle (pass -> decision -> next pass).
     if ((int)blockIdx.x == d.G) {
-        if (warp < d.C) decider_loop(&d, warp, NWARPS, lane);
+        if (warp < d.C) decider_loop(&d, warp, NWARPS, lane, reinterpret_cast<DeciderCache *>(smem_raw));
         return;
     }
     const int nworkers = NWARPS;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             // block with one coalesced request into shared memory; the other warps only watch shared memory.
             long long tA = prof ? clock64() : 0;
             if (prof && lane == 0 && round >= 1 && round <= 128) {
-                if (blockIdx.x == 20 && warp == 0) d.prof[16 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
+                if (blockIdx.x == 20 && warp == 0) d.prof[32 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
             }
             {
                 volatile unsigned long long *sv = &sh.ver[c];
@@ -158,11 +162,11 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             // ---- CTA-level then grid-level arrival
             cta_deliver_slots(d, sh, c, nc, warp, lane, nworkers, round + 1, acc);
             if (prof && lane == 0 && round == 60 && c == 0)
-                d.prof[16 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
+                d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
             if (prof && lane == 0 && round < 128) {     // arrival spread of the warps for pass #round of chain c
                 const unsigned long long tn = globaltimer_ns();
-                atomicMin(d.prof + 16 + 4096 + (c * 128 + round) * 4 + 2, tn);
-                atomicMax(d.prof + 16 + 4096 + (c * 128 + round) * 4 + 3, tn);
+                atomicMin(d.prof + 32 + 4096 + (c * 128 + round) * 4 + 2, tn);
+                atomicMax(d.prof + 32 + 4096 + (c * 128 + round) * 4 + 3, tn);
             }
             if (prof) t_arrive += clock64() - tC;
         }
@@ -176,12 +180,12 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         atomicAdd(d.prof + 9, (unsigned long long)n_notready); atomicAdd(d.prof + 10, (unsigned long long)n_look); atomicAdd(d.prof + 11, (unsigned long long)n_look_ok);
         // per-CTA view (who waits, who never does): [16 + 4 * cta + {wait, tiles, rows, smid}]
         unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 0, (unsigned long long)t_wait);
-        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 1, (unsigned long long)t_tiles);
-        atomicAdd(d.prof + 16 + 4 * blockIdx.x + 2, (unsigned long long)t_rows);
-        d.prof[16 + 4 * blockIdx.x + 3] = smid;
+        atomicAdd(d.prof + 32 + 4 * blockIdx.x + 0, (unsigned long long)t_wait);
+        atomicAdd(d.prof + 32 + 4 * blockIdx.x + 1, (unsigned long long)t_tiles);
+        atomicAdd(d.prof + 32 + 4 * blockIdx.x + 2, (unsigned long long)t_rows);
+        d.prof[32 + 4 * blockIdx.x + 3] = smid;
         // per-warp view: [16 + 4096 + 32*128*4 + (cta * NWARPS + warp) * 2 + {wait, tiles}]
-        d.prof[16 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 0] = (unsigned long long)t_wait;
+        d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 0] = (unsigned long long)t_wait;
     }
 }
 
@@ -1197,12 +1201,12 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemsetAsync(d.slots, 0, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G, h->stream));   // stamps restart with the versions
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
     if (want_prof) {
-        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 8 * (16 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128)));
-        CK(cudaMemsetAsync(h->prof_dev, 0, 8 * (16 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128), h->stream));
+        if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 8 * (32 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128)));
+        CK(cudaMemsetAsync(h->prof_dev, 0, 8 * (32 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128), h->stream));
         {   // arrival minima start at +inf
             std::vector<unsigned long long> init((size_t)32 * 128 * 4, 0ULL);
             for (size_t i = 2; i < init.size(); i += 4) init[i] = ~0ULL;
-            CK(cudaMemcpyAsync(h->prof_dev + 16 + 4096, init.data(), 8 * init.size(), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->prof_dev + 32 + 4096, init.data(), 8 * init.size(), cudaMemcpyHostToDevice, h->stream));
             CK(cudaStreamSynchronize(h->stream));
         }
     }
@@ -1254,19 +1258,22 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         fprintf(stderr, "[cgg profile] slice-width estimate shat: mean %.4g min %.4g max %.4g (%d set)\n", cnt ? m / cnt : 0.0, mn, mx, cnt);
     }
     if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT) {
-        unsigned long long pr[16];
-        CK(cudaMemcpy(pr, h->prof_dev, 128, cudaMemcpyDeviceToHost));
+        unsigned long long pr[24];
+        CK(cudaMemcpy(pr, h->prof_dev, sizeof pr, cudaMemcpyDeviceToHost));
         const double nw = pr[6] ? (double)pr[6] : 1.0;
         fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-passes/worker %.1f workers %llu\n",
                 ms, pr[0] / nw, pr[1] / nw, pr[3] / nw, pr[2] / nw, pr[5] / nw, pr[4] / nw, pr[6]);
         fprintf(stderr, "[cgg profile] decisions %llu, mean cycles per decision %.0f | polls that found the decision not yet published %llu, look-aheads %llu (published: %llu)\n",
                 pr[8], pr[8] ? (double)pr[7] / (double)pr[8] : 0.0, pr[9], pr[10], pr[11]);
+        fprintf(stderr, "[cgg profile] decision phases, mean cycles: load+sums %.0f | uniforms %.0f | step-out %.0f | proposals %.0f | judge+accept %.0f | next pass+store %.0f | fence %.0f\n",
+                pr[12] / (double)(pr[8] ? pr[8] : 1), pr[14] / (double)(pr[8] ? pr[8] : 1), pr[15] / (double)(pr[8] ? pr[8] : 1), pr[16] / (double)(pr[8] ? pr[8] : 1),
+                pr[17] / (double)(pr[8] ? pr[8] : 1), pr[18] / (double)(pr[8] ? pr[8] : 1), pr[19] / (double)(pr[8] ? pr[8] : 1));
         if (getenv("CGG_PROFILE_TRACE")) {
             std::vector<unsigned long long> tr((size_t)d.C * 128 * 4);
-            CK(cudaMemcpy(tr.data(), h->prof_dev + 16 + 4096, 8 * tr.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(tr.data(), h->prof_dev + 32 + 4096, 8 * tr.size(), cudaMemcpyDeviceToHost));
             const unsigned long long t0 = tr[(0 * 128 + 0) * 4 + 0];
             std::vector<unsigned long long> need((size_t)32 * 128);
-            CK(cudaMemcpy(need.data(), h->prof_dev + 16 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32, 8 * need.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(need.data(), h->prof_dev + 32 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32, 8 * need.size(), cudaMemcpyDeviceToHost));
             for (int v = 40; v < 44; ++v)
                 for (int c = 0; c < d.C; ++c) {
                     const unsigned long long *q = &tr[((size_t)c * 128 + v) * 4];
@@ -1276,7 +1283,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         }
         if (getenv("CGG_PROFILE_WARPS")) {
             std::vector<unsigned long long> pw(2 * (size_t)d.G * NWARPS);
-            CK(cudaMemcpy(pw.data(), h->prof_dev + 16 + 4096 + 32 * 128 * 4, 8 * pw.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(pw.data(), h->prof_dev + 32 + 4096 + 32 * 128 * 4, 8 * pw.size(), cudaMemcpyDeviceToHost));
             for (int b = 0; b < d.G; b += 1) {
                 fprintf(stderr, "[cgg warps] cta %3d wait(k cycles):", b);
                 for (int w = 0; w < NWARPS; ++w) fprintf(stderr, " %5.0f", pw[2 * ((size_t)b * NWARPS + w)] * 1e-3);
@@ -1289,7 +1296,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         }
         if (getenv("CGG_PROFILE_CTAS")) {
             std::vector<unsigned long long> pc(4 * (size_t)d.G);
-            CK(cudaMemcpy(pc.data(), h->prof_dev + 16, 8 * pc.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(pc.data(), h->prof_dev + 32, 8 * pc.size(), cudaMemcpyDeviceToHost));
             for (int b = 0; b < d.G; ++b)
                 fprintf(stderr, "[cgg cta] %3d sm %3llu wait %.3g tiles %.3g rows %.3g\n", b, pc[4 * b + 3], (double)pc[4 * b] / NWARPS, (double)pc[4 * b + 1] / NWARPS, (double)pc[4 * b + 2] / NWARPS);
         }
