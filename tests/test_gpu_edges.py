@@ -1,0 +1,97 @@
+"""Edge cases of the product path (jet passes + exact passes through the persistent driver) against the oracle:
+ragged and tiny row counts, a single column, more chains than deciding warps, degenerate and badly scaled columns,
+extreme slice widths.  Every case also has to equal the all-exact engine bit for bit."""
+import numpy as np
+import pytest
+import oracle
+from helpers import synth, PRIOR_CASES
+from mcmcglm_b200 import Engine
+
+pytestmark = pytest.mark.gpu
+ATOL = 1e-9
+
+
+def _chains(family, prior, X, y, beta0, iters, U, **kw):
+    n, p = X.shape
+    C = beta0.shape[0]
+    with Engine(n, p, family=family, sd=1.0, n_chains=C, **PRIOR_CASES[prior], **kw) as e:
+        e.set_data(X, y)
+        for c in range(C):
+            e.init_chain(c, beta0[c])
+        S, st = e.run(iters, replay_u=U)
+    return S, st
+
+
+def _check(family, prior, X, y, beta0, iters, w=0.5, max_steps=-1, seed=3, oracle_chains=None):
+    C = beta0.shape[0]
+    U = np.random.default_rng(seed).random((C, 4000 + 60 * iters * X.shape[1]))
+    S, st = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps)
+    Sx, stx = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps, jet=False)
+    assert np.array_equal(S, Sx)
+    for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
+        assert st[k] == stx[k], k
+    m = oracle.make_model(family, sd=1.0, **PRIOR_CASES[prior])
+    for c in (range(C) if oracle_chains is None else oracle_chains):
+        ref = oracle.run_chain(m, X, y, beta0[c], w=w, n_iter=iters, max_steps=max_steps, replay_u=U[c])
+        assert ref["rc"] == 0
+        assert np.max(np.abs(S[c] - ref["samples"])) <= ATOL, c
+        assert st["uniforms_used"][c] == ref["uniforms_used"]
+    return st
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 127, 1001])
+@pytest.mark.parametrize("family", ["gaussian", "binomial", "poisson"])
+def test_ragged_and_tiny_row_counts(family, n):
+    p = 2 if n > 2 else 1
+    X, y, bt = synth(family, max(n, 4), p, seed=n)
+    X, y = np.asfortranarray(X[:n]), y[:n]
+    _check(family, "normal", X, y, np.zeros((2, p)), 12, w=1.0)
+
+
+@pytest.mark.parametrize("family,prior", [("gaussian", "laplace"), ("binomial", "student_t"), ("poisson", "normal")])
+def test_single_column(family, prior):
+    X, y, _ = synth(family, 777, 1, seed=5, intercept=False)
+    _check(family, prior, X, y, np.array([[0.2], [-0.4], [0.0]]), 30, w=0.3)
+
+
+@pytest.mark.parametrize("C", [13, 32])
+def test_more_chains_than_deciding_warps(C):
+    # 12 deciding warps per GPU: with more chains a warp decides several of them
+    X, y, bt = synth("binomial", 2500, 3, seed=8)
+    beta0 = 0.3 * np.random.default_rng(1).standard_normal((C, 3))
+    st = _check("binomial", "laplace", X, y, beta0, 8, w=0.4, oracle_chains=(0, 11, 12, C - 1))
+    assert st["updates"] == C * 8 * 3
+
+
+def test_degenerate_and_badly_scaled_columns():
+    # a column of zeros (its coefficient is sampled from the prior alone), a huge and a tiny column
+    X, y, bt = synth("binomial", 3000, 5, seed=4)
+    X[:, 1] = 0.0
+    X[:, 2] *= 1e6
+    X[:, 3] *= 1e-6
+    X = np.asfortranarray(X)
+    beta0 = np.array([[0.1, 0.5, 1e-7, 2.0e4, -0.2], [0.0, -1.0, -2e-7, -1.0e4, 0.3]])
+    _check("binomial", "normal", X, y, beta0, 15, w=0.5)
+    Xg, yg, _ = synth("gaussian", 3000, 5, seed=4)
+    Xg[:, 1] = 0.0
+    Xg[:, 2] *= 1e6
+    _check("gaussian", "student_t", np.asfortranarray(Xg), yg, np.zeros((2, 5)), 15, w=0.5)
+
+
+@pytest.mark.parametrize("w,max_steps", [(1e-4, -1), (50.0, -1), (1e-3, 4), (20.0, 2)])
+def test_extreme_slice_widths(w, max_steps):
+    X, y, bt = synth("poisson", 1500, 3, seed=6)
+    _check("poisson", "laplace", X, y, np.tile(bt, (2, 1)), 10, w=w, max_steps=max_steps)
+    Xb, yb, btb = synth("binomial", 1500, 3, seed=6)
+    _check("binomial", "normal", Xb, yb, np.tile(btb, (2, 1)), 10, w=w, max_steps=max_steps)
+
+
+def test_infinite_entry_in_a_column_is_an_error_not_a_hang():
+    X, y, _ = synth("gaussian", 500, 2, seed=2)
+    X[7, 1] = np.inf
+    from mcmcglm_b200 import CggError
+    with Engine(500, 2, family="gaussian", **PRIOR_CASES["normal"]) as e:
+        e.set_data(np.asfortranarray(X), y)
+        e.init_chain(0, np.zeros(2))
+        with pytest.raises(CggError):
+            e.run(3)
