@@ -28,7 +28,7 @@ constexpr int NWARPS = THREADS / 32;
 constexpr int CMAX = 32;       // chains per device (shared-memory slots of the CTA-level reduction)
 constexpr int NU = 12;         // uniforms fetched per decision: 3 start draws + KMAX proposals (+1 spare)
 constexpr int RING_D = CGG_RING_D;  // tiles in flight per warp (cp.async ring depth)
-constexpr int RING_OPS = 4;    // eta, y, X_j, X_commit
+constexpr int RING_OPS = 5;    // eta, y, X_j, X_commit (single pass) | eta_A, eta_B, y, X_j, X_commit (pair pass)
 constexpr int TILE_ROWS = 64;  // 32 lanes x one 128-bit transfer per operand
 constexpr int RING_BYTES_PER_WARP = RING_D * RING_OPS * 32 * 16;
 
@@ -111,7 +111,7 @@ struct Dev {
     int64_t max_steps;
     double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds)
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, pad_;   // pair: chains 2k, 2k+1 share a pass when they can
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -440,6 +440,99 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
         }
     }
     if (FAMILY != CGG_GAUSSIAN) m[9] = (risk >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
+}
+
+// One warp, TWO chains that are at the same coordinate (same column j, same pending column), one jet pass: y, X_j and
+// X_commit tiles are staged once and serve both chains (the chains of a GPU run in lock-step in the stationary regime),
+// the per-tile loop overhead and the pipeline fill are paid once, and the two chains' rows are independent work for the
+// scheduler.  Ring stage layout: [eta_A, eta_B, y, X_j, X_commit] x 512 B.
+template <int FAMILY, bool FULL>
+__device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const double *cwA, const double *cwB, long long wid, long long W,
+                                               int lane, uint32_t ring, const double2 *tab, double (&mA)[NV], double (&mB)[NV]) {
+    const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
+    const int j = (int)(w0 & 0xffffffffLL), cj = (int)(w1 & 0xffffffffLL);
+    const double cdA = cwA[2], cdB = cwB[2], cscale = cwA[CTL_WORDS - 1];
+    const int64_t n = d.n;
+    double *etaA = d.eta + (int64_t)c0 * d.lde, *etaB = etaA + d.lde;
+    const double *xj = d.X + (int64_t)j * d.ldx, *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
+    const long long vw = (wid + (long long)c0 * (W / d.C)) % W;
+    const uint32_t sbase = ring + (uint32_t)lane * 16u;
+    constexpr uint32_t STAGE = RING_OPS * 512u;
+    static_assert(RING_OPS >= 5, "a pair pass stages five operands");
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
+    unsigned riskA = 0, riskB = 0;
+    const int64_t step = W * TILE_ROWS;
+    const int64_t i0 = vw * TILE_ROWS + 2 * lane;
+    const double *pa = etaA + i0, *pb = etaB + i0, *py = d.y + i0, *px = xj + i0, *pc = xc + i0;
+    const double *const pa_last = etaA + (n - 1);
+    const double *const pa_end = etaA + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
+    auto issue_next = [&](unsigned st) {
+        if (pa < pa_last) {
+            const uint32_t sa = sbase + st * STAGE;
+            cp_async16(sa, pa); cp_async16(sa + 512u, pb);
+            cp_async16(sa + 1024u, py); cp_async16(sa + 1536u, px);
+            if (cj >= 0) cp_async16(sa + 2048u, pc);
+        }
+        cp_async_commit();
+        pa += step; pb += step; py += step; px += step; pc += step;
+    };
+#pragma unroll
+    for (int s = 0; s < RING_D - 1; ++s) issue_next((unsigned)s);
+    unsigned stage = 0;
+    for (; pa < pa_end; ) {
+        issue_next((stage + RING_D - 1) & (RING_D - 1));
+        cp_async_wait<RING_D - 1>();
+        const int64_t off = (pa - etaA) - RING_D * step;        // row index of this lane's pair in the tile being scored
+        if (off + 1 < n) {
+            const uint32_t s = sbase + stage * STAGE;
+            double2 ea = lds2(s), eb = lds2(s + 512u);
+            if (cj >= 0) {
+                const double2 cv = lds2(s + 2048u);
+                ea.x = eta_shift(ea.x, cv.x, cdA); ea.y = eta_shift(ea.y, cv.y, cdA);
+                eb.x = eta_shift(eb.x, cv.x, cdB); eb.y = eta_shift(eb.y, cv.y, cdB);
+                *reinterpret_cast<double2 *>(etaA + off) = ea;
+                *reinterpret_cast<double2 *>(etaB + off) = eb;
+            }
+            const double2 yy = lds2(s + 1024u);
+            double2 xs = lds2(s + 1536u);
+            xs.x *= cscale; xs.y *= cscale;
+            JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
+            JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
+        }
+        stage = (stage + 1) & (RING_D - 1);
+    }
+    cp_async_wait<0>();
+    if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
+        const int64_t t = n - 1;
+        const long long Tl = t / TILE_ROWS;
+        if (Tl % W == vw && lane == (int)((t % TILE_ROWS) >> 1)) {
+            double ea = __ldcg(etaA + t), eb = __ldcg(etaB + t);
+            if (cj >= 0) {
+                const double cv = __ldg(xc + t);
+                ea = eta_shift(ea, cv, cdA); eb = eta_shift(eb, cv, cdB);
+                etaA[t] = ea; etaB[t] = eb;
+            }
+            const double yy = __ldg(d.y + t), xx = __ldg(xj + t) * cscale;
+            JetRow<FAMILY>::template add1<FULL>(yy, ea, xx, d.inv_sd, tab, mA, riskA);
+            JetRow<FAMILY>::template add1<FULL>(yy, eb, xx, d.inv_sd, tab, mB, riskB);
+        }
+    }
+    if (FAMILY != CGG_GAUSSIAN) {
+        mA[9] = (riskA >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
+        mB[9] = (riskB >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { mA[k] = warp_sum(mA[k]); mB[k] = warp_sum(mB[k]); }
+}
+
+// Two control blocks describe passes that can share one walk over the rows: both jet passes of the same kind on the
+// same column with the same pending column.
+__device__ __forceinline__ bool pair_batchable(const double *cwA, const double *cwB) {
+    const long long a0 = __double_as_longlong(cwA[0]), a1 = __double_as_longlong(cwA[1]);
+    const long long b0 = __double_as_longlong(cwB[0]), b1 = __double_as_longlong(cwB[1]);
+    const unsigned ma = (unsigned)(a1 >> 32);
+    return a0 == b0 && a1 == b1 && (ma & JET_BIT) && (int)(a0 & 0xffffffffLL) >= 0;
 }
 
 // A worker's whole contribution to one pass of chain c: read the control block, stream the rows and
@@ -1254,13 +1347,17 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (s.status != CGG_OK) { ct.ncand = 0; ct.commit_j = -1; }
         fin = (s.phase == PH_FINISHED) || (s.status != CGG_OK);
         if (fin) ct.j = -1;
-        d.cs[c] = s;
+        // the deciding warp of the persistent driver keeps the state in shared memory; global memory gets it when the
+        // chain stops (the host reads it after the kernel) -- every decision otherwise
+        if (!dc || fin) d.cs[c] = s;
         d.ctl[c] = ct;
         if (dc) { dc->s = s; dc->ct = ct; dc->valid = 1; }
     }
     fin = __shfl_sync(0xffffffffu, (int)fin, 0);
     CGG_TICK(18);      // next pass set up, state stored
-    fence_gpu();       // every lane: its accumulator clears must be visible before the version is released
+    // every lane that cleared accumulators (or their flags) must have that visible before the version is released; with
+    // the slot source and no pre-filter only lane 0 wrote, and its release store orders its own writes
+    if (!(src == SRC_SLOTS && cmask == 0u)) fence_gpu();
     __syncwarp();
     CGG_TICK(19);      // fence
     return fin ? DEC_FINISHED : DEC_CONTINUE;

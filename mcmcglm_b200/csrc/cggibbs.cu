@@ -104,59 +104,84 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     bool prefetched = false;
     long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0, n_notready = 0, n_look = 0, n_look_ok = 0;
     const bool prof = d.prof != nullptr;
+    // ---- wait until decision #round of chain c is published (usually it already is).  One warp at a time polls the
+    // flag for the whole CTA and, when it has advanced, fetches the chain's control block with one coalesced request
+    // into shared memory; the other warps only watch shared memory.  Returns false if the wait timed out.
+    auto wait_decision = [&](int c, unsigned long long round) -> bool {
+        volatile unsigned long long *sv = &sh.ver[c];
+        if (*sv < round) {
+            ++n_slow;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned spins = 0;
+            for (;;) {
+                int got = 0;
+                if (lane == 0) got = (atomicCAS_block(&sh.lock[c], 0, 1) == 0);
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got) {
+                    unsigned long long v = 0;
+                    if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (v < round) ++n_notready;
+                    if (v >= round && v > *sv) {
+                        if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); *sv = v; }
+                    }
+                    if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
+                }
+                if (*sv >= round) break;
+                __nanosleep(spins < 8 ? 64 : 256);
+                if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) return false;
+            }
+        }
+        __syncwarp();
+        return true;
+    };
+    double acc2[NV];
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
         for (int c = 0; c < d.C; ++c) {
-            // ---- wait until decision #round of chain c is published (usually it already is).  One warp at a
-            // time polls the flag for the whole CTA and, when it has advanced, fetches the chain's control
-            // block with one coalesced request into shared memory; the other warps only watch shared memory.
             long long tA = prof ? clock64() : 0;
             if (prof && lane == 0 && round >= 1 && round <= 128) {
                 if (blockIdx.x == 20 && warp == 0) d.prof[32 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
             }
-            {
-                volatile unsigned long long *sv = &sh.ver[c];
-                if (*sv < round) {
-                    ++n_slow;
-                    const unsigned long long t0 = globaltimer_ns();
-                    unsigned spins = 0;
-                    for (;;) {
-                        int got = 0;
-                        if (lane == 0) got = (atomicCAS_block(&sh.lock[c], 0, 1) == 0);
-                        got = __shfl_sync(0xffffffffu, got, 0);
-                        if (got) {
-                            unsigned long long v = 0;
-                            if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
-                            v = __shfl_sync(0xffffffffu, v, 0);
-                            if (v < round) ++n_notready;
-                            if (v >= round && v > *sv) {
-                                if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
-                                __syncwarp();
-                                if (lane == 0) { __threadfence_block(); *sv = v; }
-                            }
-                            if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
-                        }
-                        if (*sv >= round) break;
-                        __nanosleep(spins < 8 ? 64 : 256);
-                        if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) return;
-                    }
-                }
-                __syncwarp();
+            if (!wait_decision(c, round)) return;
+            // ---- chains 2k and 2k + 1 at the same coordinate share one walk over the rows (pair pass)
+            bool pair = false;
+            if (d.pair && !(c & 1) && c + 1 < d.C) {
+                if (!wait_decision(c + 1, round)) return;
+                // the shared control blocks must be exactly the ones of this round (a finished chain's never are)
+                pair = (*(volatile unsigned long long *)&sh.ver[c] == round) && (*(volatile unsigned long long *)&sh.ver[c + 1] == round) &&
+                       pair_batchable(sh.ctl + c * CTL_WORDS, sh.ctl + (c + 1) * CTL_WORDS);
             }
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
+            if (pair) {
+                const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
+                const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(cwA[1]) >> 32)) & JET_FULL);
+                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, acc, acc2);
+                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, acc, acc2);
+                any = true;
+                ++n_pref;
+                long long tC = prof ? clock64() : 0;
+                t_rows += tC - tB; t_tiles += tC - tB;
+                cta_deliver_slots(d, sh, c, NV, warp, lane, nworkers, round + 1, acc);
+                cta_deliver_slots(d, sh, c + 1, NV, warp, lane, nworkers, round + 1, acc2);
+                if (prof) t_arrive += clock64() - tC;
+                ++c;
+                continue;
+            }
             // ---- stream this warp's rows for chain c; if the next chain's decision is already published, its
             // first tiles are requested as soon as this chain's tiles are consumed (cross-chain prefetch)
             int j = -1;
             const int nxt = (c + 1 == d.C) ? 0 : c + 1;
             const unsigned long long nround = (c + 1 == d.C) ? round + 1 : round;
-            LookAhead la{&sh, d.sync, d.ctl, d.C > 1 ? nxt : -1, nround, 0, 0};
+            LookAhead la{&sh, d.sync, d.ctl, (d.C > 1 && !d.pair) ? nxt : -1, nround, 0, 0};
             const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
                                                acc, j, prefetched, nxt, &la, prof ? &t_tiles : nullptr);
             n_look += la.n_look; n_look_ok += la.n_ok;
             if (nc < 0) continue;
             any = true;
-            n_pref += prefetched ? 1 : 0;
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
@@ -670,6 +695,11 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     h->jet_wanted = !(cfg->flags & CGG_FLAG_NO_JET);
     d.jet = h->jet_wanted && !d.sharded;     // row-sharded: decided at cgg_set_data (needs the exchange for the column statistics)
     d.jet_bscale = (cfg->jet_bound_scale > 0.0) ? cfg->jet_bound_scale : 1.0;
+    {   // pair passes (chains 2k, 2k + 1 share a walk over the rows when they are at the same coordinate): from 4 chains on
+        // the pairs' decisions still hide behind the other pairs' passes; CGG_PAIR=0/1 overrides (experiments, tests)
+        const char *e = getenv("CGG_PAIR");
+        d.pair = e ? atoi(e) : (C >= 4);
+    }
     d.jet_light = d.jet && !(cfg->flags & CGG_FLAG_NO_JET_LIGHT);
     d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
     d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
@@ -1261,7 +1291,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         unsigned long long pr[24];
         CK(cudaMemcpy(pr, h->prof_dev, sizeof pr, cudaMemcpyDeviceToHost));
         const double nw = pr[6] ? (double)pr[6] : 1.0;
-        fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-passes/worker %.1f workers %llu\n",
+        fprintf(stderr, "[cgg profile] %.3f ms; per-worker mean cycles: wait %.3g rows %.3g (tile loop %.3g) arrive %.3g | slow-waits/worker %.1f prefetched-or-pair-passes/worker %.1f workers %llu\n",
                 ms, pr[0] / nw, pr[1] / nw, pr[3] / nw, pr[2] / nw, pr[5] / nw, pr[4] / nw, pr[6]);
         fprintf(stderr, "[cgg profile] decisions %llu, mean cycles per decision %.0f | polls that found the decision not yet published %llu, look-aheads %llu (published: %llu)\n",
                 pr[8], pr[8] ? (double)pr[7] / (double)pr[8] : 0.0, pr[9], pr[10], pr[11]);
