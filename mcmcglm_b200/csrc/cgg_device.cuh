@@ -446,46 +446,69 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
 // X_commit tiles are staged once and serve both chains (the chains of a GPU run in lock-step in the stationary regime),
 // the per-tile loop overhead and the pipeline fill are paid once, and the two chains' rows are independent work for the
 // scheduler.  Ring stage layout: [eta_A, eta_B, y, X_j, X_commit] x 512 B.
-template <int FAMILY, bool FULL>
-__device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const double *cwA, const double *cwB, long long wid, long long W,
-                                               int lane, uint32_t ring, const double2 *tab, double (&mA)[NV], double (&mB)[NV]) {
-    const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
-    const int j = (int)(w0 & 0xffffffffLL), cj = (int)(w1 & 0xffffffffLL);
-    const double cdA = cwA[2], cdB = cwB[2], cscale = cwA[CTL_WORDS - 1];
-    const int64_t n = d.n;
-    double *etaA = d.eta + (int64_t)c0 * d.lde, *etaB = etaA + d.lde;
-    const double *xj = d.X + (int64_t)j * d.ldx, *xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
-    const long long vw = (wid + (long long)c0 * (W / d.C)) % W;
-    const uint32_t sbase = ring + (uint32_t)lane * 16u;
-    constexpr uint32_t STAGE = RING_OPS * 512u;
-    static_assert(RING_OPS >= 5, "a pair pass stages five operands");
-#pragma unroll
-    for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
-    unsigned riskA = 0, riskB = 0;
-    const int64_t step = W * TILE_ROWS;
-    const int64_t i0 = vw * TILE_ROWS + 2 * lane;
-    const double *pa = etaA + i0, *pb = etaB + i0, *py = d.y + i0, *px = xj + i0, *pc = xc + i0;
-    const double *const pa_last = etaA + (n - 1);
-    const double *const pa_end = etaA + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
-    auto issue_next = [&](unsigned st) {
+struct PairStream {      // running pointers of a pair pass: the tile to be issued next
+    const double *pa, *pb, *py, *px, *pc;
+    const double *pa_last, *pa_end;
+    double *etaA, *etaB;
+    const double *xj, *xc;
+    long long vw;
+    int64_t step;
+    int cj;
+    uint32_t sbase;
+    __device__ __forceinline__ PairStream(const Dev &d, int c0, const double *cwA, long long wid, long long W, int lane, uint32_t ring) {
+        const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
+        const int j = (int)(w0 & 0xffffffffLL);
+        cj = (int)(w1 & 0xffffffffLL);
+        etaA = d.eta + (int64_t)c0 * d.lde; etaB = etaA + d.lde;
+        xj = d.X + (int64_t)j * d.ldx; xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
+        vw = (wid + (long long)c0 * (W / d.C)) % W;
+        sbase = ring + (uint32_t)lane * 16u;
+        step = W * TILE_ROWS;
+        const int64_t i0 = vw * TILE_ROWS + 2 * lane;
+        pa = etaA + i0; pb = etaB + i0; py = d.y + i0; px = xj + i0; pc = xc + i0;
+        pa_last = etaA + (d.n - 1);
+        pa_end = etaA + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
+    }
+    __device__ __forceinline__ void issue_next(unsigned st) {
         if (pa < pa_last) {
-            const uint32_t sa = sbase + st * STAGE;
+            const uint32_t sa = sbase + st * (RING_OPS * 512u);
             cp_async16(sa, pa); cp_async16(sa + 512u, pb);
             cp_async16(sa + 1024u, py); cp_async16(sa + 1536u, px);
             if (cj >= 0) cp_async16(sa + 2048u, pc);
         }
         cp_async_commit();
         pa += step; pb += step; py += step; px += step; pc += step;
-    };
+    }
+    // first RING_D - 1 tiles: may be issued early (cross-pair prefetch); `skip`: they already were
+    __device__ __forceinline__ void prologue(bool skip) {
+        if (skip) { const int64_t adv = (RING_D - 1) * step; pa += adv; pb += adv; py += adv; px += adv; pc += adv; return; }
 #pragma unroll
-    for (int s = 0; s < RING_D - 1; ++s) issue_next((unsigned)s);
+        for (int s = 0; s < RING_D - 1; ++s) issue_next((unsigned)s);
+    }
+};
+
+template <int FAMILY, bool FULL, class AFTER>
+__device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const double *cwA, const double *cwB, long long wid, long long W,
+                                               int lane, uint32_t ring, const double2 *tab, bool prefetched, AFTER &&after_tiles,
+                                               double (&mA)[NV], double (&mB)[NV]) {
+    const double cdA = cwA[2], cdB = cwB[2], cscale = cwA[CTL_WORDS - 1];
+    const int64_t n = d.n;
+    PairStream ps(d, c0, cwA, wid, W, lane, ring);
+    const int cj = ps.cj;
+    double *etaA = ps.etaA, *etaB = ps.etaB;
+    constexpr uint32_t STAGE = RING_OPS * 512u;
+    static_assert(RING_OPS >= 5, "a pair pass stages five operands");
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
+    unsigned riskA = 0, riskB = 0;
+    ps.prologue(prefetched);
     unsigned stage = 0;
-    for (; pa < pa_end; ) {
-        issue_next((stage + RING_D - 1) & (RING_D - 1));
+    for (; ps.pa < ps.pa_end; ) {
+        ps.issue_next((stage + RING_D - 1) & (RING_D - 1));
         cp_async_wait<RING_D - 1>();
-        const int64_t off = (pa - etaA) - RING_D * step;        // row index of this lane's pair in the tile being scored
+        const int64_t off = (ps.pa - etaA) - RING_D * ps.step;        // row index of this lane's pair in the tile being scored
         if (off + 1 < n) {
-            const uint32_t s = sbase + stage * STAGE;
+            const uint32_t s = ps.sbase + stage * STAGE;
             double2 ea = lds2(s), eb = lds2(s + 512u);
             if (cj >= 0) {
                 const double2 cv = lds2(s + 2048u);
@@ -506,18 +529,19 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
         const int64_t t = n - 1;
         const long long Tl = t / TILE_ROWS;
-        if (Tl % W == vw && lane == (int)((t % TILE_ROWS) >> 1)) {
+        if (Tl % W == ps.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
             double ea = __ldcg(etaA + t), eb = __ldcg(etaB + t);
             if (cj >= 0) {
-                const double cv = __ldg(xc + t);
+                const double cv = __ldg(ps.xc + t);
                 ea = eta_shift(ea, cv, cdA); eb = eta_shift(eb, cv, cdB);
                 etaA[t] = ea; etaB[t] = eb;
             }
-            const double yy = __ldg(d.y + t), xx = __ldg(xj + t) * cscale;
+            const double yy = __ldg(d.y + t), xx = __ldg(ps.xj + t) * cscale;
             JetRow<FAMILY>::template add1<FULL>(yy, ea, xx, d.inv_sd, tab, mA, riskA);
             JetRow<FAMILY>::template add1<FULL>(yy, eb, xx, d.inv_sd, tab, mB, riskB);
         }
     }
+    after_tiles();     // the ring is free: the caller may already request the next pair's first tiles
     if (FAMILY != CGG_GAUSSIAN) {
         mA[9] = (riskA >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
         mB[9] = (riskB >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
@@ -671,6 +695,33 @@ struct LookAhead {
         return (*sv == nround) ? sh->ctl + nxt * CTL_WORDS : nullptr;
     }
 };
+
+// The same for a PAIR of chains (c2, c2 + 1) with one election and two concurrent round trips (both version flags, then
+// both control blocks).  True when both shared control blocks are exactly those of pass `nround`.
+__device__ __forceinline__ bool pair_lookahead(const Dev &d, CtaShared &sh, int c2, unsigned long long nround, int lane) {
+    volatile unsigned long long *sv0 = &sh.ver[c2], *sv1 = &sh.ver[c2 + 1];
+    if (*sv0 < nround || *sv1 < nround) {
+        int got = 0;
+        if (lane == 0) got = (atomicCAS_block(&sh.lock[c2], 0, 1) == 0);
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got) {
+            unsigned long long v = 0;
+            if (lane < 2) v = ld_acquire_u64(&d.sync[c2 + lane].version);
+            const unsigned long long v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1);
+            const bool n0 = v0 >= nround && v0 > *sv0, n1 = v1 >= nround && v1 > *sv1;
+            if (n0 || n1) {
+                const int which = lane / CTL_WORDS, word = lane % CTL_WORDS;       // lanes 0..11: chain c2, 12..23: chain c2 + 1
+                if (lane < 2 * CTL_WORDS && (which ? n1 : n0))
+                    sh.ctl[(c2 + which) * CTL_WORDS + word] = __ldcg(reinterpret_cast<const double *>(d.ctl + c2 + which) + word);
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); if (n0) *sv0 = v0; if (n1) *sv1 = v1; }
+            }
+            if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c2], 0); }
+            __syncwarp();
+        }
+    }
+    return *sv0 == nround && *sv1 == nround;
+}
 
 // Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
 // has folded the CTA's NWARPS partials -- summed in warp order, so the value is reproducible -- into the

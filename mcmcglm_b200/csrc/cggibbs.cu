@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         return true;
     };
     double acc2[NV];
+    bool pair_prefetched = false;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
         for (int c = 0; c < d.C; ++c) {
@@ -156,13 +157,32 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             }
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
+            if (pair_prefetched && !pair) { cp_async_wait<0>(); pair_prefetched = false; }    // (cannot happen: the blocks were checked)
             if (pair) {
                 const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
                 const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(cwA[1]) >> 32)) & JET_FULL);
-                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, acc, acc2);
-                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, acc, acc2);
+                // when the tiles are consumed: if the NEXT pair's decisions are published and it is a pair pass again,
+                // request its first tiles now, before this pair's sums are reduced and delivered
+                const bool was_pref = pair_prefetched;
+                pair_prefetched = false;
+                auto after = [&]() {
+                    if (d.C < 6) return;          // with one or two pairs the next decision is never there yet: the look would only cost
+                    int c2; unsigned long long nround;
+                    if (c + 2 >= d.C) { c2 = 0; nround = round + 1; }           // this was the last item of the round
+                    else if (c + 3 < d.C) { c2 = c + 2; nround = round; }      // another pair follows
+                    else return;                                               // a single chain follows: it needs the ring
+                    if (c2 == c) return;
+                    if (!pair_lookahead(d, sh, c2, nround, lane)) return;
+                    const double *nA = sh.ctl + c2 * CTL_WORDS;
+                    if (!pair_batchable(nA, nA + CTL_WORDS)) return;
+                    PairStream ns(d, c2, nA, wid, W, lane, ring);
+                    ns.prologue(false);
+                    pair_prefetched = true;
+                };
+                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, after, acc, acc2);
+                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, after, acc, acc2);
                 any = true;
-                ++n_pref;
+                n_pref += pair_prefetched ? 1 : 0;
                 long long tC = prof ? clock64() : 0;
                 t_rows += tC - tB; t_tiles += tC - tB;
                 cta_deliver_slots(d, sh, c, NV, warp, lane, nworkers, round + 1, acc);
