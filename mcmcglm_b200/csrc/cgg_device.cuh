@@ -20,6 +20,9 @@ constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate 
 #ifndef CGG_RING_D
 #define CGG_RING_D 4
 #endif
+#ifndef CGG_PAIR_TPI
+#define CGG_PAIR_TPI 1       // tiles per iteration of the pair-pass loop (1 or 2)
+#endif
 #ifndef CGG_JET_TPI
 #define CGG_JET_TPI 2        // tiles a warp scores per iteration of the jet loop (1 or 2)
 #endif
@@ -503,28 +506,45 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     unsigned riskA = 0, riskB = 0;
     ps.prologue(prefetched);
     unsigned stage = 0;
+    auto score_tile = [&](unsigned st, int64_t off) {
+        const uint32_t s = ps.sbase + st * STAGE;
+        double2 ea = lds2(s), eb = lds2(s + 512u);
+        if (cj >= 0) {
+            const double2 cv = lds2(s + 2048u);
+            ea.x = eta_shift(ea.x, cv.x, cdA); ea.y = eta_shift(ea.y, cv.y, cdA);
+            eb.x = eta_shift(eb.x, cv.x, cdB); eb.y = eta_shift(eb.y, cv.y, cdB);
+            *reinterpret_cast<double2 *>(etaA + off) = ea;
+            *reinterpret_cast<double2 *>(etaB + off) = eb;
+        }
+        const double2 yy = lds2(s + 1024u);
+        double2 xs = lds2(s + 1536u);
+        xs.x *= cscale; xs.y *= cscale;
+        JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
+        JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
+    };
+#if CGG_PAIR_TPI == 2
+    for (; ps.pa < ps.pa_end; ) {
+        ps.issue_next((stage + RING_D - 1) & (RING_D - 1));
+        cp_async_wait<RING_D - 2>();
+        const int64_t off0 = (ps.pa - etaA) - RING_D * ps.step, off1 = off0 + ps.step;
+        if (off1 + 1 < n) {
+            score_tile(stage, off0);
+            score_tile((stage + 1) & (RING_D - 1), off1);
+        } else if (off0 + 1 < n) {
+            score_tile(stage, off0);
+        }
+        ps.issue_next(stage);
+        stage = (stage + 2) & (RING_D - 1);
+    }
+#else
     for (; ps.pa < ps.pa_end; ) {
         ps.issue_next((stage + RING_D - 1) & (RING_D - 1));
         cp_async_wait<RING_D - 1>();
         const int64_t off = (ps.pa - etaA) - RING_D * ps.step;        // row index of this lane's pair in the tile being scored
-        if (off + 1 < n) {
-            const uint32_t s = ps.sbase + stage * STAGE;
-            double2 ea = lds2(s), eb = lds2(s + 512u);
-            if (cj >= 0) {
-                const double2 cv = lds2(s + 2048u);
-                ea.x = eta_shift(ea.x, cv.x, cdA); ea.y = eta_shift(ea.y, cv.y, cdA);
-                eb.x = eta_shift(eb.x, cv.x, cdB); eb.y = eta_shift(eb.y, cv.y, cdB);
-                *reinterpret_cast<double2 *>(etaA + off) = ea;
-                *reinterpret_cast<double2 *>(etaB + off) = eb;
-            }
-            const double2 yy = lds2(s + 1024u);
-            double2 xs = lds2(s + 1536u);
-            xs.x *= cscale; xs.y *= cscale;
-            JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
-            JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
-        }
+        if (off + 1 < n) score_tile(stage, off);
         stage = (stage + 1) & (RING_D - 1);
     }
+#endif
     cp_async_wait<0>();
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
         const int64_t t = n - 1;
