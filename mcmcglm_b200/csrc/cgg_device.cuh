@@ -109,7 +109,7 @@ struct Dev {
     double *slots;             // [C][G][NV] per-CTA partial sums of the pass in flight (persistent driver)
     Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
     unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
-    int64_t n, p, ldx, lde, n_tiles, n_iter;
+    int64_t n, p, ldx, lde, n_tiles, n_iter, iter_stop;   // iter_stop: iteration count at which this launch stops (<= n_iter)
     uint64_t n_u, seed;
     int64_t max_steps;
     double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds)
@@ -1052,7 +1052,7 @@ __device__ __forceinline__ void accept_value(const Dev &d, int c, ChainState &s,
     s.updates++;
     s.j++;
     if (s.j == d.p) { s.j = 0; s.iter++; }
-    s.phase = (s.iter >= d.n_iter) ? PH_FLUSH : PH_START;
+    s.phase = (s.iter >= d.iter_stop) ? PH_FLUSH : PH_START;
 }
 
 // Lane-0 scalar code: consume the log-potentials F[0..ncand) of the pass that just finished.

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     __shared__ double2 s_l1p[L1P_N + 1];
     CtaShared sh(smem_raw, d.C);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (__ldcg(&d.hdr->abort)) return;        // an earlier launch of this run gave up
     load_l1p_table(s_l1p);
     for (int i = threadIdx.x; i < d.C; i += THREADS) { sh.ver[i] = 0ULL; sh.cnt[i] = 0; sh.lock[i] = 0; }
     for (int i = threadIdx.x; i < d.C * CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl) + i);
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             if (!wait_decision(c, round)) return;
             // ---- chains 2k and 2k + 1 at the same coordinate share one walk over the rows (pair pass)
             bool pair = false;
-            if (d.pair && !(c & 1) && c + 1 < d.C) {
+            if (d.pair && !(c & 1) && c + 1 < d.C &&
+                ((unsigned)(__double_as_longlong(sh.ctl[c * CTL_WORDS + 1]) >> 32) & JET_BIT)) {     // only a jet pass can be shared
                 if (!wait_decision(c + 1, round)) return;
                 // the shared control blocks must be exactly the ones of this round (a finished chain's never are)
                 pair = (*(volatile unsigned long long *)&sh.ver[c] == round) && (*(volatile unsigned long long *)&sh.ver[c + 1] == round) &&
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
             if (pair_prefetched && !pair) { cp_async_wait<0>(); pair_prefetched = false; }    // (cannot happen: the blocks were checked)
+            if (pair && prefetched) { cp_async_wait<0>(); prefetched = false; }               // a single-pass prefetch of chain c: other ring layout
             if (pair) {
                 const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
                 const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(cwA[1]) >> 32)) & JET_FULL);
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             int j = -1;
             const int nxt = (c + 1 == d.C) ? 0 : c + 1;
             const unsigned long long nround = (c + 1 == d.C) ? round + 1 : round;
-            LookAhead la{&sh, d.sync, d.ctl, (d.C > 1 && !d.pair) ? nxt : -1, nround, 0, 0};
+            LookAhead la{&sh, d.sync, d.ctl, d.C > 1 ? nxt : -1, nround, 0, 0};
             const int nc = worker_pass<FAMILY>(d, c, sh.ctl + c * CTL_WORDS, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32,
                                                acc, j, prefetched, nxt, &la, prof ? &t_tiles : nullptr);
             n_look += la.n_look; n_look_ok += la.n_ok;
@@ -558,6 +561,21 @@ __global__ void jet_debug_kernel(Dev d, int c, int j, int K, int light, double f
     if (lane < NV) out[2 * K + lane] = m[lane];
 }
 
+// Persistent driver, between two launches of one cgg_run: every chain stopped at an iteration boundary (its pending eta
+// update flushed); put the running ones back to "start the next coordinate", idle control blocks, versions from zero.
+__global__ void rearm_kernel(Dev d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    Ctl ct;
+    memset(&ct, 0, sizeof ct);
+    ct.commit_j = -1;
+    const bool alive = d.cs[c].status == CGG_OK && !d.hdr->abort;
+    if (alive) d.cs[c].phase = PH_START; else ct.j = -1;
+    d.ctl[c] = ct;
+    d.sync[c].arrive = 0ULL;
+    d.sync[c].version = alive ? 0ULL : (1ULL << 62);
+}
+
 // Row-sharded exchange tail: totals in rank order => bit-identical on every rank.
 __global__ void rank_sum_kernel(const double *gathered, int world, int count, double *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -758,8 +776,10 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     d.G = (int)G;
     d.lde = (d.n + 31) / 32 * 32;
 
-    auto A = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes); };
-    cudaError_t e = cudaSuccess;
+    // stream-ordered pool allocations (the pool keeps freed memory cached, see above): creating and destroying a handle
+    // costs no device-wide synchronising cudaMalloc / cudaFree
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    auto A = [&](void **p, size_t bytes) { return cudaMallocAsync(p, bytes, h->stream); };
     if (e == cudaSuccess) e = A((void **)&d.eta, sizeof(double) * (size_t)C * d.lde);
     if (e == cudaSuccess) e = A((void **)&d.beta, sizeof(double) * (size_t)C * d.p);
     if (e == cudaSuccess) e = A((void **)&d.shat, sizeof(double) * (size_t)C * d.p);
@@ -773,7 +793,6 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&h->scratch_dev, sizeof(double) * (3 * KMAX + NV + 2));
     if (e == cudaSuccess) e = A((void **)&h->colstat_dev, sizeof(double) * (size_t)d.p * CS_STRIDE);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->hdr_pinned, sizeof(Hdr));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) {
@@ -803,9 +822,11 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     Dev &d = h->d;
-    cudaFree(d.eta); cudaFree(d.beta); cudaFree(d.shat); cudaFree(d.acc); cudaFree(d.sync); cudaFree(d.xbuf);
-    cudaFree(d.ctl); cudaFree(d.cs); cudaFree(d.hdr); cudaFree(d.slots);
-    cudaFree(h->scratch_dev); cudaFree(h->prof_dev); cudaFree(h->colstat_dev);
+    if (h->stream) {
+        void *pool_owned[] = {d.eta, d.beta, d.shat, d.acc, d.sync, d.xbuf, d.ctl, d.cs, d.hdr, d.slots, h->scratch_dev, h->colstat_dev};
+        for (void *q : pool_owned) if (q) cudaFreeAsync(q, h->stream);
+    }
+    cudaFree(h->prof_dev);
     if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1264,11 +1285,25 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
 
     uint64_t launches = 0;
     CK(cudaEventRecord(h->ev0, h->stream));
+    d.iter_stop = n_iter;
     if (h->cfg.driver == CGG_DRIVER_PERSISTENT) {
-        Dev dd = d;
-        void *args[] = {&dd};
-        CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G + 1), dim3(THREADS), args, h->smem, h->stream));
-        launches = 1;
+        // With pair passes a long run is cut into launches of a few iterations: every launch starts all chains at
+        // coordinate 0 of the same iteration, which brings the chains of a pair back together after an exact-pass
+        // hand-over has cost one of them extra passes (inside a launch nothing re-aligns them).  A launch boundary costs
+        // ~0.1 ms: the pending eta updates are flushed, the chains re-armed on the device, no host round trip.
+        const int64_t chunk = d.pair ? (getenv("CGG_CHUNK") ? std::max(1, atoi(getenv("CGG_CHUNK"))) : 8) : n_iter;
+        for (int64_t done = 0; done < n_iter; done += chunk) {
+            if (done > 0) {
+                rearm_kernel<<<1, 32, 0, h->stream>>>(d);
+                CK(cudaGetLastError());
+                CK(cudaMemsetAsync(d.slots, 0, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G, h->stream));
+            }
+            Dev dd = d;
+            dd.iter_stop = std::min(done + chunk, n_iter);
+            void *args[] = {&dd};
+            CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G + 1), dim3(THREADS), args, h->smem, h->stream));
+            ++launches;
+        }
     } else {
         const int batch = (d.sharded && !h->comm) ? 1 : 32;   // host callbacks are synchronous; NCCL and kernels queue up
         for (;;) {
