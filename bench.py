@@ -413,7 +413,12 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if (a.driver == "persistent" and not sharded) else "pass_kernel",
                              "algorithmic_bytes_per_step": agg["algorithmic_bytes"] / a.steps, "kernel_ms_per_step": agg["sweep_ms"] / a.steps,
-                             "grid": [ctas, threads]},
+                             "grid": [ctas, threads],
+                             "dram_gbs_from_traffic": (traffic / (agg["sweep_ms"] / a.steps * 1e-3) / 1e9) if traffic else None,
+                             "note": "algorithmic bytes = 40 n per coordinate update (y, eta, X_j, X_commit read, eta written), counted per "
+                                     "chain; the chains of a GPU work on the same column, so X_j / X_commit / y are staged once per pair of "
+                                     "chains and served by L2 for the other pairs: DRAM traffic (`traffic`, ncu) is ~0.4x the algorithmic "
+                                     "bytes and frac can exceed 1"},
                 "cpu_baseline": cpu,
                 "engine_stats": {"passes_per_update": agg["passes"] / max(agg["updates"], 1) * C,
                                  "chain_passes_per_update": agg["chain_passes"] / max(agg["updates"], 1),
