@@ -95,3 +95,24 @@ def test_infinite_entry_in_a_column_is_an_error_not_a_hang():
         e.init_chain(0, np.zeros(2))
         with pytest.raises(CggError):
             e.run(3)
+
+
+def test_pair_passes_and_chunked_launches_change_nothing(monkeypatch):
+    """Pair passes (two chains per walk over the rows) and the cutting of a run into short launches are scheduling
+    only: same samples, same counts as one chain per pass in a single launch (the chains start from different points,
+    so the first iterations include exact-pass hand-overs that put the chains of a pair out of step)."""
+    X, y, bt = synth("binomial", 20000, 6, seed=17)
+    beta0 = 0.4 * np.random.default_rng(3).standard_normal((6, 6))
+    U = np.random.default_rng(4).random((6, 60000))
+
+    def run(pair, chunk):
+        monkeypatch.setenv("CGG_PAIR", str(pair))
+        monkeypatch.setenv("CGG_CHUNK", str(chunk))
+        return _chains("binomial", "laplace", X, y, beta0, 23, U, w=0.5)
+    S0, st0 = run(0, 1000)
+    for pair, chunk in ((1, 1000), (1, 3), (1, 1), (0, 2)):
+        S, st = run(pair, chunk)
+        assert np.array_equal(S, S0), (pair, chunk)
+        for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
+            assert st[k] == st0[k], (pair, chunk, k)
+    assert run(1, 3)[1]["launches"] == 8
