@@ -1,11 +1,14 @@
 // cgg_device.cuh -- device-side data layout and the device routines every sweep kernel is made of:
-//   warp_pass_chain<FAMILY>() : one warp, one chain, one pass over the warp's row tiles: scores every
-//                               live candidate and applies a pending eta update (reference a4..a9 + a5)
-//   decide_chain()            : the qslice stepping-out / shrinkage state machine (reference a3) for one
-//                               chain, run by one warp once per pass, with exact speculative candidates
-// Workers are WARPS.  Worker w owns the 64-row tiles w, w+W, w+2W, ... for the whole run (at any moment
-// the grid touches one contiguous window of every operand); chains are independent, each with its own
-// arrival counter and version flag, so there is no grid-wide barrier anywhere.
+//   warp_pass_jet<FAMILY, FULL>()  : one warp, one chain, one JET pass over the warp's row tiles: applies the pending eta
+//                                    update and accumulates the derivative moments of the log-likelihood along the
+//                                    column (cgg_jet.cuh); warp_pass_jet2: the same for two chains at the same coordinate
+//   warp_pass_chain<FAMILY>()      : one warp, one chain, one EXACT pass: scores every live candidate in fp64 (fp32
+//                                    pre-filter for far ones) and applies a pending eta update (reference a4..a9 + a5)
+//   jet_decide()                   : the whole qslice stepping-out / shrinkage update (reference a3) from one jet pass
+//   decide_chain()                 : one decision of a chain: jet_decide, or the resumable state machine over exact passes
+// Workers are WARPS.  Worker w owns the 64-row tiles w, w+W, w+2W, ... for the whole run (at any moment the grid touches
+// one contiguous window of every operand); chains are independent pipelines pass -> decision -> pass with their own
+// result slots and version flag, so there is no grid-wide barrier anywhere.
 #pragma once
 #include "cgg_math.cuh"
 #include "cgg_jet.cuh"
@@ -793,16 +796,10 @@ __device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, i
 #pragma unroll
         for (int k = 0; k < NV; ++k)
             if (k < nc) pw[k] = acc[k];
-#ifdef CGG_CTA_FENCE
-        asm volatile("fence.acq_rel.cta;" ::: "memory");
-#endif
         last = (atomicAdd_block(&sh.cnt[c], 1) == nworkers - 1);
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-#ifdef CGG_CTA_FENCE
-    asm volatile("fence.acq_rel.cta;" ::: "memory");
-#endif
     // three lanes per value, each adding every third warp's partial, then two fixed-order adds
     static_assert(3 * NV <= 32, "three lanes per value");
     const int k0 = lane % NV, g0 = lane / NV;
@@ -845,10 +842,7 @@ __device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long
 
 // Value k of chain c's finished pass = the G slots added in CTA order (lane l takes CTAs l, l + 32, ..., then a
 // butterfly: the same bits in every lane and on every run).  Returns false if some entry does not carry the stamp yet.
-#ifndef CGG_SLOTSUM_INLINE
-#define CGG_SLOTSUM_INLINE __forceinline__
-#endif
-__device__ CGG_SLOTSUM_INLINE bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
+__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
     const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
     double part[NV];
 #pragma unroll
@@ -861,10 +855,7 @@ __device__ CGG_SLOTSUM_INLINE bool slots_sum(const Dev &d, int c, int nvals, uns
     if (d.G <= 32 * SLOT_ROUNDS) {
         // five values at a time: their 5 x SLOT_ROUNDS loads are independent and all issued before the first add, so the
         // decider pays two round trips to L2 instead of one per value (the decision is on every chain's critical cycle)
-#ifndef CGG_SLOT_KB
-#define CGG_SLOT_KB 5
-#endif
-        constexpr int KB = CGG_SLOT_KB;
+        constexpr int KB = 5;
         static_assert(NV % KB == 0, "values are read in batches of five");
 #pragma unroll
         for (int k0 = 0; k0 < NV; k0 += KB) {
