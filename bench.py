@@ -333,11 +333,22 @@ def main():
 
     # ---------------------------------------------------------------- e2e (host buffers through the C ABI)
     e2e = None
-    if not a.no_e2e and not sharded:
-        Xp = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
-        yp = torch.empty(n, dtype=torch.float64, pin_memory=True)
-        Xp.copy_(X)
-        yp.copy_(y)
+    Xp = yp = None
+    e2e_ok = not a.no_e2e and not sharded
+    if e2e_ok:
+        try:                                   # N ranks pin N copies of X on the host: agree on whether that worked
+            Xp = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
+            yp = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            Xp.copy_(X)
+            yp.copy_(y)
+        except Exception as ex:                # noqa: BLE001
+            sys.stderr.write(f"[bench] rank {rank}: cannot stage pinned host buffers for e2e: {ex}\n")
+            e2e_ok = False
+        if multi:
+            t = torch.tensor([1 if e2e_ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(t.item())
+    if e2e_ok:
         eng.close()
         torch.cuda.synchronize()
         it = a.e2e_iters

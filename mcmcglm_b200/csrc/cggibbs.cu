@@ -792,7 +792,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&d.hdr, sizeof(Hdr));
     if (e == cudaSuccess) e = A((void **)&h->scratch_dev, sizeof(double) * (3 * KMAX + NV + 2));
     if (e == cudaSuccess) e = A((void **)&h->colstat_dev, sizeof(double) * (size_t)d.p * CS_STRIDE);
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->hdr_pinned, sizeof(Hdr));
+    h->hdr_pinned = new Hdr();      // (pageable: a pinned allocation per handle costs more than the 16-byte copies it serves)
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) {
@@ -823,16 +823,17 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     Dev &d = h->d;
     if (h->stream) {
-        void *pool_owned[] = {d.eta, d.beta, d.shat, d.acc, d.sync, d.xbuf, d.ctl, d.cs, d.hdr, d.slots, h->scratch_dev, h->colstat_dev};
+        void *pool_owned[] = {d.eta, d.beta, d.shat, d.acc, d.sync, d.xbuf, d.ctl, d.cs, d.hdr, d.slots, h->scratch_dev, h->colstat_dev,
+                              h->replay_dev, h->samples_dev};
         for (void *q : pool_owned) if (q) cudaFreeAsync(q, h->stream);
     }
     cudaFree(h->prof_dev);
     if (h->X_owned) cudaFreeAsync(h->X_owned, h->stream);
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->replay_dev); cudaFree(h->samples_dev); cudaFree(h->gather_dev);
+    cudaFree(h->gather_dev);
     if (h->comm) g_nccl.CommDestroy(h->comm);
-    if (h->hdr_pinned) cudaFreeHost(h->hdr_pinned);
+    delete h->hdr_pinned;
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1231,8 +1232,9 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     if (replay_u) {
         const uint64_t need = (uint64_t)C * n_u;
         if (need > h->replay_cap) {
-            cudaFree(h->replay_dev); h->replay_dev = nullptr; h->replay_cap = 0;
-            CK(cudaMalloc((void **)&h->replay_dev, sizeof(double) * (need ? need : 1)));
+            if (h->replay_dev) cudaFreeAsync(h->replay_dev, h->stream);
+            h->replay_dev = nullptr; h->replay_cap = 0;
+            CK(cudaMallocAsync((void **)&h->replay_dev, sizeof(double) * (need ? need : 1), h->stream));
             h->replay_cap = need;
         }
         CK(cudaMemcpyAsync(h->replay_dev, replay_u, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
@@ -1241,8 +1243,9 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     // sample store
     const size_t ns = (size_t)C * n_iter * d.p;
     if (ns > h->samples_cap) {
-        cudaFree(h->samples_dev); h->samples_dev = nullptr; h->samples_cap = 0;
-        CK(cudaMalloc((void **)&h->samples_dev, sizeof(double) * ns));
+        if (h->samples_dev) cudaFreeAsync(h->samples_dev, h->stream);
+        h->samples_dev = nullptr; h->samples_cap = 0;
+        CK(cudaMallocAsync((void **)&h->samples_dev, sizeof(double) * ns, h->stream));
         h->samples_cap = ns;
     }
     d.samples = h->samples_dev;
