@@ -149,8 +149,17 @@ template <> struct JetRow<CGG_POISSON> {
     template <bool FULL>
     static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *, double (&m)[JET_NV], unsigned &risk) {
         const double l = (e < kLogEps) ? kLogEps : e;
-        const double mu = exp(l);
-        m[0] += (mu > 1.7976931348623157e308) ? -INFINITY : fma(y, l, -mu);      // row_term<POISSON>
+        // exp(l), l >= -36.04: Cody-Waite reduction + the degree-11 polynomial of the fused softplus (<= 1 ulp, branch-free,
+        // ~17 fp64 instructions against ~30 for the general-purpose exp); 2^k by exponent arithmetic, overflow -> +Inf
+        const double SHIFT = 6755399441055744.0;
+        const double kd = fma(l, 1.4426950408889634, SHIFT);
+        const double kf = kd - SHIFT;
+        double r = fma(kf, -6.93147180369123816490e-01, l);
+        r = fma(kf, -1.90821492927058770002e-10, r);
+        const double pe = poly_exp(r);
+        double mu = __hiloint2double(__double2hiint(pe) + (__double2loint(kd) << 20), __double2loint(pe));
+        mu = (l > 709.0) ? INFINITY : mu;
+        m[0] += (mu > 1.7976931348623157e308) ? -INFINITY : fma(y, l, -mu);      // row_term<POISSON> (same value within 2 ulp of mu)
         const double nm = -mu;
         const double x2 = xs * xs, x3 = x2 * xs, x4 = x2 * x2, x5 = x4 * xs, x6 = x3 * x3, x7 = x6 * xs;
         m[1] = fma(xs, y - mu, m[1]);

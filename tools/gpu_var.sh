@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-B="python bench.py --no-cpu --steps 3 --warmup 2"
-P='import sys,json; d=json.loads(sys.stdin.read()); print(round(d["value"]), round(d["e2e"]["value"]), d["e2e"]["phases_last_call"]["run_ms"], d["clocks"]["sm_mhz"])'
-( echo "== 384"; timeout 300 $B 2>&1 | tail -1 | python -c "$P"
-echo "== 256"; CGG_LIB=$PWD/tools/var/lib_256.so timeout 300 $B 2>&1 | tail -1 | python -c "$P"
-echo "== 256p2"; CGG_LIB=$PWD/tools/var/lib_256p2.so timeout 300 $B 2>&1 | tail -1 | python -c "$P"
-echo "== 256p2 cfg4"; CGG_LIB=$PWD/tools/var/lib_256p2.so timeout 300 $B --workload cfg4 --no-e2e 2>&1 | tail -1 | cut -c1-100
-echo "== 256 cfg4"; CGG_LIB=$PWD/tools/var/lib_256.so timeout 300 $B --workload cfg4 --no-e2e 2>&1 | tail -1 | cut -c1-100
-echo "== 384 cfg4"; timeout 300 $B --workload cfg4 --no-e2e 2>&1 | tail -1 | cut -c1-100 ) > gpurun_out/var.log 2>&1
-cat gpurun_out/var.log
+( timeout 900 python -m pytest tests/test_gpu_jet.py tests/test_gpu_edges.py tests/test_gpu_parity.py tests/test_gpu_sharded.py -x -q -k "poisson or enclosure or chunk or more_chains" 2>&1 | tail -3 ) > gpurun_out/pois_tests.log 2>&1
+cat gpurun_out/pois_tests.log
+B="python bench.py --no-cpu --no-e2e --steps 3 --warmup 2 --workload cfg4"
+for i in 1 2; do timeout 300 $B 2>&1 | tail -1 | cut -c1-100; done
