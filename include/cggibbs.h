@@ -14,6 +14,10 @@
  *   - matrices are column-major fp64 exactly as R stores them: X[i + j*ldx], ldx >= n.
  *   - j is 0-based here; the R shim subtracts 1.
  *   - a handle is not re-entrant; all calls block until their results are in the output buffers.
+ *   - environment switches read by the library (experiments and tests only; none of them can change a result):
+ *     CGG_PAIR=0|1 (pair passes off/on; default on from 4 chains), CGG_CHUNK=<iterations per launch when pair passes
+ *     are on; default 8>, CGG_COARSE_THETA=<fp32 pre-filter policy>, CGG_PROFILE[_TRACE|_CTAS|_WARPS]=1 (phase counters
+ *     of the persistent kernel on stderr).
  *   - there is NO CPU fallback: unsupported family/link/prior/sampler => CGG_E_UNSUPPORTED,
  *     no usable CUDA device => CGG_E_CUDA.
  */
