@@ -39,5 +39,5 @@ cgg_sampler_args <- function(qslice_fun, dots) {
 
 cgg_config <- function(n, p, fam_code, prior_code, sampler, sd, n_chains, K, device, seed) {
   as.list(c(n = n, p = p, fam_code, prior_code, sampler, sd = sd, n_chains = n_chains, K = K,
-            device = device, driver = 0, chain_offset = 0, seed = seed, spec_tau = 0.5))
+            device = device, driver = 0, chain_offset = 0, seed = seed, spec_tau = 0.12))
 }

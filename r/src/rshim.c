@@ -44,7 +44,7 @@ SEXP C_cgg_create(SEXP cfg) {
     c.mode = CGG_MODE_CHAINS;
     c.chain_offset = (int32_t)num(cfg, "chain_offset", 0);
     c.seed = (uint64_t)num(cfg, "seed", 0);
-    c.spec_tau = num(cfg, "spec_tau", 0.5);
+    c.spec_tau = num(cfg, "spec_tau", 0.12);
     c.flags = (int32_t)num(cfg, "flags", 0);
     cgg_handle *h = NULL;
     chk(cgg_create(&c, &h));
