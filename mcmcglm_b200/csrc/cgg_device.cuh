@@ -203,6 +203,9 @@ struct ChainStream {
     // The tile -> worker map is rotated per chain (fixed for the run): n_tiles is rarely a multiple of W, so some
     // workers own one tile more than others; rotating by c * W / C spreads those extra tiles evenly over the
     // workers within a round of C chains, which is the granularity at which workers have slack.
+    // OWNERSHIP INVARIANT (the protocol's only ordering of eta accesses): for the whole run, row i of chain c's eta is
+    // read and written by one and the same warp -- `vw` below is the only tile -> warp map and PairStream computes the
+    // same value -- so eta never needs a fence or a release between passes.
     __device__ __forceinline__ ChainStream(const Dev &d, int c, const double *cw, long long wid, long long W_, int lane, uint32_t ring) {
         const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
         const int j = (int)(w0 & 0xffffffffLL);
@@ -211,7 +214,9 @@ struct ChainStream {
         xj = d.X + (int64_t)(j < 0 ? 0 : j) * d.ldx;
         xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
         y = d.y; eta = d.eta + (int64_t)c * d.lde;
-        W = W_; vw = (wid + (long long)c * (W / d.C)) % W; n_tiles = d.n_tiles; n = d.n;
+        // with pair passes on, both chains of a pair use the even chain's rotation in EVERY kind of pass (PairStream does the
+        // same), so a chain's eta rows keep their owner warp when it moves between pair passes and single passes
+        W = W_; vw = (wid + (long long)(d.pair ? (c & ~1) : c) * (W / d.C)) % W; n_tiles = d.n_tiles; n = d.n;
         slot0 = ring + (uint32_t)lane * 16u;
     }
     __device__ __forceinline__ void issue(long long T, int stage, int lane) const {
@@ -246,7 +251,7 @@ struct ChainStream {
 // chains a warp needs in flight with 2 warps per scheduler.
 template <int FAMILY, int NP>
 __device__ __forceinline__ void score_pairs(const RowPair<FAMILY> (&rp)[NP], int nc, unsigned cmask, const double *s_dl, double inv_sd,
-                                            const double2 *tab, double *sacc, int lane, float &bE, float &bX, unsigned &nearmask) {
+                                            const double2 *tab, double *sacc, int lane, float &bE, float &bX, unsigned &nearmask, float &smax) {
     const unsigned all = (nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u);
     unsigned fine = all & ~cmask;
     if (FAMILY == CGG_BINOMIAL && cmask) {
@@ -269,8 +274,11 @@ __device__ __forceinline__ void score_pairs(const RowPair<FAMILY> (&rp)[NP], int
             float v0 = 0.0f, v1 = 0.0f;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                v0 += softplus32(fmaf(xf0[q], d0, ef0[q]), n0) + softplus32(fmaf(xf1[q], d0, ef1[q]), n0);
-                v1 += softplus32(fmaf(xf0[q], d1, ef0[q]), n1) + softplus32(fmaf(xf1[q], d1, ef1[q]), n1);
+                const float s00 = fmaf(xf0[q], d0, ef0[q]), s01 = fmaf(xf1[q], d0, ef1[q]);
+                const float s10 = fmaf(xf0[q], d1, ef0[q]), s11 = fmaf(xf1[q], d1, ef1[q]);
+                smax = fmaxf(smax, fmaxf(fmaxf(s00, s01), fmaxf(s10, s11)));      // for the bound on R's log(1 - p) rounding
+                v0 += softplus32(s00, n0) + softplus32(s01, n0);
+                v1 += softplus32(s10, n1) + softplus32(s11, n1);
             }
             if (n0) nearmask |= 1u << k0;
             sacc[k0 * 32 + lane] -= (double)v0;
@@ -305,6 +313,8 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
     const int nc = cs.nc, cj = cs.cj;
     const int64_t n = cs.n;
     double *eta = cs.eta;
+    float smax = -INFINITY;     // largest s = +-eta' a pre-filtered candidate met on this lane's rows
+    unsigned nrows = 0;         // rows this lane scored
     if (!prefetched) cs.prologue(lane);
     for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] = 0.0;
     static_assert(RING_D >= 4 && (RING_D & (RING_D - 1)) == 0, "two tiles per iteration: ring of >= 4 stages, power of two");
@@ -332,14 +342,16 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
                 const uint32_t sa = cs.slot0 + stage * (RING_OPS * 512u), sb = cs.slot0 + st1 * (RING_OPS * 512u);
                 const RowPair<FAMILY> rp[2] = {RowPair<FAMILY>(lds2(sa + 512u), ea, lds2(sa + 1024u)),
                                                RowPair<FAMILY>(lds2(sb + 512u), eb, lds2(sb + 1024u))};
-                score_pairs<FAMILY, 2>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask);
+                score_pairs<FAMILY, 2>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask, smax);
+                nrows += 4;
             }
         } else if (i0 + 1 < n) {
             const double2 ea = load_eta(stage, i0);
             if (nc > 0) {
                 const uint32_t sa = cs.slot0 + stage * (RING_OPS * 512u);
                 const RowPair<FAMILY> rp[1] = {RowPair<FAMILY>(lds2(sa + 512u), ea, lds2(sa + 1024u))};
-                score_pairs<FAMILY, 1>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask);
+                score_pairs<FAMILY, 1>(rp, nc, cmask, s_dl, d.inv_sd, tab, sacc, lane, bE, bX, nearmask, smax);
+                nrows += 2;
             }
         }
         cs.issue(T + RING_D * cs.W, (int)stage, lane);
@@ -356,13 +368,22 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
             for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] += row_term<FAMILY>(yy, eta_shift(e, xx, s_dl[k]), d.inv_sd, tab);
         }
     }
+    if (FAMILY == CGG_BINOMIAL && cmask && nrows) {
+        // The pre-filter's bound is against the smooth -softplus; an exact evaluation follows R's log(1 - p) form, which
+        // deviates by at most 2^-54 (1 + e^s) per row for s <= 30 (rform_log1p_rho; above the clamp it is a constant).
+        // Folded into the sum the decider multiplies by (2^-22 + kappa) = 7.15e-7: 5.6e-17 / 7.15e-7, rounded up.
+        float ex;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fminf(smax, 30.01f) * 1.44269514f));
+        bE += (float)nrows * (1.0f + ex) * 8.2e-11f;
+    }
 }
 
 // One warp, one chain, one JET pass (cgg_jet.cuh): applies the pending eta update like any pass and accumulates
 // the exact log-likelihood at the committed eta plus the derivative moments along column j in registers.
 template <int FAMILY, bool FULL>
 __device__ __forceinline__ void jet_tile(const ChainStream &cs, double cdelta, double cscale, double inv_sd, int stage, double *eta_i,
-                                         const double2 *tab, double (&m)[NV], unsigned &risk) {
+                                         const double2 *tab, double (&m)[NV], unsigned &risk, unsigned &rows) {
+    rows += 2;
     const uint32_t s = cs.slot0 + (uint32_t)stage * (RING_OPS * 512u);
     double2 e = lds2(s);
     if (cs.cj >= 0) {
@@ -386,6 +407,7 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
 #pragma unroll
     for (int k = 0; k < NV; ++k) m[k] = 0.0;
     unsigned risk = 0;     // running max of a per-row integer key (JetRow): compared with the family's threshold at the end
+    unsigned rows = 0;     // rows this lane scored
     // Running pointers of the tile being ISSUED (RING_D - 1 tiles ahead of the one being scored), advanced by one
     // stride per iteration: four 64-bit adds instead of re-deriving four addresses from the chain/column indices.
     {
@@ -417,10 +439,10 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
             cp_async_wait<RING_D - 2>();
             double *e0 = const_cast<double *>(pe) - RING_D * step, *e1 = e0 + step;
             if (e1 < pe_last) {
-                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk);
-                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)((stage + 1) & (RING_D - 1)), e1, tab, m, risk);
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk, rows);
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)((stage + 1) & (RING_D - 1)), e1, tab, m, risk, rows);
             } else if (e0 < pe_last) {
-                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk);
+                jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, e0, tab, m, risk, rows);
             }
             issue_next(stage);
             stage = (stage + 2) & (RING_D - 1);
@@ -430,7 +452,7 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
             issue_next((stage + RING_D - 1) & (RING_D - 1));
             cp_async_wait<RING_D - 1>();
             double *ecur = const_cast<double *>(pe) - RING_D * step;
-            if (ecur < pe_last) jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk);
+            if (ecur < pe_last) jet_tile<FAMILY, FULL>(cs, cdelta, cscale, d.inv_sd, (int)stage, ecur, tab, m, risk, rows);
             stage = (stage + 1) & (RING_D - 1);
         }
 #endif
@@ -443,9 +465,11 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
             double e = __ldcg(eta + t);
             if (cj >= 0) { e = eta_shift(e, __ldg(cs.xc + t), cdelta); eta[t] = e; }
             JetRow<FAMILY>::template add1<FULL>(__ldg(cs.y + t), e, __ldg(cs.xj + t) * cscale, d.inv_sd, tab, m, risk);
+            rows += 1;
         }
     }
     if (FAMILY != CGG_GAUSSIAN) m[9] = (risk >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
+    if (FAMILY == CGG_BINOMIAL) m[8] = rform_noise_sum(risk, rows);
 }
 
 // One warp, TWO chains that are at the same coordinate (same column j, same pending column), one jet pass: y, X_j and
@@ -467,7 +491,7 @@ struct PairStream {      // running pointers of a pair pass: the tile to be issu
         cj = (int)(w1 & 0xffffffffLL);
         etaA = d.eta + (int64_t)c0 * d.lde; etaB = etaA + d.lde;
         xj = d.X + (int64_t)j * d.ldx; xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
-        vw = (wid + (long long)c0 * (W / d.C)) % W;
+        vw = (wid + (long long)(c0 & ~1) * (W / d.C)) % W;      // == ChainStream's rotation of c0 and of c0 + 1 (d.pair is on)
         sbase = ring + (uint32_t)lane * 16u;
         step = W * TILE_ROWS;
         const int64_t i0 = vw * TILE_ROWS + 2 * lane;
@@ -506,7 +530,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     static_assert(RING_OPS >= 5, "a pair pass stages five operands");
 #pragma unroll
     for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
-    unsigned riskA = 0, riskB = 0;
+    unsigned riskA = 0, riskB = 0, rows = 0;
     ps.prologue(prefetched);
     unsigned stage = 0;
     auto score_tile = [&](unsigned st, int64_t off) {
@@ -522,6 +546,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
         const double2 yy = lds2(s + 1024u);
         double2 xs = lds2(s + 1536u);
         xs.x *= cscale; xs.y *= cscale;
+        rows += 2;
         JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
         JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
     };
@@ -562,6 +587,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
             const double yy = __ldg(d.y + t), xx = __ldg(ps.xj + t) * cscale;
             JetRow<FAMILY>::template add1<FULL>(yy, ea, xx, d.inv_sd, tab, mA, riskA);
             JetRow<FAMILY>::template add1<FULL>(yy, eb, xx, d.inv_sd, tab, mB, riskB);
+            rows += 1;
         }
     }
     after_tiles();     // the ring is free: the caller may already request the next pair's first tiles
@@ -569,6 +595,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
         mA[9] = (riskA >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
         mB[9] = (riskB >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
     }
+    if (FAMILY == CGG_BINOMIAL) { mA[8] = rform_noise_sum(riskA, rows); mB[8] = rform_noise_sum(riskB, rows); }
 #pragma unroll
     for (int k = 0; k < NV; ++k) { mA[k] = warp_sum(mA[k]); mB[k] = warp_sum(mB[k]); }
 }
@@ -776,13 +803,28 @@ __device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, 
 
 // Persistent driver: the same CTA-level fold, but the CTA's sums go to the CTA's own slot of the chain as 16-byte
 // {value, stamp} pairs (stamp = number of the pass + 1), written by ONE lane with plain vector stores: no atomic, no
-// fence, nothing to wait for -- the warp moves on to its next chain at once.  A 16-byte aligned store / load is a
-// single memory transaction, so a pair is never torn; the decider polls the stamps and only uses a value whose own
-// stamp is the expected one (the protocol of NCCL's low-latency paths).  With atomics on shared accumulators -- and
+// fence, nothing to wait for -- the warp moves on to its next chain at once.  The decider polls the stamps and only uses
+// a value whose own stamp is the expected one (the protocol of NCCL's low-latency paths).  With atomics on shared accumulators -- and
 // still with a release-increment of an arrival counter, whose implied membar costs microseconds under load -- the last
 // warp of every CTA fell behind, was therefore last again, and paced the whole grid.  Entry 0 is always written (an
 // idle pass delivers nothing else).  The decider adds the G slots in CTA order: reproducible.
-struct __align__(16) SlotEntry { double v; unsigned long long stamp; };
+// Each 64-bit word of an entry validates itself: {stamp32 : value half32}.  The PTX memory model makes every element of a
+// vector access a scalar access of its own, so two words {value64, stamp64} could in principle be observed torn; a 64-bit
+// element cannot.  The stamp is the pass number + 1 (32 bits: versions restart at every launch; 0 = never written).
+struct __align__(16) SlotEntry { unsigned long long w0, w1; };      // w0 = stamp << 32 | lo32(value), w1 = stamp << 32 | hi32(value)
+__device__ __forceinline__ void slot_store(SlotEntry *dst, double v, unsigned stamp) {
+    const unsigned long long s = (unsigned long long)stamp << 32;
+    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(s | (unsigned)__double2loint(v)), "l"(s | (unsigned)__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ bool slot_load(const SlotEntry *src, unsigned stamp, double &v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+    return (unsigned)(w0 >> 32) == stamp && (unsigned)(w1 >> 32) == stamp;
+}
+__device__ __forceinline__ bool slot_stamped(const SlotEntry *src, unsigned stamp) {
+    return (unsigned)(__ldcg(&src->w0) >> 32) == stamp;
+}
 __device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers,
                                                   unsigned long long stamp, const double (&acc)[NV]) {
     // Shared-memory hand-over without a MEMBAR: the partials are written with volatile stores and the counter is bumped by
@@ -811,47 +853,43 @@ __device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, i
     }
     v = (v + __shfl_down_sync(0xffffffffu, v, NV)) + __shfl_down_sync(0xffffffffu, v, 2 * NV);   // valid in lanes < NV
     if (lane == 0) sh.cnt[c] = 0;
-    if (lane < NV && (lane < nc || lane == 0)) {
-        SlotEntry *dst = reinterpret_cast<SlotEntry *>(d.slots) + ((size_t)c * d.G + blockIdx.x) * NV + lane;
-        asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(v)), "l"(stamp) : "memory");   // ONE 16-byte store
-    }
+    if (lane < NV && (lane < nc || lane == 0))
+        slot_store(reinterpret_cast<SlotEntry *>(d.slots) + ((size_t)c * d.G + blockIdx.x) * NV + lane, v, (unsigned)stamp);
     __syncwarp();
 }
 
 // Decider side: has every CTA delivered pass `stamp - 1` of chain c?  (entry 0 of each slot; the other entries are
 // validated when they are read)
 constexpr int SLOT_ROUNDS = 5;     // 32 * 5 = 160 >= worker CTAs of a B200: the decider's loads are all issued before any is used
-__device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long long stamp, int lane) {
+__device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long long stamp64, int lane) {
     const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
+    const unsigned stamp = (unsigned)stamp64;
     bool ok = true;
     if (d.G <= 32 * SLOT_ROUNDS) {
         // a light first look (one load per lane): the deciders share an SM, and a warp that polls with everything it has
         // slows down the warps that are deciding
-        const bool ok0 = (lane < d.G) ? (__ldcg(&base[(size_t)lane * NV].stamp) == stamp) : true;
+        const bool ok0 = (lane < d.G) ? slot_stamped(base + (size_t)lane * NV, stamp) : true;
         if (!__all_sync(0xffffffffu, ok0)) return false;
         unsigned long long st[SLOT_ROUNDS];
 #pragma unroll
-        for (int r = 1; r < SLOT_ROUNDS; ++r) { const int g = lane + 32 * r; st[r] = (g < d.G) ? __ldcg(&base[(size_t)g * NV].stamp) : stamp; }
+        for (int r = 1; r < SLOT_ROUNDS; ++r) { const int g = lane + 32 * r; st[r] = (g < d.G) ? __ldcg(&base[(size_t)g * NV].w0) : stamp64 << 32; }
 #pragma unroll
-        for (int r = 1; r < SLOT_ROUNDS; ++r) ok = ok && (st[r] == stamp);
+        for (int r = 1; r < SLOT_ROUNDS; ++r) ok = ok && ((unsigned)(st[r] >> 32) == stamp);
     } else {
-        for (int g = lane; g < d.G; g += 32) ok = ok && (__ldcg(&base[(size_t)g * NV].stamp) == stamp);
+        for (int g = lane; g < d.G; g += 32) ok = ok && slot_stamped(base + (size_t)g * NV, stamp);
     }
     return __all_sync(0xffffffffu, ok);
 }
 
 // Value k of chain c's finished pass = the G slots added in CTA order (lane l takes CTAs l, l + 32, ..., then a
 // butterfly: the same bits in every lane and on every run).  Returns false if some entry does not carry the stamp yet.
-__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp, int lane, double (&out)[NV]) {
+__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp64, int lane, double (&out)[NV]) {
     const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
+    const unsigned stamp = (unsigned)stamp64;
     double part[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) part[k] = 0.0;
     bool ok = true;
-    auto take = [&](const int4 &t, int k) {
-        part[k] += __hiloint2double(t.y, t.x);
-        ok = ok && ((((unsigned long long)(unsigned)t.w << 32) | (unsigned)t.z) == stamp);
-    };
     if (d.G <= 32 * SLOT_ROUNDS) {
         // five values at a time: their 5 x SLOT_ROUNDS loads are independent and all issued before the first add, so the
         // decider pays two round trips to L2 instead of one per value (the decision is on every chain's critical cycle)
@@ -860,27 +898,27 @@ __device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsign
 #pragma unroll
         for (int k0 = 0; k0 < NV; k0 += KB) {
             if (k0 < nvals) {
-                int4 t[KB][SLOT_ROUNDS];
+                double t[KB][SLOT_ROUNDS];
+                bool tk[KB][SLOT_ROUNDS];
 #pragma unroll
                 for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                     for (int r = 0; r < SLOT_ROUNDS; ++r) {
                         const int g = lane + 32 * r;
-                        t[kk][r] = (g < d.G && k0 + kk < nvals) ? __ldcg(reinterpret_cast<const int4 *>(base + (size_t)g * NV) + k0 + kk)
-                                                                : make_int4(0, 0, (int)(unsigned)stamp, (int)(unsigned)(stamp >> 32));
+                        t[kk][r] = 0.0; tk[kk][r] = true;
+                        if (g < d.G && k0 + kk < nvals) tk[kk][r] = slot_load(base + (size_t)g * NV + k0 + kk, stamp, t[kk][r]);
                     }
 #pragma unroll
                 for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
-                    for (int r = 0; r < SLOT_ROUNDS; ++r) take(t[kk][r], k0 + kk);
+                    for (int r = 0; r < SLOT_ROUNDS; ++r) { part[k0 + kk] += t[kk][r]; ok = ok && tk[kk][r]; }
             }
         }
     } else {
         for (int g = lane; g < d.G; g += 32) {
-            const int4 *src = reinterpret_cast<const int4 *>(base + (size_t)g * NV);
 #pragma unroll
             for (int k = 0; k < NV; ++k)
-                if (k < nvals) take(__ldcg(src + k), k);
+                if (k < nvals) { double v; ok = slot_load(base + (size_t)g * NV + k, stamp, v) && ok; part[k] += v; }
         }
     }
 #pragma unroll

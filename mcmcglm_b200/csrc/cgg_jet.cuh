@@ -17,8 +17,9 @@
 //
 // Slot layout of the NV values a jet pass delivers:
 //   gaussian : 0..2 M_0..M_2 (exact quadratic, no remainder) | 3 sum|z||eta| | 4 sum|z| | 5 sum|eta|
-//   binomial : 0 M_0 (full passes only; light passes leave it 0) | 1..7 the positive-form sums m_1..m_7 (see JetRow<CGG_BINOMIAL>) | 9 rows with |eta| >= 21.9 (the
-//              stats logit clamp at |eta| = 30 is then within reach of the enclosure's radius)
+//   binomial : 0 M_0 (full passes only; light passes leave it 0) | 1..7 the positive-form sums m_1..m_7 (see JetRow<CGG_BINOMIAL>) |
+//              8 an upper bound of sum_i e^|eta_i| (rform_noise_sum: bounds the rounding of p that R's log(1 - p) carries) |
+//              9 rows with |eta| >= 21.9 (the stats logit clamp at |eta| = 30 is then within reach of the enclosure's radius)
 //   poisson  : 0..6 M_0..M_6 | 7 sum|xs|^7 mu | 8 sum(|y| + mu)(|eta| + 1) | 9 rows too close to the pmax(., eps) clamp
 #pragma once
 #include "cgg_math.cuh"
@@ -94,10 +95,14 @@ template <> struct JetRow<CGG_BINOMIAL> {
         const double kf = kd - SHIFT;
         double r = fma(kf, -6.93147180369123816490e-01, -a);
         r = fma(kf, -1.90821492927058770002e-10, r);
-        const double p = poly_exp(r);
-        const double T = __hiloint2double(__double2hiint(p) + (__double2loint(kd) << 20), __double2loint(p));   // exp(-a)
+        double pe, po;
+        poly_exp_eo(r, pe, po);
+        const double p = fma(po, r, pe);
+        const double T = scale2(p, __double2loint(kd));                      // exp(-a)
         double rr;
         if (FULL) {
+            // y = 0 and 8 < eta <= 30: R's log(1 - p) carries the rounding of p (cgg_math.cuh, rform_log1p_rho)
+            if (!(y > 0.5) && e > kRFormLo && e <= 30.0) m[0] += rform_log1p_rho(T, scale2(fma(-po, r, pe), -__double2loint(kd)));
             const int hs = he ^ ((__double2hiint(y) << 2) & 0x80000000);    // sign of s = (y == 1) ? -eta : eta
             const double md = fma(T, (double)L1P_N, SHIFT);
             int mi = __double2loint(md);
@@ -180,6 +185,16 @@ template <> struct JetRow<CGG_POISSON> {
     }
 };
 
+// Upper bound of sum_i e^|eta_i| over the `rows` rows a lane scored, from the running maximum of the high words of
+// |eta_i| (JetRow<CGG_BINOMIAL>'s risk key): rows * e^amax, amax rounded up, ex2.approx (2^-22) and the fp32 roundings
+// covered by the factor 1.001.  Overflow gives +Inf and a NaN key NaN: the enclosure then decides nothing.
+__device__ __forceinline__ double rform_noise_sum(unsigned risk_key, unsigned rows) {
+    const float amax = __double2float_ru(__hiloint2double((int)risk_key, -1));
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(__fmul_ru(amax, 1.44269514f)));
+    return (double)rows * (double)(ex * 1.001f);
+}
+
 // ---- the enclosure --------------------------------------------------------------------------------
 // m[]: the pass's sums; cst: the column's statistics; delta = cand - x0; fmag: the magnitude of the log-likelihood
 // (|M_0|, or the carried |f(x0)| after a light pass).  Returns the surrogate log-likelihood DIFFERENCE
@@ -217,7 +232,12 @@ __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV]
         // exact passes: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|) with every |eta| < 21.9 (else
         // m[9] != 0); softplus and sums relative to |f|, for both evaluations
         const double bex = JET_EPS * (21.9 * n + 2.0 * a * cst[2]) + ce * (2.0 * fmag + fabs(dl) + bt);
-        B = 1.01 * (bt + ce * bmom + bex);
+        // R's log(1 - p) form (rform_log1p_rho): an exact evaluation deviates from the smooth function by at most
+        // 2^-54 (1 + e^t) per row, t <= |eta| + a; both evaluations of the difference, and slack for log1p(rho) vs rho
+        float ea;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(__fmul_ru(__double2float_ru(a), 1.44269514f)));
+        const double brf = 2.0 * JET_EPS * (n + (double)(ea * 1.001f) * m[8]);
+        B = 1.01 * (bt + ce * bmom + bex + brf);
         if (!(a <= JET_AMAX) || m[9] != 0.0) B = INFINITY;
         return dl;
     }

@@ -29,17 +29,46 @@ __device__ __forceinline__ double eta_shift(double eta, double x, double diff) {
 // evaluating at |s| = 36.04...: applied here to a = |s|.  Coefficients and table: cgg_math_tables.cuh
 // (tools/gen_math_tables.py, checked against mpmath).  NaN propagates; the table index is clamped so a NaN
 // can never index out of bounds.
-__device__ __forceinline__ double poly_exp(double r) {
+// exp(r) = pe + r po and exp(-r) = pe - r po: even and odd halves of the degree-11 polynomial (two interleaved
+// Horner chains in r^2, depth 7 instead of 11)
+__device__ __forceinline__ void poly_exp_eo(double r, double &pe, double &po) {
     static_assert(EXP_DEG == 11, "layout below assumes degree 11");
-    // two interleaved half-degree Horner chains in r^2 (depth 7 instead of 11)
     const double r2 = r * r;
-    double pe = EXP_C[10], po = EXP_C[11];
+    pe = EXP_C[10]; po = EXP_C[11];
     pe = fma(pe, r2, EXP_C[8]); po = fma(po, r2, EXP_C[9]);
     pe = fma(pe, r2, EXP_C[6]); po = fma(po, r2, EXP_C[7]);
     pe = fma(pe, r2, EXP_C[4]); po = fma(po, r2, EXP_C[5]);
     pe = fma(pe, r2, EXP_C[2]); po = fma(po, r2, EXP_C[3]);
     pe = fma(pe, r2, EXP_C[0]); po = fma(po, r2, EXP_C[1]);
+}
+__device__ __forceinline__ double poly_exp(double r) {
+    double pe, po;
+    poly_exp_eo(r, pe, po);
     return fma(po, r, pe);
+}
+// v * 2^k by exponent arithmetic (v in [0.5, 2], the result a normal number)
+__device__ __forceinline__ double scale2(double v, int k) { return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v)); }
+
+// ---- R's dbinom(0, 1, p, log = TRUE) at large eta ---------------------------------------------------
+// For y = 0 R does not evaluate log(1 - p) = -softplus(eta) as a function of eta: stats' logit_linkinv rounds
+// p = e / (1 + e), e = exp(eta), to a double first, and nmath's dbinom_raw then takes log(q) of q = 1 - p (exact by
+// Sterbenz; reference: R/glm_utils.R:45-47 -> dbinom -> dbinom_raw(x = 0, n = 1, p, q = 1 - p), p >= 0.1 branch).  For
+// eta > ~2.2, p lies in [0.9, 1) where doubles are 2^-53 apart, so q carries an absolute error of up to 2^-54 and log(q)
+// one of up to 2^-54 / q = 5.6e-17 (1 + e^eta): 1.7e-13 at eta = 8, 5e-8 at eta = 20, 6e-4 at eta = 30.  That is R's
+// result, so it is reproduced: with T = exp(-eta), q_hat = T / (1 + T) (1 ulp), p_R = fl(1 - q_hat), q_R = 1 - p_R and
+//     log(q_R) = -softplus(eta) + log1p(rho),   rho = (q_R - q_hat) / q_hat = (q_R - q_hat) (1 + T) e^eta,
+// |rho| <= 6e-4.  q_R is the very double R forms except when 1 - q lies within ~1e-16 q of a rounding boundary (3 rows
+// in 1e4 at eta = 8, none from eta = 15 on; checked against the literal form in tests/test_oracle_math.py).  Applied for
+// kRFormLo < eta <= 30; below kRFormLo the two forms differ by < 2e-14 relative per row (covered by the 1e-12 gate), above
+// 30 stats' clamp makes p, q constants and both forms give log(2^-52).
+constexpr double kRFormLo = 8.0;
+__device__ __forceinline__ double rform_log1p_rho(double T /* exp(-eta) < e^-8 */, double Einv /* exp(eta) */) {
+    const double u = fma(-T, fma(-T, fma(-T, 1.0 - T, 1.0), 1.0), 1.0);     // 1 / (1 + T), T^5 < 5e-18
+    const double qh = T * u;
+    const double pR = __dadd_rn(1.0, -qh);
+    const double qR = __dadd_rn(1.0, -pR);
+    const double rho = (qR - qh) * (Einv * (1.0 + T));
+    return rho * fma(-rho, fma(-rho, 1.0 / 3.0, 0.5), 1.0);                  // log1p(rho), rho^4 / 4 < 4e-14 |rho|
 }
 __device__ __forceinline__ double poly_l1p_q(double v, double v2) {
     static_assert(L1P_QDEG == 6, "layout below assumes degree 6");
@@ -49,7 +78,8 @@ __device__ __forceinline__ double poly_l1p_q(double v, double v2) {
     qe = fma(qe, v2, L1P_Q[0]);
     return fma(qo, v, qe);
 }
-__device__ __forceinline__ void softplus2(double s0, double s1, const double2 *tab, double &o0, double &o1) {
+// z0 / z1: the row's response is 0 (s = eta): R's log(q) form applies above kRFormLo (see rform_log1p_rho)
+__device__ __forceinline__ void softplus2(double s0, double s1, const double2 *tab, double &o0, double &o1, bool z0 = false, bool z1 = false) {
     const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer
     double a0 = fabs(s0), a1 = fabs(s1);
     a0 = (a0 > 30.0) ? kLogitClampEta : a0;
@@ -58,9 +88,10 @@ __device__ __forceinline__ void softplus2(double s0, double s1, const double2 *t
     const double kf0 = kd0 - SHIFT, kf1 = kd1 - SHIFT;
     double r0 = fma(kf0, -6.93147180369123816490e-01, -a0), r1 = fma(kf1, -6.93147180369123816490e-01, -a1);
     r0 = fma(kf0, -1.90821492927058770002e-10, r0); r1 = fma(kf1, -1.90821492927058770002e-10, r1);
-    const double p0 = poly_exp(r0), p1 = poly_exp(r1);
-    const double t0 = __hiloint2double(__double2hiint(p0) + (__double2loint(kd0) << 20), __double2loint(p0));   // p * 2^k, k in [-52, 0]
-    const double t1 = __hiloint2double(__double2hiint(p1) + (__double2loint(kd1) << 20), __double2loint(p1));
+    double pe0, po0, pe1, po1;
+    poly_exp_eo(r0, pe0, po0); poly_exp_eo(r1, pe1, po1);
+    const double p0 = fma(po0, r0, pe0), p1 = fma(po1, r1, pe1);
+    const double t0 = scale2(p0, __double2loint(kd0)), t1 = scale2(p1, __double2loint(kd1));   // p * 2^k, k in [-52, 0]
     const double md0 = fma(t0, (double)L1P_N, SHIFT), md1 = fma(t1, (double)L1P_N, SHIFT);
     int m0 = __double2loint(md0), m1 = __double2loint(md1);
     m0 = min(max(m0, 0), L1P_N); m1 = min(max(m1, 0), L1P_N);
@@ -71,6 +102,11 @@ __device__ __forceinline__ void softplus2(double s0, double s1, const double2 *t
     const double l0 = tb0.y + fma(w0, q0, v0), l1 = tb1.y + fma(w1, q1, v1);
     o0 = ((s0 > 0.0) ? a0 : 0.0) + l0;
     o1 = ((s1 > 0.0) ? a1 : 0.0) + l1;
+    const bool f0 = z0 && s0 > kRFormLo && s0 <= 30.0, f1 = z1 && s1 > kRFormLo && s1 <= 30.0;
+    if (f0 || f1) {     // rare once a chain is near its stationary region (|eta| of a few units)
+        if (f0) o0 -= rform_log1p_rho(t0, scale2(fma(-po0, r0, pe0), -__double2loint(kd0)));
+        if (f1) o1 -= rform_log1p_rho(t1, scale2(fma(-po1, r1, pe1), -__double2loint(kd1)));
+    }
 }
 
 // ---- fp32 "coarse" softplus for the pre-filter ------------------------------------------------------
@@ -95,7 +131,8 @@ __device__ __forceinline__ float softplus32(float s, bool &near) {
 // hoisted out of the candidate loop.  term(delta) returns the sum of the two rows' log-density terms up to
 // a per-dataset constant (added once per sum, ll_const):
 //   gaussian  dnorm(y, eta', sd, log=TRUE)            -> -0.5 z^2            (R/glm_utils.R:40-42)
-//   binomial  dbinom(y, 1, logit_linkinv(eta'), TRUE) -> -softplus(+-eta')   (R/glm_utils.R:45-47)
+//   binomial  dbinom(y, 1, logit_linkinv(eta'), TRUE) -> -softplus(+-eta')   (R/glm_utils.R:45-47; y = 0 and
+//             eta' > 8: plus the rounding of p that R's log(1 - p) carries, rform_log1p_rho)
 //   poisson   dpois(y, pmax(exp(eta'), eps), TRUE)    -> y log(mu) - mu      (R/glm_utils.R:50-52)
 // with eta' = eta + X_j * delta formed as two roundings (eta_shift).
 template <int FAMILY> struct RowPair;
@@ -114,13 +151,15 @@ template <> struct RowPair<CGG_GAUSSIAN> {
 // +-(eta + x * delta): the sign is applied once per row instead of once per candidate.
 template <> struct RowPair<CGG_BINOMIAL> {
     double e0, e1, x0, x1;
+    bool z0, z1;     // y == 0: R's log(1 - p) branch (rform_log1p_rho)
     __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) {
-        const double g0 = (y.x > 0.5) ? -1.0 : 1.0, g1 = (y.y > 0.5) ? -1.0 : 1.0;
+        z0 = !(y.x > 0.5); z1 = !(y.y > 0.5);
+        const double g0 = z0 ? 1.0 : -1.0, g1 = z1 ? 1.0 : -1.0;
         e0 = e.x * g0; e1 = e.y * g1; x0 = x.x * g0; x1 = x.y * g1;
     }
     __device__ __forceinline__ double term(double dk, double, const double2 *tab) const {
         double o0, o1;
-        softplus2(eta_shift(e0, x0, dk), eta_shift(e1, x1, dk), tab, o0, o1);
+        softplus2(eta_shift(e0, x0, dk), eta_shift(e1, x1, dk), tab, o0, o1, z0, z1);
         return -(o0 + o1);
     }
 };
@@ -147,7 +186,7 @@ __device__ __forceinline__ double row_term(double y, double eta, double inv_sd, 
     if (FAMILY == CGG_BINOMIAL) {
         double o0, o1;
         const double s = (y > 0.5) ? -eta : eta;
-        softplus2(s, s, tab, o0, o1);
+        softplus2(s, s, tab, o0, o1, !(y > 0.5), false);
         return -o0;
     }
     double le = (eta < kLogEps) ? kLogEps : eta;

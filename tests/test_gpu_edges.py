@@ -116,3 +116,32 @@ def test_pair_passes_and_chunked_launches_change_nothing(monkeypatch):
         for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
             assert st[k] == st0[k], (pair, chunk, k)
     assert run(1, 3)[1]["launches"] == 8
+
+
+def test_pair_single_handover_stress_keeps_eta_ownership(monkeypatch):
+    """32 chains, n = 1e6, inflated enclosure bounds: every few updates some chain of a pair falls back to exact passes
+    (single-chain walks) while its partner goes on, then rejoins the pair at the next launch.  A chain's eta rows must be
+    owned by the same warp in both kinds of pass (ChainStream / PairStream use the pair's rotation): the run is
+    bit-identical to the one without pair passes, and eta == X beta at the end."""
+    n, p, C, iters = 1_000_000, 6, 32, 50
+    X, y, bt = synth("binomial", n, p, seed=23)
+    beta0 = bt + 0.01 * np.random.default_rng(2).standard_normal((C, p))
+
+    def run(pair):
+        monkeypatch.setenv("CGG_PAIR", str(pair))
+        with Engine(n, p, family="binomial", w=0.5, n_chains=C, K=8, seed=9, jet_bound_scale=3e5, **PRIOR_CASES["laplace"]) as e:
+            e.set_data(X, y)
+            for c in range(C):
+                e.init_chain(c, beta0[c])
+            S, st = e.run(iters)
+            fin = [e.state(c) for c in (0, 1, 17, 31)]
+        return S, st, fin
+    S1, st1, fin1 = run(1)
+    S0, st0, fin0 = run(0)
+    assert 0.002 * st1["updates"] < st1["jet_fallbacks"] + st1["jet_retries"] < 0.5 * st1["updates"]     # hand-overs did happen, not always
+    assert np.array_equal(S1, S0)
+    for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
+        assert st1[k] == st0[k], k
+    for (b1, e1), (b0, e0) in zip(fin1, fin0):
+        assert np.array_equal(e1, e0) and np.array_equal(b1, b0)
+        assert np.max(np.abs(e1 - X @ b1)) < 1e-11

@@ -45,6 +45,32 @@ def test_g1_log_potential(family, prior, n):
         assert abs(e.fx(0) - oracle.log_potential(m, X, y, beta, eta, 0, [beta[0]])[0]) <= RTOL_G1 * abs(e.fx(0))
 
 
+@pytest.mark.parametrize("sd_eta", [5.0, 15.0, 45.0])
+@pytest.mark.parametrize("prior", ["laplace", "normal"])
+def test_g1_binomial_large_eta(sd_eta, prior):
+    """G1 where the headline workload starts: a chain drawn from the prior at p = 1000 has sd(eta) ~ 45.  For y = 0 and
+    large eta R takes log(q) of q = 1 - p with p already rounded (dbinom_raw, R/glm_utils.R:45-47 + stats' logit_linkinv):
+    the engine reproduces that form (cgg_math.cuh: rform_log1p_rho), the +-30 clamps included."""
+    n, p = 200_000, 6
+    rng = np.random.default_rng(int(sd_eta))
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    X[:, 0] = 1.0
+    beta = rng.standard_normal(p) * sd_eta / np.sqrt(p)
+    y = (rng.random(n) < 0.5).astype(np.float64)          # responses unrelated to eta: every (y, sign of eta) pair occurs
+    m = oracle.make_model("binomial", **PRIOR_CASES[prior])
+    with _engine("binomial", prior, X) as e:
+        e.set_data(X, y)
+        e.init_chain(0, beta)
+        eta = oracle.init_eta(X, beta)
+        assert np.std(eta) > 0.8 * sd_eta
+        for j in (0, 2, p - 1):
+            cands = beta[j] + np.array([0.0, -0.4, 0.4, 1e-3, -2.0, 3.0, 0.05, -0.05])
+            got = e.log_potential(0, j, cands)
+            ref = oracle.log_potential(m, X, y, beta, eta, j, cands)
+            assert np.all(np.abs(got - ref) <= RTOL_G1 * np.abs(ref)), (sd_eta, j, (got - ref) / ref)
+        assert abs(e.fx(0) - oracle.log_potential(m, X, y, beta, eta, 0, [beta[0]])[0]) <= RTOL_G1 * abs(e.fx(0))
+
+
 def test_update_eta_bit_exact():
     X, y, bt = synth("poisson", 5003, 4, seed=5)
     with _engine("poisson", "normal", X) as e:
@@ -110,6 +136,61 @@ def test_g2_replay_and_philox_vs_oracle(family, prior, w, max_steps, driver):
                 assert st["uniforms_used"][c] == ref["uniforms_used"]
                 beta, eta = e.state(c)
                 assert np.max(np.abs(eta - ref["eta"])) <= 1e-9 and np.max(np.abs(beta - ref["beta"])) <= ATOL_G2
+
+
+@pytest.mark.parametrize("jet", [True, False])
+def test_g2_binomial_from_a_laplace_prior_draw(jet):
+    """G2 in the transient of the headline workload's shape: beta0 ~ laplace(0, 1) at p = 200 gives sd(eta) ~ 20, i.e.
+    thousands of rows beyond stats' +-30 logit clamp and in R's log(1 - p) rounding regime.  Samples, uniform consumption
+    and qslice's evaluation / step-out / shrink counts must be the oracle's."""
+    n, p, C, iters = 20_000, 200, 2, 3
+    X, y, _ = synth("binomial", n, p, seed=31)
+    rng = np.random.default_rng(5)
+    beta0 = rng.laplace(0.0, 1.0, (C, p))
+    m = oracle.make_model("binomial", **PRIOR_CASES["laplace"])
+    with _engine("binomial", "laplace", X, w=0.5, n_chains=C, K=8, spec_tau=0.12, seed=11, jet=jet) as e:
+        e.set_data(X, y)
+        for c in range(C):
+            e.init_chain(c, beta0[c])
+        assert np.std(e.state(0)[1]) > 12.0
+        S, st = e.run(iters)
+        ne = ns = nh = 0
+        for c in range(C):
+            ref = oracle.run_chain(m, X, y, beta0[c], w=0.5, n_iter=iters, seed=11, chain=c)
+            assert ref["rc"] == 0
+            assert np.max(np.abs(S[c] - ref["samples"])) <= ATOL_G2, c
+            assert st["uniforms_used"][c] == ref["uniforms_used"]
+            ne += ref["n_eval"]; ns += ref["n_stepout"]; nh += ref["n_shrink"]
+            beta, eta = e.state(c)
+            assert np.max(np.abs(eta - ref["eta"])) <= 1e-9 * max(1.0, np.max(np.abs(ref["eta"])))
+        assert (st["ref_evals"], st["stepouts"], st["shrinks"]) == (ne, ns, nh)
+
+
+def test_g2_cfg2_shape_full_grid_pair_passes():
+    """BASELINE configs[1] at its own size against the oracle: binomial n = 1e5, p = 100, normal prior, 4 chains.  All 147
+    worker CTAs take part (slot delivery, 5 slot rounds) and the chains run as pairs; started near the mode so that jet
+    passes (light, pair) carry the updates.  2 iterations = 800 updates; the oracle needs ~30 s of CPU."""
+    n, p, C, iters = 100_000, 100, 4, 2
+    X, y, bt = synth("binomial", n, p, seed=12)
+    rng = np.random.default_rng(6)
+    beta0 = bt + 0.02 * rng.standard_normal((C, p))
+    m = oracle.make_model("binomial", **PRIOR_CASES["normal"])
+    with _engine("binomial", "normal", X, w=0.5, n_chains=C, K=8, spec_tau=0.12, seed=3) as e:
+        e.set_data(X, y)
+        for c in range(C):
+            e.init_chain(c, beta0[c])
+        ctas, _ = e.launch_shape()
+        assert ctas >= 100                      # the full grid, not the few CTAs of the small replay tests
+        S, st = e.run(iters)
+        assert st["jet_passes"] >= 0.9 * st["updates"]
+        ne = 0
+        for c in range(C):
+            ref = oracle.run_chain(m, X, y, beta0[c], w=0.5, n_iter=iters, seed=3, chain=c)
+            assert ref["rc"] == 0
+            assert np.max(np.abs(S[c] - ref["samples"])) <= ATOL_G2, c
+            assert st["uniforms_used"][c] == ref["uniforms_used"]
+            ne += ref["n_eval"]
+        assert st["ref_evals"] == ne
 
 
 def test_chunked_runs_continue_the_chain():

@@ -24,7 +24,25 @@ def test_binomial_row_term_vs_mpmath():
     got = debug_row_terms("binomial", y, eta)
     exact = [yi * mp.mpf(float(e)) - mp.log1p(mp.exp(mp.mpf(float(e)))) for yi, e in zip(y, eta)]
     err = _ulp_err(got, exact)
-    assert err.max() <= 2.0, err.max()      # <= 2 ulp of max(|value|, 1)
+    rform = (y == 0.0) & (eta > 8.0)        # R's log(1 - p) regime: checked against the literal form below
+    assert err[~rform].max() <= 2.0, err[~rform].max()      # <= 2 ulp of max(|value|, 1)
+
+
+def test_binomial_row_term_follows_r_log_q_form():
+    """y = 0, eta > 8: R computes log(q) with q = 1 - p and p = e / (1 + e) already rounded (stats logit_linkinv +
+    nmath dbinom_raw), which differs from the smooth -softplus(eta) by up to 2^-54 (1 + e^eta): 5e-8 at eta = 20.  The
+    kernels reproduce R's value: the same double q in all but a few rows near a rounding boundary of p."""
+    import oracle
+    rng = np.random.default_rng(4)
+    eta = np.concatenate([rng.uniform(8.0, 30.0, 4000), np.linspace(8.001, 29.999, 1000)])
+    y = np.zeros(eta.size)
+    got = debug_row_terms("binomial", y, eta)
+    ref = oracle.log_density("binomial", oracle.linkinv("binomial", eta), y)
+    smooth = -(eta + np.log1p(np.exp(-eta)))
+    assert np.max(np.abs(ref - smooth)[eta > 20]) > 1e-9          # the effect is real ...
+    d = np.abs(got - ref)
+    assert np.all(d <= 2.0 ** -53 * (1.0 + np.exp(eta)) + 4 * EPS * np.abs(ref))      # ... never off by more than one grid step of p
+    assert np.mean(d <= 4 * EPS * np.abs(ref)) >= 0.995            # ... and bit-level agreement in (nearly) every row
 
 
 def test_binomial_clamps_follow_stats_logit_linkinv():

@@ -155,3 +155,25 @@ def test_replay_stream_exhaustion_is_an_error():
     m = oracle.make_model("gaussian", **PRIOR_CASES["normal"])
     out = oracle.run_chain(m, X, y, np.zeros(2), w=0.5, n_iter=10, replay_u=np.full(5, 0.5))
     assert out["rc"] == oracle.E_STREAM
+
+
+def test_r_log_q_shortcut_matches_the_literal_form():
+    """The device evaluates R's `log(q), q = 1 - p, p = fl(e / (1 + e))` (y = 0, eta in (8, 30]) as
+    -softplus(eta) + log1p(rho) with q_R = 1 - fl(1 - T / (1 + T)), T = exp(-eta) (cgg_math.cuh: rform_log1p_rho).
+    This is the same arithmetic in numpy against the oracle's literal dbinom form: the same q in all but a few rows,
+    and sums that agree to ~1e-17 relative (the smooth -softplus alone is off by 1e-9 at sd(eta) ~ 15)."""
+    rng = np.random.default_rng(0)
+    eta = rng.uniform(8.0, 30.0, 200_000)
+    y = np.zeros(eta.size)
+    lit = oracle.log_density("binomial", oracle.linkinv("binomial", eta), y)
+    T = np.exp(-eta)
+    u = 1 - T * (1 - T * (1 - T * (1 - T)))
+    qh = T * u
+    qR = 1 - (1 - qh)
+    rho = (qR - qh) * (np.exp(eta) * (1 + T))
+    mine = -(eta + np.log1p(T)) + rho * (1 - rho * (0.5 - rho / 3))
+    q_lit = 1 - oracle.linkinv("binomial", eta)
+    assert np.mean(q_lit == qR) > 0.999
+    assert np.all(np.abs(mine - lit) <= 2.0 ** -53 * (1 + np.exp(eta)) + 1e-14)
+    assert abs(mine.sum() - lit.sum()) <= 1e-15 * abs(lit.sum())
+    assert abs(-(eta + np.log1p(T)).sum() - lit.sum()) > 1e-9 * abs(lit.sum())
