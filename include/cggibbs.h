@@ -178,6 +178,11 @@ int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double 
  * fp64 one; returns max |err| / (1 + |s|), the constant its error bound relies on (pre-filter). */
 int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plus_abs_s, double *at_s);
 
+/* Diagnostic: max absolute error of the per-row quantities of a binomial LIGHT jet pass (tanh(|eta|/2), s(1-s) and their
+ * product, evaluated with a 1e-14 exp and a one-step reciprocal) against double-precision library routines over a grid of
+ * 6.7e7 values of |eta| in [0, 40); the enclosure's error bound budgets 2e-11 for it. */
+int cgg_debug_light_error(int32_t device, double *max_abs_err);
+
 /* Diagnostic: runs one jet pass of chain `chain` along column j (no state change) and evaluates its enclosure at K
  * (<= CGG_KMAX) values of new_beta_j: value[k] = surrogate log-LIKELIHOOD (per-dataset constant included, prior
  * excluded), bound[k] = the error bound the decider uses (Inf: enclosure not applicable), sums[CGG_KMAX + 2] = the

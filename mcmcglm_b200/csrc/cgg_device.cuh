@@ -103,13 +103,14 @@ struct Hdr {
     int32_t pad;
 };
 
+struct LimbAcc;
 struct Dev {
     const double *X; const double *y;
     double *eta, *beta, *shat, *samples, *xbuf;
     const double *replay;
     const double *colstat;     // [p][CS_STRIDE] per-column scale and absolute moments (jet passes)
     const double *gathered;    // row-sharded over NCCL: [world][C * NV] all-gathered per-rank sums (added in rank order by the decider)
-    double *slots;             // [C][G][NV] per-CTA partial sums of the pass in flight (persistent driver)
+    LimbAcc *lacc;             // [C][NV] limb accumulators of the pass in flight (persistent driver), see cta_deliver_limbs
     Ctl *ctl; ChainState *cs; Hdr *hdr; ChainSync *sync; Acc *acc;
     unsigned long long *prof;  // optional phase counters (CGG_PROFILE=1)
     int64_t n, p, ldx, lde, n_tiles, n_iter, iter_stop;   // iter_stop: iteration count at which this launch stops (<= n_iter)
@@ -470,6 +471,7 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
     }
     if (FAMILY != CGG_GAUSSIAN) m[9] = (risk >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
     if (FAMILY == CGG_BINOMIAL) m[8] = rform_noise_sum(risk, rows);
+    if (FAMILY == CGG_BINOMIAL && !FULL) jet_light_pack(m);
 }
 
 // One warp, TWO chains that are at the same coordinate (same column j, same pending column), one jet pass: y, X_j and
@@ -596,8 +598,10 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
         mB[9] = (riskB >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
     }
     if (FAMILY == CGG_BINOMIAL) { mA[8] = rform_noise_sum(riskA, rows); mB[8] = rform_noise_sum(riskB, rows); }
+    if (FAMILY == CGG_BINOMIAL && !FULL) { jet_light_pack(mA); jet_light_pack(mB); }
+    constexpr int NVD = (FAMILY == CGG_BINOMIAL && !FULL) ? JET_NVL : NV;      // values this pass delivers
 #pragma unroll
-    for (int k = 0; k < NV; ++k) { mA[k] = warp_sum(mA[k]); mB[k] = warp_sum(mB[k]); }
+    for (int k = 0; k < NVD; ++k) { mA[k] = warp_sum(mA[k]); mB[k] = warp_sum(mB[k]); }
 }
 
 // Two control blocks describe passes that can share one walk over the rows: both jet passes of the same kind on the
@@ -639,6 +643,7 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
             else warp_pass_jet<FAMILY, false>(d, cs, cw[2], cw[CTL_WORDS - 1], lane, tab, was_prefetched, acc);
             if (t_tiles) *t_tiles += clock64() - t0;
         }
+        const int nvd = jet_nvals(FAMILY, !(cmask & JET_FULL));
         if (const double *next_cw = la->poll(d, lane)) {
             const ChainStream ns(d, next_c, next_cw, wid, W, lane, ring);
             const long long nw0 = __double_as_longlong(next_cw[0]);
@@ -646,8 +651,8 @@ __device__ __forceinline__ int worker_pass(const Dev &d, int c, const double *cw
             if (nj >= 0 && (ns.need_yx || ns.cj >= 0)) { ns.prologue(lane); prefetched = true; }
         }
 #pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
-        return NV;
+        for (int k = 0; k < NV; ++k) if (k < nvd) acc[k] = warp_sum(acc[k]);
+        return nvd;
     }
     if (nc == 0 && cj < 0) return 0;
     float bE = 0.0f, bX = 0.0f;
@@ -801,32 +806,68 @@ __device__ __forceinline__ bool cta_deliver(const Dev &d, CtaShared &sh, int c, 
     return true;
 }
 
-// Persistent driver: the same CTA-level fold, but the CTA's sums go to the CTA's own slot of the chain as 16-byte
-// {value, stamp} pairs (stamp = number of the pass + 1), written by ONE lane with plain vector stores: no atomic, no
-// fence, nothing to wait for -- the warp moves on to its next chain at once.  The decider polls the stamps and only uses
-// a value whose own stamp is the expected one (the protocol of NCCL's low-latency paths).  With atomics on shared accumulators -- and
-// still with a release-increment of an arrival counter, whose implied membar costs microseconds under load -- the last
-// warp of every CTA fell behind, was therefore last again, and paced the whole grid.  Entry 0 is always written (an
-// idle pass delivers nothing else).  The decider adds the G slots in CTA order: reproducible.
-// Each 64-bit word of an entry validates itself: {stamp32 : value half32}.  The PTX memory model makes every element of a
-// vector access a scalar access of its own, so two words {value64, stamp64} could in principle be observed torn; a 64-bit
-// element cannot.  The stamp is the pass number + 1 (32 bits: versions restart at every launch; 0 = never written).
-struct __align__(16) SlotEntry { unsigned long long w0, w1; };      // w0 = stamp << 32 | lo32(value), w1 = stamp << 32 | hi32(value)
-__device__ __forceinline__ void slot_store(SlotEntry *dst, double v, unsigned stamp) {
-    const unsigned long long s = (unsigned long long)stamp << 32;
-    asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(s | (unsigned)__double2loint(v)), "l"(s | (unsigned)__double2hiint(v)) : "memory");
+// ---------------------------------------------------------------------------------------------
+// Persistent driver: how a pass's sums travel from the G worker CTAs to the chain's deciding warp.
+//
+// Every value of a chain has a LIMB ACCUMULATOR: four 64-bit words in global memory that only ever receive integer
+// `red.add` operations (fire-and-forget atomics: nobody waits for them).  A CTA's sum v (the fold of its warps' partials)
+// is split EXACTLY into four signed 32-bit-wide limbs v = p0 2^32 + p1 + p2 2^-32 + p3 2^-64 and the CTA adds, to word l,
+//     2^56  +  (p_l + 2^47).
+// The top 8 bits of a word therefore COUNT the CTAs that have added to it, and the low 56 bits hold the sum of their
+// payloads (each payload + 2^47 is positive and G <= 255 of them stay below 2^56: no carry into the count), so each word
+// validates itself: the decider reads the words of the values it expects with ONE load per lane, and when every count
+// field has advanced by G since the previous pass, the differences of the low fields ARE the pass's sums.  No stamps, no
+// flags, no fences, nothing is ever reset during a launch (the decider keeps the previous words; arithmetic is mod 2^64),
+// and -- integer addition being associative -- the totals do not depend on arrival order: bit-reproducible.
+// Resolution 2^-64 per contribution (absolute 147 x 2.7e-20: below one ulp of any sum the deciders use); magnitudes from
+// 2^68 on, infinities and NaN travel as marker payloads no finite sum can reach.
+// Round 1 gave every CTA its own slot per chain and value (147 x 10 stamped 16-byte entries per chain): the decider then
+// needed ~50 dependent-on-nothing-but-still-slow loads per lane and spent 16 of its 27 us per decision reading them.
+struct __align__(128) LimbAcc { unsigned long long w[4]; unsigned long long pad[12]; };    // one value: one L2 line
+constexpr int LIMB_OFFSET_LOG2 = 47;
+constexpr long long LIMB_MARK = 1LL << 45;     // marker payloads: limb 0 -MARK: a -Inf term; limb 1 +MARK: +Inf / out of range; limb 2 +MARK: NaN
+__device__ __forceinline__ void limbs_split(double v, long long (&p)[4]) {
+    if (!(fabs(v) < 2.9514790517935283e20 /* 2^68 */)) {
+        p[0] = (v < 0.0) ? -LIMB_MARK : 0; p[1] = (v > 0.0) ? LIMB_MARK : 0; p[2] = (v != v) ? LIMB_MARK : 0; p[3] = 0;
+        return;
+    }
+    const double h0 = trunc(v * 2.3283064365386963e-10 /* 2^-32 */);      // |h0| < 2^36
+    double r = fma(-h0, 4294967296.0, v);                                   // exact: the low part of v, |r| < 2^32
+    const double h1 = trunc(r);
+    r -= h1;                                                                // exact, |r| < 1
+    const double h2 = trunc(r * 4294967296.0);
+    r = fma(-h2, 2.3283064365386963e-10, r);                                // exact, |r| < 2^-32
+    p[0] = (long long)h0; p[1] = (long long)h1; p[2] = (long long)h2; p[3] = (long long)rint(r * 18446744073709551616.0 /* 2^64 */);
 }
-__device__ __forceinline__ bool slot_load(const SlotEntry *src, unsigned stamp, double &v) {
-    unsigned long long w0, w1;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-    v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
-    return (unsigned)(w0 >> 32) == stamp && (unsigned)(w1 >> 32) == stamp;
+__device__ __forceinline__ void limbs_add(LimbAcc *a, double v) {
+    long long p[4];
+    limbs_split(v, p);
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        atomicAdd(&a->w[l], (1ULL << 56) + (unsigned long long)(p[l] + (1LL << LIMB_OFFSET_LOG2)));     // result unused: RED
 }
-__device__ __forceinline__ bool slot_stamped(const SlotEntry *src, unsigned stamp) {
-    return (unsigned)(__ldcg(&src->w0) >> 32) == stamp;
+// The sum of the G contributions a limb pair received since `prev`: lane-local decoding of two words.
+// ok: both count fields advanced by exactly G.  half 0: p0 2^32 + p1, half 1: p2 2^-32 + p3 2^-64; flags: 1 -Inf, 4 +Inf, 2 NaN.
+__device__ __forceinline__ double limbs_decode_half(unsigned long long w0, unsigned long long w1, unsigned long long prev0, unsigned long long prev1,
+                                                    int G, int half, bool &ok, unsigned &flags) {
+    const unsigned long long d0 = w0 - prev0, d1 = w1 - prev1;
+    ok = (int)(d0 >> 56) == G && (int)(d1 >> 56) == G;
+    const long long bias = (long long)G << LIMB_OFFSET_LOG2;
+    const long long s0 = (long long)(d0 & ((1ULL << 56) - 1)) - bias, s1 = (long long)(d1 & ((1ULL << 56) - 1)) - bias;
+    flags = 0;
+    if (half == 0) {
+        if (s0 < -(LIMB_MARK >> 1)) flags |= 1u;
+        if (s1 > (LIMB_MARK >> 1)) flags |= 4u;
+        return fma((double)s0, 4294967296.0, (double)s1);
+    }
+    if (s0 > (LIMB_MARK >> 1)) flags |= 2u;
+    return fma((double)s0, 2.3283064365386963e-10, (double)s1 * 5.421010862427522e-20);
 }
-__device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers,
-                                                  unsigned long long stamp, const double (&acc)[NV]) {
+
+// Worker side: fold the CTA's warp partials (last warp to arrive, fixed order) and add the CTA's sums to the chain's limb
+// accumulators.  Value 0 is always delivered (an idle or commit-only pass delivers nothing else): it is the arrival signal.
+__device__ __forceinline__ void cta_deliver_limbs(const Dev &d, CtaShared &sh, int c, int nc, int warp, int lane, int nworkers,
+                                                  const double (&acc)[NV]) {
     // Shared-memory hand-over without a MEMBAR: the partials are written with volatile stores and the counter is bumped by
     // the same thread afterwards; shared-memory operations of a thread are performed in program order by the SM's
     // one shared-memory pipe, and the reader's loads depend on the value its own atomic returned.  (A __threadfence_block()
@@ -853,77 +894,37 @@ __device__ __forceinline__ void cta_deliver_slots(const Dev &d, CtaShared &sh, i
     }
     v = (v + __shfl_down_sync(0xffffffffu, v, NV)) + __shfl_down_sync(0xffffffffu, v, 2 * NV);   // valid in lanes < NV
     if (lane == 0) sh.cnt[c] = 0;
-    if (lane < NV && (lane < nc || lane == 0))
-        slot_store(reinterpret_cast<SlotEntry *>(d.slots) + ((size_t)c * d.G + blockIdx.x) * NV + lane, v, (unsigned)stamp);
+    if (lane < NV && (lane < nc || lane == 0)) limbs_add(d.lacc + (size_t)c * NV + lane, v);
     __syncwarp();
 }
 
-// Decider side: has every CTA delivered pass `stamp - 1` of chain c?  (entry 0 of each slot; the other entries are
-// validated when they are read)
-constexpr int SLOT_ROUNDS = 5;     // 32 * 5 = 160 >= worker CTAs of a B200: the decider's loads are all issued before any is used
-__device__ __forceinline__ bool slots_arrived(const Dev &d, int c, unsigned long long stamp64, int lane) {
-    const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
-    const unsigned stamp = (unsigned)stamp64;
-    bool ok = true;
-    if (d.G <= 32 * SLOT_ROUNDS) {
-        // a light first look (one load per lane): the deciders share an SM, and a warp that polls with everything it has
-        // slows down the warps that are deciding
-        const bool ok0 = (lane < d.G) ? slot_stamped(base + (size_t)lane * NV, stamp) : true;
-        if (!__all_sync(0xffffffffu, ok0)) return false;
-        unsigned long long st[SLOT_ROUNDS];
-#pragma unroll
-        for (int r = 1; r < SLOT_ROUNDS; ++r) { const int g = lane + 32 * r; st[r] = (g < d.G) ? __ldcg(&base[(size_t)g * NV].w0) : stamp64 << 32; }
-#pragma unroll
-        for (int r = 1; r < SLOT_ROUNDS; ++r) ok = ok && ((unsigned)(st[r] >> 32) == stamp);
-    } else {
-        for (int g = lane; g < d.G; g += 32) ok = ok && slot_stamped(base + (size_t)g * NV, stamp);
+// Decider side: one load per lane (lanes 2k, 2k + 1: the two limb pairs of value k) fetches everything chain c's pass
+// delivered; true when all `nvals` expected values are complete, out[k] then holds them (identical in every lane) and
+// `prev` (the deciding warp's copy of the words, in shared memory) has moved on.  NaN / +-Inf markers become those values.
+__device__ __forceinline__ bool limbs_take(const Dev &d, int c, int nvals, int lane, unsigned long long *prev /* [NV][4] */, double (&out)[NV]) {
+    static_assert(2 * NV <= 32, "two lanes per value");
+    const int k = lane >> 1, half = lane & 1;
+    const bool mine = k < (nvals < 1 ? 1 : nvals);
+    unsigned long long w0 = 0, w1 = 0;
+    if (mine) {
+        const unsigned long long *src = d.lacc[(size_t)c * NV + k].w + 2 * half;
+        asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
     }
-    return __all_sync(0xffffffffu, ok);
-}
-
-// Value k of chain c's finished pass = the G slots added in CTA order (lane l takes CTAs l, l + 32, ..., then a
-// butterfly: the same bits in every lane and on every run).  Returns false if some entry does not carry the stamp yet.
-__device__ __forceinline__ bool slots_sum(const Dev &d, int c, int nvals, unsigned long long stamp64, int lane, double (&out)[NV]) {
-    const SlotEntry *base = reinterpret_cast<const SlotEntry *>(d.slots) + (size_t)c * d.G * NV;
-    const unsigned stamp = (unsigned)stamp64;
-    double part[NV];
+    bool ok = true; unsigned fl = 0; double part = 0.0;
+    if (mine) part = limbs_decode_half(w0, w1, prev[k * 4 + 2 * half], prev[k * 4 + 2 * half + 1], d.G, half, ok, fl);
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    if (mine) { prev[k * 4 + 2 * half] = w0; prev[k * 4 + 2 * half + 1] = w1; }
+    const double other = __shfl_xor_sync(0xffffffffu, part, 1);
+    fl |= __shfl_xor_sync(0xffffffffu, fl, 1);
+    double v = half ? other + part : part + other;         // hi + lo in both lanes
+    if (fl & 2u) v = NAN;
+    else if ((fl & 1u) && (fl & 4u)) v = NAN;
+    else if (fl & 1u) v = -INFINITY;
+    else if (fl & 4u) v = INFINITY;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) part[k] = 0.0;
-    bool ok = true;
-    if (d.G <= 32 * SLOT_ROUNDS) {
-        // five values at a time: their 5 x SLOT_ROUNDS loads are independent and all issued before the first add, so the
-        // decider pays two round trips to L2 instead of one per value (the decision is on every chain's critical cycle)
-        constexpr int KB = 5;
-        static_assert(NV % KB == 0, "values are read in batches of five");
-#pragma unroll
-        for (int k0 = 0; k0 < NV; k0 += KB) {
-            if (k0 < nvals) {
-                double t[KB][SLOT_ROUNDS];
-                bool tk[KB][SLOT_ROUNDS];
-#pragma unroll
-                for (int kk = 0; kk < KB; ++kk)
-#pragma unroll
-                    for (int r = 0; r < SLOT_ROUNDS; ++r) {
-                        const int g = lane + 32 * r;
-                        t[kk][r] = 0.0; tk[kk][r] = true;
-                        if (g < d.G && k0 + kk < nvals) tk[kk][r] = slot_load(base + (size_t)g * NV + k0 + kk, stamp, t[kk][r]);
-                    }
-#pragma unroll
-                for (int kk = 0; kk < KB; ++kk)
-#pragma unroll
-                    for (int r = 0; r < SLOT_ROUNDS; ++r) { part[k0 + kk] += t[kk][r]; ok = ok && tk[kk][r]; }
-            }
-        }
-    } else {
-        for (int g = lane; g < d.G; g += 32) {
-#pragma unroll
-            for (int k = 0; k < NV; ++k)
-                if (k < nvals) { double v; ok = slot_load(base + (size_t)g * NV + k, stamp, v) && ok; part[k] += v; }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) out[k] = (k < nvals) ? warp_sum(part[k]) : 0.0;
-    return __all_sync(0xffffffffu, ok);
+    for (int q = 0; q < NV; ++q) { const double t = __shfl_sync(0xffffffffu, v, 2 * q); out[q] = (q < nvals) ? t : 0.0; }
+    __syncwarp();
+    return true;
 }
 
 // What the deciding warp of the persistent driver keeps in its CTA's shared memory between two decisions of a chain, so
@@ -937,6 +938,7 @@ struct DeciderCache {
     double beta_j, shat_j, beta_n, shat_n, cscale_n;
     int32_t pref_j;             // column the prefetched values belong to (-1: none)
     int32_t valid;              // s / ct hold the chain's current state
+    unsigned long long prev[NV * 4];   // the chain's limb-accumulator words as of its last decided pass (limbs_take)
 };
 __device__ __forceinline__ void decider_prefetch(const Dev &d, int c, DeciderCache *dc, int lane) {
     const int jq = dc->ct.j;
@@ -1200,7 +1202,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     // verdict on candidate v; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
     auto verdict = [&](double v, bool &in, bool &out, double &fnew) {
         double B;
-        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B);
+        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B, light);
         B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
         if (light) {
             const double t = dl + (prior_logdens(d.prior, v) - prior_x0);
@@ -1305,8 +1307,7 @@ __device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
     return v;
 }
 enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
-__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, unsigned long long stamp = 0,
-                                         DeciderCache *dc = nullptr) {
+__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, DeciderCache *dc = nullptr) {
     const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
     // ---- control block, state, beta/shat of j and j+1: from the deciding warp's shared-memory cache if it has them,
@@ -1331,13 +1332,14 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     const unsigned cmask = jetpass ? 0u : (unsigned)ct.coarse_mask;
     double jm[NV];        // the pass's sums, identical in every lane (slots source: all of them; else only for a jet pass)
     if (src == SRC_SLOTS) {
-        const int nvals = jetpass ? NV : (cmask ? nc + 2 : nc);
-        if (!slots_sum(d, c, nvals, stamp, lane, jm)) return DEC_NOT_READY;      // some value is still on its way: nothing was changed
+        const int nvals = jetpass ? jet_nvals(d.family, ((unsigned)ct.coarse_mask & JET_FULL) == 0u) : (cmask ? nc + 2 : nc);
+        if (!limbs_take(d, c, nvals, lane, dc->prev, jm)) return DEC_NOT_READY;  // some CTA's sums are still on their way: nothing was changed
     } else if (jetpass) {
         const double mv = (lane < NV) ? (from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
 #pragma unroll
         for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
     }
+    if (jetpass && d.family == CGG_BINOMIAL && ((unsigned)ct.coarse_mask & JET_FULL) == 0u) jet_light_unpack(jm);
     if (s.x0 != s.x0) tick = 0;   // (keeps the state loads above the first timestamp)
     CGG_TICK(12);      // state loaded, sums read
     // lane k: total log-likelihood of candidate k + its prior term

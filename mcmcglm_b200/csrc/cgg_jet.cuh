@@ -34,6 +34,10 @@ constexpr int CS_STRIDE = 12;              // per-column statistics: {cs, 1/cs, 
 constexpr double JET_AMAX = 8.0;           // the enclosure is only used for |h| <= JET_AMAX (binomial, poisson)
 constexpr double JET_EPS = 1.1102230246251565e-16;   // 2^-53
 constexpr double JET_CROUND = 256.0;       // rounding allowance of one accumulated moment, in units of eps * sum|terms|
+constexpr int JET_DL = 3;                  // order of the binomial LIGHT pass
+constexpr double JET_LIGHT_EPS = 2e-11;    // absolute error of sigmoid-derived quantities (ua, v, v ua) in a light pass: the reciprocal
+                                           // seed is taken from the high word of 1 + T (>= 2^-19.5 relative), one Newton step squares it;
+                                           // measured by cgg_debug_light_error (tests/test_gpu_jet.py asserts <= half of this)
 
 // sup_t |softplus^(k)(t)|, k = 1..8, rounded up (tools/gen_math_tables.py prints them; polynomial in sigmoid)
 __device__ __constant__ double JET_G[9] = {0.0, 1.0, 0.25, 0.0962250449, 0.125, 0.127683922, 0.25, 0.408327759, 1.0625};
@@ -84,8 +88,41 @@ template <> struct JetRow<CGG_BINOMIAL> {
     // FULL: also the exact M_0 term (softplus through the log1p table, stats' clamp).  Light passes skip it: the slice
     // decisions only involve differences f(v) - f(x0), in which M_0 cancels; 1/(1+T) then comes from the hardware
     // reciprocal seed (rcp.approx.ftz.f64, 2^-23) and two Newton steps instead of the table split.
+    // LIGHT passes (the product path in the stationary regime): order JET_DL = 3 and every per-row quantity only to
+    // JET_LIGHT_EPS absolute -- the approximation errors enter the enclosure's bound (jet_eval), which stays ~1e-7 against
+    // slice margins of O(1), and a test the looser enclosure cannot decide is repeated as a FULL pass (order CGG_JET_D,
+    // 1-ulp routines, exact M_0).  exp(-a) = 2^(K/64) e^r: K = rint(-a 64/ln2), one-constant reduction, 64-entry table in
+    // shared memory, degree-4 polynomial on |r| <= ln2/128 (1.8e-14 relative, tools/gen_math_tables.py); 1/(1+T) from the
+    // hardware seed and ONE Newton step.  20 fp64 instructions per row (FULL: ~60; round 1's light pass: 40).
+    static __device__ __forceinline__ void add_light(double e, double xs, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
+        const double SHIFT = 6755399441055744.0;
+        const int he = __double2hiint(e);
+        risk = max(risk, (unsigned)he & 0x7fffffffu);
+        const double a = fabs(e);
+        const double kd = fma(-a, 9.2332482616893656e+01 /* 64 / ln2 */, SHIFT);
+        const double r = fma(kd - SHIFT, -1.0830424696249145e-02 /* ln2 / 64 */, -a);
+        double p = fma(EX64_C[4], r, EX64_C[3]);
+        p = fma(p, r, EX64_C[2]);
+        p = fma(p, r, 1.0);
+        p = fma(p, r, 1.0);
+        const int K = __double2loint(kd);      // <= 0; meaningless for |eta| >~ 1e7, far beyond the risk key: T and the sums may then
+                                               // be anything, NaN included -- the pass is flagged (m[9]) and its sums are not used
+        const double T = scale2(ex64_table(tab)[K & (EX64_N - 1)] * p, K >> 6);   // exp(-a)
+        const double dd = 1.0 + T;                                           // in (1, 2]
+        double rr;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(dd));
+        rr = fma(rr, fma(-dd, rr, 1.0), rr);                                 // sigmoid(a)
+        const double v = fma(-rr, rr, rr);
+        const double ua = fma(2.0, rr, -1.0);
+        const double xh = __hiloint2double(__double2hiint(xs) ^ (he & 0x80000000), __double2loint(xs));
+        const double x2 = xh * xh;
+        m[1] = fma(xh, ua, m[1]);
+        m[2] = fma(x2, v, m[2]);
+        m[3] = fma(x2 * xh, v * ua, m[3]);
+    }
     template <bool FULL>
     static __device__ __forceinline__ void add1(double y, double e, double xs, double, const double2 *tab, double (&m)[JET_NV], unsigned &risk) {
+        if (!FULL) { add_light(e, xs, tab, m, risk); return; }
         const double SHIFT = 6755399441055744.0;
         const int he = __double2hiint(e);
         risk = max(risk, (unsigned)he & 0x7fffffffu);                       // max |eta| (high word): checked against 21.9 at the end
@@ -185,6 +222,16 @@ template <> struct JetRow<CGG_POISSON> {
     }
 };
 
+// A binomial LIGHT pass delivers five values, compactly: m1, m2, m3, the noise sum (canonical slot 8), the risk-row count
+// (canonical slot 9).  pack: canonical -> compact (worker, before the reduction); unpack: compact -> canonical (decider).
+constexpr int JET_NVL = 5;
+__device__ __forceinline__ int jet_nvals(int family, bool light) { return (family == CGG_BINOMIAL && light) ? JET_NVL : JET_NV; }
+__device__ __forceinline__ void jet_light_pack(double (&m)[JET_NV]) { m[0] = m[1]; m[1] = m[2]; m[2] = m[3]; m[3] = m[8]; m[4] = m[9]; }
+__device__ __forceinline__ void jet_light_unpack(double (&m)[JET_NV]) {
+    m[9] = m[4]; m[8] = m[3]; m[3] = m[2]; m[2] = m[1]; m[1] = m[0];
+    m[0] = 0.0; m[4] = 0.0; m[5] = 0.0; m[6] = 0.0; m[7] = 0.0;
+}
+
 // Upper bound of sum_i e^|eta_i| over the `rows` rows a lane scored, from the running maximum of the high words of
 // |eta_i| (JetRow<CGG_BINOMIAL>'s risk key): rows * e^amax, amax rounded up, ex2.approx (2^-22) and the fp32 roundings
 // covered by the factor 1.001.  Overflow gives +Inf and a NaN key NaN: the enclosure then decides nothing.
@@ -203,7 +250,7 @@ __device__ __forceinline__ double rform_noise_sum(unsigned risk_key, unsigned ro
 // two exact evaluations.  B is +Inf (or NaN) when the enclosure does not apply: the caller must treat any comparison
 // that is not strictly decided as undecided.
 __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV], const double *cst, double n, double inv_sd,
-                                           double delta, double fmag, double &B) {
+                                           double delta, double fmag, double &B, bool light = false) {
     const double h = delta * cst[1];
     const double a = fabs(h);
     const double ce = JET_CROUND * JET_EPS;
@@ -217,18 +264,22 @@ __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV]
         return dl;
     }
     if (family == CGG_BINOMIAL) {
-        constexpr int D = CGG_JET_D;
+        constexpr int DF = CGG_JET_D;
+        static_assert((DF & 1) && (JET_DL & 1) && JET_DL <= DF, "odd orders: the top moment enters with a + sign");
+        const int D = light ? JET_DL : DF;
         // signed moments from the positive-form sums: M_1 = C1 - m1/2, M_k = (-1)^(k+1) m_k
-        double f = m[D] * JET_IFACT[D];                       // D odd: + sign
+        double f = 0.0;
 #pragma unroll
-        for (int k = D - 1; k >= 2; --k) f = fma(f, h, ((k & 1) ? m[k] : -m[k]) * JET_IFACT[k]);
+        for (int k = DF; k >= 2; --k) if (k <= D) f = fma(f, h, ((k & 1) ? m[k] : -m[k]) * JET_IFACT[k]);
         f = fma(f, h, fma(-0.5, m[1], cst[11]));
         const double dl = f * h;
-        // remainder: G_(D+1) S_(D+1) a^(D+1) / (D+1)!;  moment k: rounding <= ce G_k S_k (terms are bounded by |xs|^k G_k)
-        double pw = a, bmom = 0.0;
+        // remainder: G_(D+1) S_(D+1) a^(D+1) / (D+1)!;  moment k: rounding <= ce G_k S_k (terms are bounded by |xs|^k G_k);
+        // light passes: + the approximation error of the row quantities, JET_LIGHT_EPS |xs|^k per term
+        double pw = a, bmom = 0.0, bapx = 0.0;
 #pragma unroll
-        for (int k = 1; k <= D; ++k) { bmom = fma(JET_G[k] * JET_IFACT[k] * cst[1 + k], pw, bmom); pw *= a; }
-        const double bt = JET_G[D + 1] * JET_IFACT[D + 1] * cst[2 + D] * pw;
+        for (int k = 1; k <= DF; ++k) if (k <= D) { bmom = fma(JET_G[k] * JET_IFACT[k] * cst[1 + k], pw, bmom); bapx = fma(JET_IFACT[k] * cst[1 + k], pw, bapx); pw *= a; }
+        double bt = JET_G[DF + 1] * JET_IFACT[DF + 1] * cst[2 + DF] * pw;
+        if (light) bt = JET_G[JET_DL + 1] * JET_IFACT[JET_DL + 1] * cst[2 + JET_DL] * pw + JET_LIGHT_EPS * bapx;
         // exact passes: |l'| <= 1, so the rounding of t costs <= eps (|eta| + 2 |x delta|) with every |eta| < 21.9 (else
         // m[9] != 0); softplus and sums relative to |f|, for both evaluations
         const double bex = JET_EPS * (21.9 * n + 2.0 * a * cst[2]) + ce * (2.0 * fmag + fabs(dl) + bt);

@@ -194,10 +194,14 @@ __device__ __forceinline__ double row_term(double y, double eta, double inv_sd, 
     return (mu > 1.7976931348623157e308) ? -INFINITY : fma(y, le, -mu);
 }
 
-// Cooperative copy of the log1p split table into shared memory (call from every thread, then sync).
+// Cooperative copy of the math tables into shared memory (call from every thread, then sync): the log1p split table
+// (L1P_N + 1 double2 entries) followed by the 64 doubles 2^(j/64) of the light jet pass's exp (cgg_jet.cuh).
+constexpr int MATH_TAB_N = L1P_N + 1 + EX64_N / 2;
 __device__ __forceinline__ void load_l1p_table(double2 *dst) {
     for (int i = threadIdx.x; i <= L1P_N; i += blockDim.x) dst[i] = make_double2(L1P_TAB[2 * i], L1P_TAB[2 * i + 1]);
+    for (int i = threadIdx.x; i < EX64_N / 2; i += blockDim.x) dst[L1P_N + 1 + i] = make_double2(EX64_TAB[2 * i], EX64_TAB[2 * i + 1]);
 }
+__device__ __forceinline__ const double *ex64_table(const double2 *tab) { return reinterpret_cast<const double *>(tab + L1P_N + 1); }
 
 struct PriorParams {
     int kind;

@@ -44,7 +44,10 @@ __device__ __forceinline__ bool wait_timed_out(const Dev &d, unsigned long long 
 // carries the stamp of the pass in flight, decide and publish; then fetch what the chain's next decision will need.
 __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int stride, int lane, DeciderCache *cache) {
     const Dev &d = *dp;
-    for (int c = first_chain; c < d.C; c += stride) { if (lane == 0) { cache[c].valid = 0; cache[c].pref_j = -1; } }
+    for (int c = first_chain; c < d.C; c += stride) {
+        if (lane == 0) { cache[c].valid = 0; cache[c].pref_j = -1; }
+        for (int i = lane; i < NV * 4; i += 32) cache[c].prev[i] = 0ULL;      // the accumulators are zeroed before every launch
+    }
     __syncwarp();
     unsigned long long t0 = globaltimer_ns();
     unsigned idle = 0;
@@ -56,11 +59,10 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             v = __shfl_sync(0xffffffffu, v, 0);
             if (v >= VERSION_FINISHED) continue;
             all_fin = false;
-            if (!slots_arrived(d, c, v + 1, lane)) continue;       // pass #v still has CTAs streaming
             const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
             const long long td0 = d.prof ? clock64() : 0;
-            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, v + 1, cache + c);
-            if (oc == DEC_NOT_READY) continue;
+            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c);     // reads the limb accumulators itself: one load per lane
+            if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
             const bool fin = oc == DEC_FINISHED;
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
             if (!fin) decider_prefetch(d, c, cache + c, lane);       // after publishing: off the chain's critical path
@@ -82,7 +84,7 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
 template <int FAMILY>
 __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __grid_constant__ Dev d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double2 s_l1p[L1P_N + 1];
+    __shared__ double2 s_l1p[MATH_TAB_N];
     CtaShared sh(smem_raw, d.C);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (__ldcg(&d.hdr->abort)) return;        // an earlier launch of this run gave up
@@ -188,8 +190,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 n_pref += pair_prefetched ? 1 : 0;
                 long long tC = prof ? clock64() : 0;
                 t_rows += tC - tB; t_tiles += tC - tB;
-                cta_deliver_slots(d, sh, c, NV, warp, lane, nworkers, round + 1, acc);
-                cta_deliver_slots(d, sh, c + 1, NV, warp, lane, nworkers, round + 1, acc2);
+                const int nvd = jet_nvals(FAMILY, !full);
+                cta_deliver_limbs(d, sh, c, nvd, warp, lane, nworkers, acc);
+                cta_deliver_limbs(d, sh, c + 1, nvd, warp, lane, nworkers, acc2);
                 if (prof) t_arrive += clock64() - tC;
                 ++c;
                 continue;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
-            cta_deliver_slots(d, sh, c, nc, warp, lane, nworkers, round + 1, acc);
+            cta_deliver_limbs(d, sh, c, nc, warp, lane, nworkers, acc);
             if (prof && lane == 0 && round == 60 && c == 0)
                 d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
             if (prof && lane == 0 && round < 128) {     // arrival spread of the warps for pass #round of chain c
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaShared sh(smem_raw, d.C);
     __shared__ int s_flag;
-    __shared__ double2 s_l1p[L1P_N + 1];
+    __shared__ double2 s_l1p[MATH_TAB_N];
     if (d.hdr->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_l1p_table(s_l1p);
@@ -275,9 +278,12 @@ __global__ void __launch_bounds__(THREADS, 1) pass_kernel(const __grid_constant_
     for (int c = warp; c < d.C; c += NWARPS) {
         if (mode == 0) decide_chain(&d, c, lane, -1, SRC_ACC);
         else {
-            const bool jet = ((unsigned)d.ctl[c].coarse_mask & JET_BIT) != 0u;
-            const int nc = jet ? NV : d.ctl[c].ncand;
-            if (lane < NV) d.xbuf[c * NV + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + ((jet && !(d.sharded && lane == 0)) ? 0.0 : d.ll_const) : 0.0;
+            const unsigned cm = (unsigned)d.ctl[c].coarse_mask;
+            const bool jet = (cm & JET_BIT) != 0u, full = (cm & JET_FULL) != 0u;
+            const int nc = jet ? jet_nvals(d.family, !full) : d.ctl[c].ncand;
+            // the additive constant goes with every candidate sum and, row-sharded, with the M_0 of a full jet pass (value 0)
+            const bool with_const = !jet || (d.sharded && lane == 0 && (full || d.family != CGG_BINOMIAL));
+            if (lane < NV) d.xbuf[c * NV + lane] = (lane < nc) ? acc_take(d.acc + c * NV + lane) + (with_const ? d.ll_const : 0.0) : 0.0;
         }
     }
     __syncthreads();
@@ -359,7 +365,7 @@ __global__ void __launch_bounds__(THREADS) axpy_eta_kernel(Dev d, int c, int64_t
 
 // Diagnostic: the per-row log-density term (without the per-dataset constant) of each (y_i, eta_i).
 __global__ void row_terms_kernel(int family, int64_t n, const double *y, const double *eta, double inv_sd, double *out) {
-    __shared__ double2 s_l1p[L1P_N + 1];
+    __shared__ double2 s_l1p[MATH_TAB_N];
     load_l1p_table(s_l1p);
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -376,7 +382,7 @@ __global__ void row_terms_kernel(int family, int64_t n, const double *y, const d
 // Diagnostic: max over ALL fp32 s with |s| <= 37 of |softplus32(s) - softplus(s)| / (1 + |s|), the constant the
 // coarse pre-filter's error bound is built on.  out[0] = that maximum, out[1] = the s where it occurs.
 __global__ void coarse_error_scan_kernel(double *out, unsigned long long *out_bits) {
-    __shared__ double2 s_l1p[L1P_N + 1];
+    __shared__ double2 s_l1p[MATH_TAB_N];
     load_l1p_table(s_l1p);
     __syncthreads();
     double worst = 0.0;
@@ -405,6 +411,35 @@ __global__ void coarse_error_scan_kernel(double *out, unsigned long long *out_bi
     if (threadIdx.x == 0) {
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) if (s_w[i] > worst) { worst = s_w[i]; worst_bits = s_b[i]; }
         out[blockIdx.x] = worst; out_bits[blockIdx.x] = worst_bits;
+    }
+}
+
+// Diagnostic: max absolute error of the binomial LIGHT jet row's quantities (ua = tanh(a/2), v = s(1-s), v ua) against
+// libdevice over a grid of a = |eta| in [0, 40): the constant JET_LIGHT_EPS (cgg_jet.cuh) has to cover it.
+__global__ void light_error_scan_kernel(double *out, int per_thread) {
+    __shared__ double2 s_l1p[MATH_TAB_N];
+    __shared__ double s_w[32];
+    load_l1p_table(s_l1p);
+    __syncthreads();
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    double worst = 0.0;
+    for (int i = 0; i < per_thread; ++i) {
+        const double a = 40.0 * ((double)(tid + (long long)i * nthr) + 0.37) / (double)(nthr * per_thread);
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            double m[NV] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            unsigned risk = 0;
+            JetRow<CGG_BINOMIAL>::add_light(sgn ? -a : a, 1.0, s_l1p, m, risk);
+            const double sg = 1.0 / (1.0 + exp(-a)), ua = 2.0 * sg - 1.0, v = sg * (1.0 - sg);
+            const double xh = sgn ? -1.0 : 1.0;        // xh = sign(eta) xs: m1 = xh ua, m2 = v, m3 = xh v ua
+            worst = fmax(worst, fmax(fabs(m[1] - xh * ua), fmax(fabs(m[2] - v), fabs(m[3] - xh * v * ua))));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = worst;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) worst = fmax(worst, s_w[i]);
+        out[blockIdx.x] = worst;
     }
 }
 
@@ -550,11 +585,12 @@ __global__ void jet_debug_kernel(Dev d, int c, int j, int K, int light, double f
     const double mv = (lane < NV) ? d.xbuf[c * NV + lane] : 0.0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) m[k] = __shfl_sync(0xffffffffu, mv, k);
+    if (light && d.family == CGG_BINOMIAL) jet_light_unpack(m);
     const double x0 = d.beta[(int64_t)c * d.p + j];
     if (lane < K) {
         double B;
         const double fmag = light ? fmag_light : fabs(m[0]);
-        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, d.n_total, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B);
+        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, d.n_total, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B, light != 0);
         out[lane] = light ? dl : (m[0] + dl) + (d.sharded ? 0.0 : d.ll_const);
         out[K + lane] = B * d.jet_bscale + 8.0 * JET_EPS * (fmag + fabs(dl));
     }
@@ -772,6 +808,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     const int64_t gmax = h->max_grid - (cfg->driver == CGG_DRIVER_PERSISTENT ? 1 : 0);   // persistent driver: one more CTA hosts the deciders
     if (gmax < 1) { delete h; return fail(CGG_E_CUDA, "cgg_create: the device cannot co-schedule a worker CTA and the decider CTA"); }
     if (G > gmax) G = gmax;
+    if (G > 250) G = 250;      // the limb accumulators count arrivals in 8 bits (cgg_device.cuh: LimbAcc)
     if (G < 1) G = 1;
     d.G = (int)G;
     d.lde = (d.n + 31) / 32 * 32;
@@ -786,7 +823,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (e == cudaSuccess) e = A((void **)&d.acc, sizeof(Acc) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.sync, sizeof(ChainSync) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.xbuf, sizeof(double) * (size_t)C * NV);
-    if (e == cudaSuccess) e = A((void **)&d.slots, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G);
+    if (e == cudaSuccess) e = A((void **)&d.lacc, sizeof(LimbAcc) * (size_t)C * NV);
     if (e == cudaSuccess) e = A((void **)&d.ctl, sizeof(Ctl) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.cs, sizeof(ChainState) * (size_t)C);
     if (e == cudaSuccess) e = A((void **)&d.hdr, sizeof(Hdr));
@@ -823,7 +860,7 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     Dev &d = h->d;
     if (h->stream) {
-        void *pool_owned[] = {d.eta, d.beta, d.shat, d.acc, d.sync, d.xbuf, d.ctl, d.cs, d.hdr, d.slots, h->scratch_dev, h->colstat_dev,
+        void *pool_owned[] = {d.eta, d.beta, d.shat, d.acc, d.sync, d.xbuf, d.ctl, d.cs, d.hdr, d.lacc, h->scratch_dev, h->colstat_dev,
                               h->replay_dev, h->samples_dev};
         for (void *q : pool_owned) if (q) cudaFreeAsync(q, h->stream);
     }
@@ -1124,6 +1161,23 @@ extern "C" int cgg_debug_coarse_error(int32_t device, double *max_err_over_1_plu
     return CGG_OK;
 }
 
+extern "C" int cgg_debug_light_error(int32_t device, double *max_abs_err) {
+    if (!max_abs_err) return fail(CGG_E_ARG, "cgg_debug_light_error: NULL output");
+    CK(cudaSetDevice(device));
+    const int G = 1024;
+    double *dv = nullptr;
+    CK(cudaMalloc((void **)&dv, sizeof(double) * G));
+    light_error_scan_kernel<<<G, 256>>>(dv, 256);            // 6.7e7 grid points
+    std::vector<double> hv(G);
+    cudaError_t e = cudaMemcpy(hv.data(), dv, sizeof(double) * G, cudaMemcpyDeviceToHost);
+    cudaFree(dv);
+    CK(e);
+    double w = 0.0;
+    for (int i = 0; i < G; ++i) w = (hv[i] > w || hv[i] != hv[i]) ? hv[i] : w;
+    *max_abs_err = w;
+    return CGG_OK;
+}
+
 extern "C" int cgg_debug_jet(cgg_handle *h, int32_t chain, int64_t j, int32_t K, int32_t light, const double *cand_host,
                              double *value_host, double *bound_host, double *sums_host) {
     int rc = check_chain(h, chain, "cgg_debug_jet", true);
@@ -1272,7 +1326,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemcpyAsync(d.hdr, &hdr, sizeof hdr, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * NV, h->stream));
     CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
-    CK(cudaMemsetAsync(d.slots, 0, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G, h->stream));   // stamps restart with the versions
+    CK(cudaMemsetAsync(d.lacc, 0, sizeof(LimbAcc) * (size_t)C * NV, h->stream));   // counts restart with the versions
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
     if (want_prof) {
         if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 8 * (32 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128)));
@@ -1299,7 +1353,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
             if (done > 0) {
                 rearm_kernel<<<1, 32, 0, h->stream>>>(d);
                 CK(cudaGetLastError());
-                CK(cudaMemsetAsync(d.slots, 0, sizeof(SlotEntry) * (size_t)C * NV * (size_t)d.G, h->stream));
+                CK(cudaMemsetAsync(d.lacc, 0, sizeof(LimbAcc) * (size_t)C * NV, h->stream));
             }
             Dev dd = d;
             dd.iter_stop = std::min(done + chunk, n_iter);

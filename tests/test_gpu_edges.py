@@ -127,18 +127,27 @@ def test_pair_single_handover_stress_keeps_eta_ownership(monkeypatch):
     X, y, bt = synth("binomial", n, p, seed=23)
     beta0 = bt + 0.01 * np.random.default_rng(2).standard_normal((C, p))
 
-    def run(pair):
+    def run(pair, scale, iters=iters):
         monkeypatch.setenv("CGG_PAIR", str(pair))
-        with Engine(n, p, family="binomial", w=0.5, n_chains=C, K=8, seed=9, jet_bound_scale=3e5, **PRIOR_CASES["laplace"]) as e:
+        with Engine(n, p, family="binomial", w=0.5, n_chains=C, K=8, seed=9, jet_bound_scale=scale, **PRIOR_CASES["laplace"]) as e:
             e.set_data(X, y)
             for c in range(C):
                 e.init_chain(c, beta0[c])
             S, st = e.run(iters)
             fin = [e.state(c) for c in (0, 1, 17, 31)]
         return S, st, fin
-    S1, st1, fin1 = run(1)
-    S0, st0, fin0 = run(0)
-    assert 0.002 * st1["updates"] < st1["jet_fallbacks"] + st1["jet_retries"] < 0.5 * st1["updates"]     # hand-overs did happen, not always
+    # an inflation of the bound that makes SOME updates hand over (the far stepping-out tests have a margin of a few
+    # hundred, the tests near the slice edge one of ~1e8): calibrated on a short run
+    for scale in (100.0, 300.0, 1e3, 3e3, 1e4, 1e5, 30.0, 10.0):
+        st = run(1, scale, 4)[1]
+        frac = (st["jet_fallbacks"] + st["jet_retries"]) / st["updates"]
+        if 0.02 <= frac <= 0.6:
+            break
+    else:
+        pytest.fail("no bound inflation produced occasional hand-overs")
+    S1, st1, fin1 = run(1, scale)
+    S0, st0, fin0 = run(0, scale)
+    assert 0.01 * st1["updates"] < st1["jet_fallbacks"] + st1["jet_retries"] < 0.8 * st1["updates"]     # hand-overs did happen, not always
     assert np.array_equal(S1, S0)
     for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
         assert st1[k] == st0[k], k

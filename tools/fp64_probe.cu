@@ -13,7 +13,7 @@ __global__ void k_dfma(double *out, int iters) {
 }
 template <int FAM>
 __global__ void k_term(double *out, int iters) {
-    __shared__ double2 tab[L1P_N + 1];
+    __shared__ double2 tab[MATH_TAB_N];
     load_l1p_table(tab);
     __syncthreads();
     const double yv = (threadIdx.x & 1), eta = 0.13 * (threadIdx.x & 31) - 2.0 + 1e-3 * (threadIdx.x >> 5), x = 1.0 + 1e-3 * blockIdx.x;
