@@ -113,6 +113,7 @@ def make_data(wl, device, seed, n_rows=None, row_seed=0):
         j1 = min(p, j0 + 64)
         X[j0:j1].normal_(generator=g)
     X[0].fill_(1.0)
+    make_data.beta_true = bt
     eta = torch.mv(X.t(), bt)
     if wl["family"] == "gaussian":
         y = eta + torch.randn(n, dtype=torch.float64, device=device, generator=g)
@@ -171,6 +172,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def config_of(a, wl, n_total, n, world, sharded):
+    """The `config` object of the JSON line: identical keys and values for both arms (`--impl ours|reference`)."""
+    C, p = wl["chains"], wl["p"]
+    return {"workload": wl["desc"], "n": n_total, "rows_per_gpu": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
+            "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver, "jet_passes": not a.no_jet,
+            "parallelism": (f"row-sharded x{world} (peer-memory exchange of the per-pass sums, rank-ordered)" if sharded
+                            else f"chain-parallel x{world} (no collective)"),
+            "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
+            "beta0": "prior draw x %g" % wl["init_scale"], "burnin_iterations": a.burnin_iters}
+
+
 def cpu_port_run(wl, Xh, yh, beta0, eta0, seconds, threads=None, per_thread_updates=None):
     """Times the oracle port (CPU restatement of the R algorithm -- NOT R) on the host cores.
     One independent chain per thread, the way parallel::mclapply would spread chains; each chain performs
@@ -200,7 +212,7 @@ def cpu_port_run(wl, Xh, yh, beta0, eta0, seconds, threads=None, per_thread_upda
     evals = sum(r[1] for r in res)
     info = {"cores": cores, "updates": total, "wall_s": wall, "evals_per_update": evals / total,
             "sample": f"{per_thread_updates} consecutive coordinate updates on each of {cores} independent "
-                      f"chains (one per host thread), started from the chains' state after the burn-in, same X/y as the GPU run"}
+                      f"chains (one per host thread), started in the stationary region, same X/y as the GPU run"}
     return total / wall, info
 
 
@@ -222,7 +234,6 @@ def main():
         return 1
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    from mcmcglm_b200 import Engine
 
     n, p, C = wl["n"], wl["p"], wl["chains"]
     sharded = bool(wl.get("sharded")) and world > 1
@@ -244,6 +255,7 @@ def main():
     peak_gbs, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
     def new_engine():
+        from mcmcglm_b200 import Engine      # (the reference arm never gets here: it does not load libcggibbs.so)
         e = Engine(n, p, family=wl["family"], sd=1.0, w=wl["w"], n_chains=C, K=wl["K"], device=local,
                    driver="stepwise" if sharded else a.driver, seed=a.seed, chain_offset=0 if sharded else rank * C,
                    spec_tau=a.tau, rows_per_cta_min=a.rows_per_cta_min, row_sharded=sharded, jet=not a.no_jet,
@@ -254,18 +266,14 @@ def main():
 
     # ---------------------------------------------------------------- reference arm (CPU port)
     if a.impl == "reference":
+        # Engine-free: this arm never loads libcggibbs.so.  The chains start near the stationary region the GPU arm is
+        # timed in: beta* + 0.05 noise (beta* = the coefficients the synthetic response was drawn from), eta0 = X beta0
+        # formed here with torch; the port's cost per update depends on the state only through qslice's evaluation count.
+        bt = make_data.beta_true.cpu().numpy()
+        beta0 = bt[None, :] + 0.05 * rng.standard_normal((C, p))
+        eta0 = [torch.mv(X.t(), torch.from_numpy(beta0[c]).to(dev)).cpu().numpy() for c in range(C)]
         Xh = X.cpu().numpy().T      # F-contiguous n x p view, no copy
         yh = y.cpu().numpy()
-        eng = new_engine()
-        eng.set_data_ptr(X.data_ptr(), n, y.data_ptr(), device=True, keepalive=(X, y))
-        for c in range(C):
-            eng.init_chain(c, beta0[c])
-        if a.burnin_iters > 0:               # untimed state preparation: the CPU sample starts from the same
-            eng.run(a.burnin_iters, want_samples=False)   # stationary regime the GPU arm is timed in
-        st_ = [eng.state(c) for c in range(C)]
-        beta0 = np.stack([b for b, _ in st_])
-        eta0 = [e_ for _, e_ in st_]
-        eng.close()
         del X
         cores = os.cpu_count() or 1
         t1 = time.perf_counter()
@@ -283,7 +291,7 @@ def main():
         line = {"impl": "reference", "metric": "coordinate updates/sec", "value": v, "unit": "updates/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["desc"], "n": n, "p": p, "family": wl["family"], "prior": wl["prior"], "w": wl["w"]},
+                "config": config_of(a, wl, n_total, n, world, sharded),
                 "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
                                  "sample": info["sample"] + f"; per step. evals/update {info['evals_per_update']:.2f}. "
                                  "R is not installed in this image: this is the C restatement of the R algorithm (oracle/oracle.c), not R"},
@@ -329,7 +337,12 @@ def main():
         ms = float(t.item())
     updates_per_rank = a.steps * C * p
     value = (1 if sharded else world) * updates_per_rank / (ms * 1e-3)     # sharded: one chain set, rows split
-    achieved = agg["algorithmic_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9
+    # with C chains batched on a GPU the shared operands (y, X_j, X_commit) are read once per C chains, eta
+    # is read (and, with a pending update, written) once per chain: bytes = 8n [(chain_passes + commit_passes)
+    # + (2 chain_passes + commit_passes) / C].  One jet update per chain per column: n (16 C + 24) bytes per column.
+    batched_bytes = 8.0 * n * ((agg["chain_passes"] + agg["commit_passes"]) + (2.0 * agg["chain_passes"] + agg["commit_passes"]) / C)
+    achieved = batched_bytes / (agg["sweep_ms"] * 1e-3) / 1e9
+    per_chain_gbs = agg["algorithmic_bytes"] / (agg["sweep_ms"] * 1e-3) / 1e9
 
     # ---------------------------------------------------------------- e2e (host buffers through the C ABI)
     e2e = None
@@ -415,21 +428,18 @@ def main():
         line = {"metric": "coordinate updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["desc"], "n": n_total, "rows_per_gpu": n, "p": p, "chains_per_gpu": C, "family": wl["family"],
-                           "prior": wl["prior"], "w": wl["w"], "K": wl["K"], "spec_tau": a.tau, "driver": a.driver, "jet_passes": not a.no_jet,
-                           "parallelism": (f"row-sharded x{world} (NCCL all-gather of {C * 10} partial sums per pass, rank-ordered sum in the decide kernel)" if sharded
-                                           else f"chain-parallel x{world} (no collective)"), "l2": "inputs_larger_than_l2 (X streamed: %.1f GB/step/chain)" % (8e-9 * n * p),
-                           "beta0": "prior draw x %g" % wl["init_scale"], "burnin_iterations": a.burnin_iters},
+                "config": config_of(a, wl, n_total, n, world, sharded),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(agg["launches"]),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "sweep_persistent_kernel" if (a.driver == "persistent" and not sharded) else "pass_kernel",
-                             "algorithmic_bytes_per_step": agg["algorithmic_bytes"] / a.steps, "kernel_ms_per_step": agg["sweep_ms"] / a.steps,
+                             "algorithmic_bytes_per_step": batched_bytes / a.steps, "kernel_ms_per_step": agg["sweep_ms"] / a.steps,
+                             "l2_algorithmic_gbs": per_chain_gbs,
                              "grid": [ctas, threads],
                              "dram_gbs_from_traffic": (traffic / (agg["sweep_ms"] / a.steps * 1e-3) / 1e9) if traffic else None,
-                             "note": "algorithmic bytes = 40 n per coordinate update (y, eta, X_j, X_commit read, eta written), counted per "
-                                     "chain; the chains of a GPU work on the same column, so X_j / X_commit / y are staged once per pair of "
-                                     "chains and served by L2 for the other pairs: DRAM traffic (`traffic`, ncu) is ~0.4x the algorithmic "
-                                     "bytes and frac can exceed 1"},
+                             "note": "achieved = SURVEY 8(d) batched bytes (y, X_j, X_commit once per column for the C chains of the GPU, eta "
+                                     "read + written per chain: n (16 C + 24) per column) / device time of the sweep kernel; "
+                                     "l2_algorithmic_gbs counts the shared operands once per chain (40 n per update), which is what the SMs "
+                                     "pull from L2; `traffic` is ncu dram__bytes of one steady launch"},
                 "cpu_baseline": cpu,
                 "engine_stats": {"passes_per_update": agg["passes"] / max(agg["updates"], 1) * C,
                                  "chain_passes_per_update": agg["chain_passes"] / max(agg["updates"], 1),

@@ -927,6 +927,21 @@ __device__ __forceinline__ bool limbs_take(const Dev &d, int c, int nvals, int l
     return true;
 }
 
+// (see jet_prepare / jet_decide below for how these are used)
+constexpr int JET_R1_SO = 4;         // stepping-out tests per side in round 1
+constexpr int JET_R1_PROP = 32 - 2 * JET_R1_SO;
+struct JetLane { double x, l, r, pr, uA, uB; };            // this lane's point, the bracket a proposal was drawn from, log-prior at x, its uniforms
+struct JetScal {
+    double x0, logu, L0, R0, Jb, Kb, prior_x0, lend, rend; // lend / rend: the bracket after all JET_R1_PROP proposals were rejected
+    uint64_t cursor;
+    int32_t j, nAvail, openL, openR;
+};
+struct JetPre {                      // the deciding warp's shared-memory copy, one per chain
+    double x[32], l[32], r[32], pr[32], uA[32], uB[32];
+    JetScal sc;
+    int32_t valid, pad;
+};
+
 // What the deciding warp of the persistent driver keeps in its CTA's shared memory between two decisions of a chain, so
 // that a decision starts from shared memory instead of a chain of dependent global loads: the chain's state and control
 // block as it left them, and -- fetched right AFTER a decision is published, i.e. off the critical path -- the beta /
@@ -939,6 +954,7 @@ struct DeciderCache {
     int32_t pref_j;             // column the prefetched values belong to (-1: none)
     int32_t valid;              // s / ct hold the chain's current state
     unsigned long long prev[NV * 4];   // the chain's limb-accumulator words as of its last decided pass (limbs_take)
+    JetPre pre;                 // the next update's draws and first-round points (jet_prepare), computed while its pass runs
 };
 __device__ __forceinline__ void decider_prefetch(const Dev &d, int c, DeciderCache *dc, int lane) {
     const int jq = dc->ct.j;
@@ -1165,8 +1181,68 @@ enum JetOutcome : int { JET_EXACT = 0, JET_ACCEPTED = 1, JET_RETRY = 2 };
 #else
 #define CGG_TICK(slot) do { if (d.prof && lane == 0) { const long long t_ = clock64(); atomicAdd(d.prof + (slot), (unsigned long long)(t_ - tick)); tick = t_; } } while (0)
 #endif
+
+// Everything a fresh update needs that does NOT depend on the pass's sums: the uniforms, log(u), the initial bracket, and
+// -- because stepping-out tests and shrink proposals are functions of (L, R, x0, u) only -- the points the first round of
+// verdicts will be asked about, with their log-prior.  The deciding warp computes this right after it has published the
+// previous decision, i.e. while the workers are streaming the rows, so that once the sums arrive only the enclosure
+// evaluations and the comparisons remain on the chain's critical cycle.
+// Lane roles of the first round: lanes 0..3 test L0 - i w, lanes 4..7 test R0 + i w, lanes 8..31 are the first 24 shrink
+// proposals drawn from the bracket (L0, R0) -- valid iff stepping out does not move it, the common case.
+__device__ __forceinline__ void jet_prepare(const Dev &d, int c, int lane, int j, uint64_t cursor, double x0, JetLane &jl, JetScal &sc) {
+    sc.x0 = x0; sc.cursor = cursor; sc.j = j;
+    double uA = 0.5, uB = 0.5;
+    const bool okA = draw_uniform(d, c, cursor + lane, uA);
+    const bool okB = draw_uniform(d, c, cursor + 32 + lane, uB);
+    const unsigned mA = __ballot_sync(0xffffffffu, okA), mB = __ballot_sync(0xffffffffu, okB);
+    sc.nAvail = (mA == 0xffffffffu) ? 32 + ((mB == 0xffffffffu) ? 32 : __ffs(~mB) - 1) : __ffs(~mA) - 1;
+    jl.uA = uA; jl.uB = uB;
+    const double u0 = __shfl_sync(0xffffffffu, uA, 0), u1 = __shfl_sync(0xffffffffu, uA, 1), u2 = __shfl_sync(0xffffffffu, uA, 2);
+    sc.logu = log(u0);                                    // y <- log(runif(1)) + f(x)
+    sc.L0 = __dadd_rn(x0, -__dmul_rn(u1, d.w));           // L <- x - runif(1) * w
+    sc.R0 = __dadd_rn(sc.L0, d.w);                        // R <- L + w
+    sc.prior_x0 = prior_logdens(d.prior, x0);
+    if (d.max_steps < 0) { sc.openL = sc.openR = 1; sc.Jb = sc.Kb = 0.0; }
+    else if (d.max_steps > 0) {
+        sc.Jb = floor(u2 * (double)d.max_steps);          // J <- floor(runif(1) * max)
+        sc.Kb = (double)d.max_steps - 1.0 - sc.Jb;        // K <- max - 1 - J
+        sc.openL = sc.Jb > 0.0; sc.openR = sc.Kb > 0.0;
+    } else { sc.openL = sc.openR = 0; sc.Jb = sc.Kb = 0.0; }
+    // repeat { x1 <- L + runif(1) * (R - L); ... shrink }: the proposals under the bracket (L0, R0)
+    const int base = base_draws(d);
+    double l = sc.L0, r = sc.R0, xi = 0.0, li = l, ri = r;
+    for (int t = 0; t < JET_R1_PROP; ++t) {
+        const int idx = base + t;
+        const double ut = (idx < 32) ? __shfl_sync(0xffffffffu, uA, idx) : __shfl_sync(0xffffffffu, uB, idx - 32);
+        const double x = __dadd_rn(l, __dmul_rn(ut, __dadd_rn(r, -l)));
+        if (lane == 2 * JET_R1_SO + t) { xi = x; li = l; ri = r; }
+        if (x < x0) l = x; else r = x;
+    }
+    sc.lend = l; sc.rend = r;
+    if (lane < 2 * JET_R1_SO) {                           // stepping-out test points: L0, L0 - w, ... / R0, R0 + w, ...
+        const bool left = lane < JET_R1_SO;
+        const int i = left ? lane : lane - JET_R1_SO;
+        double v = left ? sc.L0 : sc.R0;
+        const double step = left ? -d.w : d.w;
+        for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
+        xi = v; li = sc.L0; ri = sc.R0;
+    }
+    jl.x = xi; jl.l = li; jl.r = ri;
+    jl.pr = prior_logdens(d.prior, xi);
+}
+__device__ __forceinline__ void jet_pre_store(JetPre *p, int lane, const JetLane &jl, const JetScal &sc) {
+    p->x[lane] = jl.x; p->l[lane] = jl.l; p->r[lane] = jl.r; p->pr[lane] = jl.pr; p->uA[lane] = jl.uA; p->uB[lane] = jl.uB;
+    if (lane == 0) { p->sc = sc; p->valid = 1; }
+    __syncwarp();
+}
+__device__ __forceinline__ void jet_pre_load(const JetPre *p, int lane, JetLane &jl, JetScal &sc) {
+    jl.x = p->x[lane]; jl.l = p->l[lane]; jl.r = p->r[lane]; jl.pr = p->pr[lane]; jl.uA = p->uA[lane]; jl.uB = p->uB[lane];
+    sc = p->sc;
+}
+
 __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV], bool light,
-                                          double x0, double shat_j, const double *cst, double &x1_out, double &shat_out, long long &tick) {
+                                          double x0, double shat_j, const double *cst, const JetPre *pre,
+                                          double &x1_out, double &shat_out, long long &tick) {
     s.npass++; s.jet_passes++;
     if (ct.commit_j >= 0) { s.commit_passes++; ct.commit_j = -1; ct.commit_delta = 0.0; }
     ct.coarse_mask = 0;
@@ -1179,105 +1255,125 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
         if (d.family != CGG_GAUSSIAN && m[9] != 0.0) s.jet_skip = 1;
     }
     const double fmag = light ? fabs(s.fx0) + 1.0 : fabs(m[0]);
-    // ---- uniforms: 2 (3 with a finite max) start draws + up to 32 shrink draws
-    double uA = 0.5, uB = 0.5;
-    const bool okA = draw_uniform(d, c, s.cursor + lane, uA);
-    const bool okB = draw_uniform(d, c, s.cursor + 32 + lane, uB);
-    const unsigned mA = __ballot_sync(0xffffffffu, okA), mB = __ballot_sync(0xffffffffu, okB);
-    const int nAvail = (mA == 0xffffffffu) ? 32 + ((mB == 0xffffffffu) ? 32 : __ffs(~mB) - 1) : __ffs(~mA) - 1;
+    // ---- the update's draws and first-round points: prepared while the pass was running, or now
+    JetLane jl; JetScal sc;
+    if (pre && pre->valid && pre->sc.j == s.j && pre->sc.cursor == s.cursor && pre->sc.x0 == x0) jet_pre_load(pre, lane, jl, sc);
+    else jet_prepare(d, c, lane, s.j, s.cursor, x0, jl, sc);
+    CGG_TICK(14);      // uniforms and points at hand
     const int base = base_draws(d);
-    double U3[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) U3[i] = __shfl_sync(0xffffffffu, uA, i);
-    CGG_TICK(14);      // uniforms drawn
-    start_coordinate(d, s, x0, U3, nAvail < 3 ? nAvail : 3);
-    if (s.status != CGG_OK) return JET_EXACT;
-    const double logu = log(U3[0]);
-    const double prior_x0 = prior_logdens(d.prior, s.x0);
-    const int sidx = base + lane;                     // this lane's shrink draw
-    const double usA = __shfl_sync(0xffffffffu, uA, sidx & 31), usB = __shfl_sync(0xffffffffu, uB, sidx & 31);
-    const double us = (sidx < 32) ? usA : usB;
-    const bool us_ok = sidx < nAvail;
+    // start of the update (qslice::slice_stepping_out up to the first f(L) test; R/mcmcglm.R:258-261)
+    s.x0 = x0;
+    s.prior_rest = s.prior_sum - sc.prior_x0;
+    s.sdrawn = 0; s.npass = 0;
+    if (sc.nAvail < base) { s.status = CGG_E_STREAM; return JET_EXACT; }
+    s.ylev = __dadd_rn(sc.logu, s.fx0);
+    s.L = sc.L0; s.R = sc.R0;
+    s.ref_evals += 1;                                     // qslice's f(x0)
+    s.openL = sc.openL; s.openR = sc.openR; s.Jb = sc.Jb; s.Kb = sc.Kb;
+    s.phase = (s.openL || s.openR) ? PH_STEPOUT : PH_SHRINK;
+    const double logu = sc.logu, prior_x0 = sc.prior_x0;
     const double bscale = d.jet_bscale;
-    // verdict on candidate v; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
-    auto verdict = [&](double v, bool &in, bool &out, double &fnew) {
+    // verdict on candidate v with log-prior pv; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
+    auto verdict = [&](double v, double pv, bool &in, bool &out, double &fnew) {
         double B;
         const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B, light);
         B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
         if (light) {
-            const double t = dl + (prior_logdens(d.prior, v) - prior_x0);
+            const double t = dl + (pv - prior_x0);
             fnew = s.fx0 + t;
             in = logu + B < t;
             out = t + B <= logu;
         } else {
             // same expression order as the exact path: (ll + ll_const) + (prior_rest + prior(v)), monotone in ll
             const double ll = m[0] + dl;
-            const double pr = s.prior_rest + prior_logdens(d.prior, v);
+            const double pr = s.prior_rest + pv;
             const double flo = ((ll - B) + llc) + pr, fhi = ((ll + B) + llc) + pr;
             fnew = (ll + llc) + pr;
             in = s.ylev < flo;
             out = fhi <= s.ylev;
         }
     };
-    if (s.phase == PH_STEPOUT) {
-        const bool left = lane < 16;
-        const int i = lane & 15;
-        double v = left ? s.L : s.R;
-        const double step = left ? -d.w : d.w;
-        for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
-        bool in = false, out = false; double fm;
-        if (left ? s.openL : s.openR) verdict(v, in, out, fm);
-        const unsigned min_ = __ballot_sync(0xffffffffu, in), mout = __ballot_sync(0xffffffffu, out);
-        bool expanded = false;
-        // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
-        for (int t = 0; t < 16 && s.openL; ++t) {
-            const bool tin = (min_ >> t) & 1u, tout = (mout >> t) & 1u;
-            if (!tin && !tout) break;
+    // consume stepping-out verdicts of one side, in sequence; false: a test was not certain (the state is exact up to it)
+    auto consume = [&](unsigned vin, unsigned vout, int ntests, bool left, bool &expanded) -> bool {
+        for (int t = 0; t < ntests && (left ? s.openL : s.openR); ++t) {
+            const bool tin = (vin >> t) & 1u, tout = (vout >> t) & 1u;
+            if (!tin && !tout) return false;
             s.ref_evals++;
-            if (tin) {
-                s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true;
-                if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; }
-            } else s.openL = 0;
+            if (left) {           // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
+                if (tin) { s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; } }
+                else s.openL = 0;
+            } else {
+                if (tin) { s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; } }
+                else s.openR = 0;
+            }
         }
-        for (int t = 0; t < 16 && s.openR; ++t) {
-            const bool tin = (min_ >> (16 + t)) & 1u, tout = (mout >> (16 + t)) & 1u;
-            if (!tin && !tout) break;
-            s.ref_evals++;
-            if (tin) {
-                s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true;
-                if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; }
-            } else s.openR = 0;
+        return true;
+    };
+    // ---- round 1: the first stepping-out tests of both sides AND the proposals under the initial bracket, in one go
+    bool in = false, out = false; double fm = 0.0;
+    {
+        const bool active = (lane < JET_R1_SO) ? (s.openL != 0) : ((lane < 2 * JET_R1_SO) ? (s.openR != 0) : (base + lane - 2 * JET_R1_SO < sc.nAvail));
+        if (active) verdict(jl.x, jl.pr, in, out, fm);
+    }
+    unsigned vin = __ballot_sync(0xffffffffu, in), vout = __ballot_sync(0xffffffffu, out);
+    CGG_TICK(15);      // round 1 judged
+    bool expanded = false, certain = true;
+    if (s.phase == PH_STEPOUT) {
+        certain = consume(vin, vout, JET_R1_SO, true, expanded);
+        if (certain) certain = consume(vin >> JET_R1_SO, vout >> JET_R1_SO, JET_R1_SO, false, expanded);
+        // more than JET_R1_SO expansions on a side (a slice much wider than w): further rounds of 16 tests per side
+        for (int round = 0; certain && (s.openL || s.openR) && round < 64; ++round) {
+            const bool left = lane < 16;
+            const int i = lane & 15;
+            double v = left ? s.L : s.R;
+            const double step = left ? -d.w : d.w;
+            for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
+            bool in2 = false, out2 = false; double f2;
+            if (left ? s.openL : s.openR) verdict(v, prior_logdens(d.prior, v), in2, out2, f2);
+            const unsigned vi = __ballot_sync(0xffffffffu, in2), vo = __ballot_sync(0xffffffffu, out2);
+            certain = consume(vi, vo, 16, true, expanded);
+            if (certain) certain = consume(vi >> 16, vo >> 16, 16, false, expanded);
         }
         s.pexp = 0.9 * s.pexp + (expanded ? 0.1 : 0.0);
-        if (s.openL || s.openR) {                    // a test the enclosure could not decide
+        if (s.openL || s.openR) {                    // a test the enclosure could not decide (or an endless expansion)
             if (light) return JET_RETRY;
             s.jet_fallbacks++;
             return JET_EXACT;
         }
         s.phase = PH_SHRINK;
     }
-    CGG_TICK(15);      // stepping out decided
-    // repeat { x1 <- L + runif(1) * (R - L); if (y < f(x1)) return x1; shrink }: the proposals depend on (L, R, x0, u) only
-    double l = s.L, r = s.R, xi = 0.0, li = l, ri = r;
-    for (int t = 0; t < 32; ++t) {
-        const double ut = __shfl_sync(0xffffffffu, us, t);
-        const double x = __dadd_rn(l, __dmul_rn(ut, __dadd_rn(r, -l)));
-        if (lane == t) { xi = x; li = l; ri = r; }
-        if (x < s.x0) l = x; else r = x;
+    // ---- the shrink proposals: round 1's if the bracket did not move, else drawn again from the expanded bracket
+    int nprop = JET_R1_PROP, poff = 2 * JET_R1_SO;
+    double lend = sc.lend, rend = sc.rend, xi = jl.x, li = jl.l, ri = jl.r;
+    if (expanded) {
+        nprop = 32; poff = 0;
+        const int sidx = base + lane;
+        const double usA = __shfl_sync(0xffffffffu, jl.uA, sidx & 31), usB = __shfl_sync(0xffffffffu, jl.uB, sidx & 31);
+        const double us = (sidx < 32) ? usA : usB;
+        double l = s.L, r = s.R;
+        for (int t = 0; t < 32; ++t) {
+            const double ut = __shfl_sync(0xffffffffu, us, t);
+            const double x = __dadd_rn(l, __dmul_rn(ut, __dadd_rn(r, -l)));
+            if (lane == t) { xi = x; li = l; ri = r; }
+            if (x < s.x0) l = x; else r = x;
+        }
+        lend = l; rend = r;
+        in = false; out = false; fm = 0.0;
+        if (sidx < sc.nAvail) verdict(xi, prior_logdens(d.prior, xi), in, out, fm);
+        vin = __ballot_sync(0xffffffffu, in); vout = __ballot_sync(0xffffffffu, out);
     }
-    CGG_TICK(16);      // proposal sequence generated
-    bool in = false, out = false; double fm = 0.0;
-    if (us_ok) verdict(xi, in, out, fm);
-    const unsigned mout = __ballot_sync(0xffffffffu, out);
-    const int k = (mout == 0xffffffffu) ? 32 : __ffs(~mout) - 1;      // first proposal that is not certainly rejected
-    if (k == 32) {
+    CGG_TICK(16);      // stepping out decided, proposals judged
+    const unsigned pmask = (nprop == 32) ? 0xffffffffu : ((1u << nprop) - 1u);
+    const unsigned pout = (vout >> poff) & pmask, pin = (vin >> poff) & pmask;
+    const int k = (pout == pmask) ? nprop : __ffs(~pout) - 1;      // first proposal that is not certainly rejected
+    if (k == nprop) {
         if (light) return JET_RETRY;
-        s.shrinks += 32; s.ref_evals += 32; s.sdrawn = 32; s.L = l; s.R = r;
+        s.shrinks += nprop; s.ref_evals += nprop; s.sdrawn = nprop; s.L = lend; s.R = rend;
         s.jet_fallbacks++;
         return JET_EXACT;
     }
-    const bool kin = __shfl_sync(0xffffffffu, (int)in, k);
-    s.L = __shfl_sync(0xffffffffu, li, k); s.R = __shfl_sync(0xffffffffu, ri, k);   // the bracket proposal k was drawn from
+    const bool kin = (pin >> k) & 1u;
+    s.L = __shfl_sync(0xffffffffu, li, k + poff); s.R = __shfl_sync(0xffffffffu, ri, k + poff);   // the bracket proposal k was drawn from
     s.shrinks += k; s.ref_evals += k;
     if (!kin) {                 // undecided (or its draw is not available): the exact passes continue from proposal k
         if (light) return JET_RETRY;
@@ -1286,10 +1382,21 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
         return JET_EXACT;
     }
     s.shrinks++; s.ref_evals++;
-    const double x1 = __shfl_sync(0xffffffffu, xi, k), f1 = __shfl_sync(0xffffffffu, fm, k);
+    const double x1 = __shfl_sync(0xffffffffu, xi, k + poff), f1 = __shfl_sync(0xffffffffu, fm, k + poff);
     accept_value(d, c, s, ct, x1, f1, shat_j, k + 1, lane == 0, x1_out, shat_out);
-    CGG_TICK(17);      // proposals judged, value accepted
+    CGG_TICK(17);      // value accepted
     return JET_ACCEPTED;
+}
+
+// Persistent driver, right after a decision was published and the next column's beta / statistics were prefetched: if the
+// pass now in flight is a jet pass that starts a fresh update, prepare that update (jet_prepare) while the rows stream.
+__device__ __forceinline__ void decider_prephase(const Dev &d, int c, DeciderCache *dc, int lane) {
+    const bool want = dc->valid && dc->s.status == CGG_OK && dc->s.phase == PH_JET && dc->ct.j >= 0 && dc->pref_j == dc->ct.j;
+    if (!want) { if (lane == 0) dc->pre.valid = 0; __syncwarp(); return; }
+    if (dc->pre.valid && dc->pre.sc.j == dc->s.j && dc->pre.sc.cursor == dc->s.cursor && dc->pre.sc.x0 == dc->beta_j) return;   // (a retry of the same update)
+    JetLane jl; JetScal sc;
+    jet_prepare(d, c, lane, dc->s.j, dc->s.cursor, dc->beta_j, jl, sc);
+    jet_pre_store(&dc->pre, lane, jl, sc);
 }
 
 // One warp decides one chain after every worker's contribution to the pass is visible.
@@ -1384,7 +1491,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (jetpass) {
         double x1 = 0.0, sh1 = 0.0;
         const bool light = ((unsigned)ct.coarse_mask & JET_FULL) == 0u;
-        const int oc = jet_decide(d, c, lane, s, ct, jm, light, beta_j, shat_j, cst_j, x1, sh1, tick);
+        const int oc = jet_decide(d, c, lane, s, ct, jm, light, beta_j, shat_j, cst_j, dc ? &dc->pre : nullptr, x1, sh1, tick);
         if (oc == JET_ACCEPTED) {
             if (jn != jq) { x0 = beta_n; shat = shat_n; } else { x0 = x1; shat = sh1; }
         } else if (oc == JET_RETRY) {

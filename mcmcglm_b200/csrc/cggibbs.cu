@@ -45,7 +45,7 @@ __device__ __forceinline__ bool wait_timed_out(const Dev &d, unsigned long long 
 __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int stride, int lane, DeciderCache *cache) {
     const Dev &d = *dp;
     for (int c = first_chain; c < d.C; c += stride) {
-        if (lane == 0) { cache[c].valid = 0; cache[c].pref_j = -1; }
+        if (lane == 0) { cache[c].valid = 0; cache[c].pref_j = -1; cache[c].pre.valid = 0; }
         for (int i = lane; i < NV * 4; i += 32) cache[c].prev[i] = 0ULL;      // the accumulators are zeroed before every launch
     }
     __syncwarp();
@@ -65,7 +65,10 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
             const bool fin = oc == DEC_FINISHED;
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
-            if (!fin) decider_prefetch(d, c, cache + c, lane);       // after publishing: off the chain's critical path
+            if (!fin) {                                              // after publishing: off the chain's critical path
+                decider_prefetch(d, c, cache + c, lane);
+                decider_prephase(d, c, cache + c, lane);
+            }
             if (d.prof && lane == 0) {
                 atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL);
                 if (v < 128) { d.prof[32 + 4096 + (c * 128 + v) * 4 + 0] = tg0; d.prof[32 + 4096 + (c * 128 + v) * 4 + 1] = globaltimer_ns(); }
@@ -850,6 +853,29 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     h->fx_valid.assign(C, 0);
     h->fx_mag.assign(C, 0);
     d.colstat = h->colstat_dev;
+    {   // Keep the chains' eta vectors resident in the 126 MB L2 across passes (cfg3: 8 x 8 MB): they are the only operand
+        // that is read AND written every pass, and the only one whose traffic grows with the number of chains.  With eta
+        // pinned (persisting lines, set-aside carved out of L2) HBM only carries each X column once per column step.
+        // CGG_L2_PERSIST=0 turns it off (experiments).  Never changes results.
+        const char *e2 = getenv("CGG_L2_PERSIST");
+        const bool want = e2 ? atoi(e2) != 0 : true;
+        const size_t eta_bytes = sizeof(double) * (size_t)C * d.lde;
+        if (want && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, eta_bytes);
+            size_t cur = 0;
+            cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+            if (cur < carve) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = (void *)d.eta;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(eta_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)cur / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+    }
     *out = h;
     return CGG_OK;
 }

@@ -76,7 +76,7 @@ def test_enclosure_contains_the_exact_value(family):
                     pk = oracle.log_prior_density(m, np.r_[beta[:j], cands[k], beta[j + 1:]])
                     ex_diff = (f_ex[k] - pk) - (f_ex[0] - oracle.log_prior_density(m, beta))
                     assert abs(dval[k] - ex_diff) <= dbnd[k] + 16 * np.spacing(abs(f_ex[k])), (j, k)
-                assert np.all(dbnd[:3] < 1e-9) and np.all(dbnd[:5] < 1e-4)
+                assert np.all(dbnd[:3] < 1e-7) and np.all(dbnd[:5] < 1e-3)      # order 3 + 2e-11 approximations: looser than a full pass, still << 1
 
 
 def _run(family, prior, X, y, beta0, iters, U=None, **kw):
