@@ -155,13 +155,26 @@ int cgg_log_potential(cgg_handle *h, int32_t chain, int64_t j, int32_t K, const 
 int cgg_update_eta(cgg_handle *h, int32_t chain, int64_t j, double new_beta_j);
 
 /* The (k, j) loop of R/mcmcglm.R:226-274 for n_iter further iterations of every chain.
- *   replay_u  NULL => on-device Philox; else n_chains streams of n_u uniforms each
- *             (replay_u[c*n_u + i]) consumed exactly as qslice's runif(1) calls would.
- *   u_consumed  [n_chains] cumulative uniforms consumed per chain (nullable).
+ *   replay_u  NULL => on-device Philox; else n_chains streams of n_u uniforms each: replay_u[c*n_u + i] is the i-th
+ *             uniform chain c consumes IN THIS CALL (every call brings its own buffer), consumed exactly as qslice's
+ *             runif(1) calls would.  Running out of them is CGG_E_STREAM.
+ *   u_consumed  [n_chains] cumulative uniforms consumed per chain since it was initialised (nullable).
  *   samples_out [n_chains][n_iter][p] row-major: beta after each iteration (nullable).
- * May be called repeatedly; the chain state persists between calls. */
+ * May be called repeatedly; the chain state persists between calls.  The Philox stream of a chain is indexed by that
+ * cumulative count, which cgg_init_chain / cgg_set_state reset to 0: re-initialising a chain replays the same numbers
+ * unless cfg.seed or cfg.chain_offset differ.
+ * After a device-side failure of a chain (CGG_E_NAN, CGG_E_STREAM, CGG_E_NOTERM) that chain stopped in the middle of an
+ * update; it is marked uninitialised and must be given a state again (cgg_init_chain / cgg_set_state) before the next
+ * cgg_run, which otherwise returns CGG_E_STATE. */
 int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, uint64_t n_u, uint64_t *u_consumed,
             double *samples_out, cgg_stats *stats);
+
+/* qslice's tuning parameter per chain: w_host[n_chains] replaces cfg.w from the next cgg_run on.  This is how
+ * mcmcglm_across_tuningparams (R/slice_utilities.R:43-85) becomes ONE engine run: the chains share every X_j read. */
+int cgg_set_chain_w(cgg_handle *h, const double *w_host);
+/* The counters of one chain from the last cgg_run (ref_evals = qslice's nEvaluations, which the reference drops at
+ * R/mcmcglm.R:261); launches and sweep_ms are not per chain and stay 0. */
+int cgg_get_chain_stats(cgg_handle *h, int32_t chain, cgg_stats *out);
 
 /* Current beta[p] and (nullable) eta[n] of a chain, to host. */
 int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, double *eta_host);

@@ -220,7 +220,7 @@ def _engine_kwargs(family, beta_prior, log_likelihood_extra_args):
 def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likelihood_extra_args=None,
             linear_predictor_calc="update", sample_method="slice_sampling", qslice_fun=slice_stepping_out,
             n_samples=500, burnin=100, *, n_chains=1, device=0, K=8, seed=None, beta_init=None,
-            replay_uniforms=None, driver="persistent", **tuning):
+            replay_uniforms=None, driver="persistent", _w_per_chain=None, **tuning):
     """mcmcglm() of R/mcmcglm.R:147-299 on the GPU engine.  `**tuning` is the reference's `...` (forwarded
     to qslice_fun: `w`, `max`).  Keyword-only arguments after `burnin` are engine extensions.
     """
@@ -262,9 +262,12 @@ def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likeliho
     with Engine(n, p, w=float(tuning["w"]), max_steps=-1 if np.isinf(mx) else int(mx), n_chains=n_chains, K=K,
                 device=device, driver=driver, seed=eng_seed, **ekw) as e:
         e.set_data(X, Y)
+        if _w_per_chain is not None:                                          # a tuning sweep: every chain its own w
+            e.set_chain_w(_w_per_chain)
         for c in range(n_chains):
             e.init_chain(c, beta0[c])                                         # :215 init_eta = X %*% init_beta
         S, st = e.run(n_samples, replay_u=replay_uniforms)                    # :226-274
+        st["per_chain"] = [e.chain_stats(c) for c in range(n_chains)]
     import pandas as pd
     chains = np.concatenate([beta0[:, None, :], S], axis=1)                   # row 0 = the prior draw, :222
     df = pd.DataFrame(chains[0], columns=names)
@@ -308,9 +311,40 @@ def update_linear_predictor(new_beta_j, current_beta_j, current_eta, X_j, device
         return e.state(0)[1]
 
 
-def mcmcglm_across_tuningparams(*values, tuning_parameter_name="w", **kw):
-    """mcmcglm_across_tuningparams of R/slice_utilities.R:43-85: one mcmcglm() per value of the tuning
-    parameter; returns the list (the reference attaches attr 'tuning_parameter_name')."""
-    out = [mcmcglm(**{tuning_parameter_name: v}, **kw) for v in values[0]] if len(values) == 1 and np.ndim(values[0]) else \
-          [mcmcglm(**{tuning_parameter_name: v}, **kw) for v in values]
+def mcmcglm_across_tuningparams(*values, tuning_parameter_name="w", parallelise=False, n_cores=None, **kw):
+    """mcmcglm_across_tuningparams of R/slice_utilities.R:43-85.  The reference runs one mcmcglm() per value of the tuning
+    parameter (`lapply`, or `future_lapply` over worker processes with `parallelise = TRUE`).  Here a sweep over `w` is
+    ONE engine run: the values become the chains of a single upload of X and y (every chain its own `w`, prior draw and
+    Philox substream), walking the columns together, up to 32 values per run.  `parallelise` / `n_cores` are accepted and
+    ignored.  Returns the list of mcmcglm objects (one per value, in order), each with `stats["nEvaluations"]` = the number
+    of log-potential evaluations qslice made for that value -- which the reference computes and drops (R/mcmcglm.R:261)."""
+    if len(values) == 0:
+        raise ValueError("a vector of tuning parameter values is needed")
+    vals = list(np.atleast_1d(values[0])) if np.ndim(values[0]) else list(values)
+    other = {}
+    if np.ndim(values[0]) and len(values) > 1:                      # R: further positional tuning args are passed through
+        raise ValueError("pass further tuning parameters by name")
+    if tuning_parameter_name != "w":
+        return [mcmcglm(**{tuning_parameter_name: v}, **kw) for v in vals]
+    kw = dict(kw)
+    kw.pop("w", None)
+    user_chains = kw.pop("n_chains", 1)
+    if user_chains != 1:
+        raise L.CggError(L.E_ARG, "mcmcglm_across_tuningparams runs one chain per tuning value")
+    out = []
+    for i0 in range(0, len(vals), 32):
+        chunk = [float(v) for v in vals[i0:i0 + 32]]
+        fit = mcmcglm(w=chunk[0], n_chains=len(chunk), _w_per_chain=np.array(chunk), **kw, **other)
+        for c, v in enumerate(chunk):
+            import pandas as pd
+            names = list(fit.beta_samples.columns[:-2])
+            df = pd.DataFrame(fit.chains[c], columns=names)
+            df["iteration"] = fit.beta_samples["iteration"].to_numpy()
+            df["burnin"] = fit.beta_samples["burnin"].to_numpy()
+            st = dict(fit.stats["per_chain"][c])
+            st["nEvaluations"] = st["ref_evals"]
+            out.append(McmcGlm(beta_samples=df, beta_mean=df.loc[~df["burnin"], names].mean().to_frame().T, data=fit.data,
+                               model_matrix=fit.model_matrix, param_list=None, family=fit.family, formula=fit.formula,
+                               call=fit.call.replace(f"w = {chunk[0]}", f"w = {v}"), burnin=fit.burnin, sample_method=fit.sample_method,
+                               qslice_fun=fit.qslice_fun, tuning={**fit.tuning, "w": v}, chains=fit.chains[c:c + 1], stats=st))
     return out

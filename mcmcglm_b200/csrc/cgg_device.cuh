@@ -18,7 +18,8 @@ namespace cgg {
 constexpr int KMAX = CGG_KMAX;
 constexpr int NV = KMAX + 2;    // values a chain pass delivers: KMAX candidate sums + the two error-bound sums of the pre-filter
 #ifndef CGG_THREADS
-#define CGG_THREADS 384     // 12 warps per SM: measured best (16 warps pay more per-pass overhead than the extra latency hiding gains, 8 hide too little)
+#define CGG_THREADS 256     // 8 warps per SM: measured best for the round-2 kernels (cfg3: 128 -> 186k, 192 -> 199k, 256 -> 222k, 320 -> 203k,
+                            // 384 -> 203k, 512 -> 154k updates/s): every warp pays the per-pass fixed work (reductions, delivery, control)
 #endif
 #ifndef CGG_RING_D
 #define CGG_RING_D 4
@@ -92,7 +93,8 @@ struct __align__(16) ChainState {
     uint64_t cursor;    // uniforms consumed before this update
     uint64_t updates, chain_passes, commit_passes, cand_evals, ref_evals, stepouts, shrinks, passes;
     uint64_t coarse_evals, coarse_undecided;
-    uint64_t jet_passes, jet_fallbacks, jet_retries, pad2;
+    uint64_t jet_passes, jet_fallbacks, jet_retries;
+    double w;           // this chain's slice width (qslice's `w`; per chain so that a tuning sweep is ONE engine run)
 };
 static_assert(sizeof(ChainState) % 16 == 0, "ChainState is copied with 128-bit accesses");
 
@@ -116,7 +118,9 @@ struct Dev {
     int64_t n, p, ldx, lde, n_tiles, n_iter, iter_stop;   // iter_stop: iteration count at which this launch stops (<= n_iter)
     uint64_t n_u, seed;
     int64_t max_steps;
-    double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds)
+    double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds); w: default slice width (ChainState::w is what the chains use)
+    double jet_ce;             // rounding allowance of one accumulated moment, relative to the sum of its terms' magnitudes (cgg_create: from the summation depth)
+    uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
     PriorParams prior;
     int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, pad_;   // pair: chains 2k, 2k+1 share a pass when they can
 };
@@ -519,10 +523,10 @@ struct PairStream {      // running pointers of a pair pass: the tile to be issu
     }
 };
 
-template <int FAMILY, bool FULL, class AFTER>
+template <int FAMILY, bool FULL, class EARLY, class AFTER>
 __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const double *cwA, const double *cwB, long long wid, long long W,
-                                               int lane, uint32_t ring, const double2 *tab, bool prefetched, AFTER &&after_tiles,
-                                               double (&mA)[NV], double (&mB)[NV]) {
+                                               int lane, uint32_t ring, const double2 *tab, bool prefetched, EARLY &&after_prologue,
+                                               AFTER &&after_tiles, double (&mA)[NV], double (&mB)[NV]) {
     const double cdA = cwA[2], cdB = cwB[2], cscale = cwA[CTL_WORDS - 1];
     const int64_t n = d.n;
     PairStream ps(d, c0, cwA, wid, W, lane, ring);
@@ -534,6 +538,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
     unsigned riskA = 0, riskB = 0, rows = 0;
     ps.prologue(prefetched);
+    after_prologue();     // the first tiles are on their way: a good moment for a (blocking) look at the next pair's decision
     unsigned stage = 0;
     auto score_tile = [&](unsigned st, int64_t off) {
         const uint32_t s = ps.sbase + st * STAGE;
@@ -982,8 +987,9 @@ __device__ __forceinline__ void decider_prefetch(const Dev &d, int c, DeciderCac
 // Uniform #i (0-based within the chain's stream): replayed (R's runif record) or Philox.
 __device__ __forceinline__ bool draw_uniform(const Dev &d, int c, uint64_t i, double &u) {
     if (d.replay) {
-        if (i >= d.n_u) { u = 0.5; return false; }
-        u = __ldcg(d.replay + (uint64_t)c * d.n_u + i);
+        const uint64_t r = i - d.replay_origin[c];      // the buffer of this cgg_run starts at the chain's cursor at entry
+        if (r >= d.n_u) { u = 0.5; return false; }
+        u = __ldcg(d.replay + (uint64_t)c * d.n_u + r);
     } else {
         u = philox_uniform(d.seed, (uint32_t)(d.chain_offset + c), i);
     }
@@ -1010,13 +1016,13 @@ __device__ __forceinline__ void build_candidates(const Dev &d, ChainState &s, Ct
             int m = depth;
             if (d.max_steps > 0 && (double)m > s.Jb) m = (int)s.Jb;
             double v = s.L;
-            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nL++; v = __dadd_rn(v, -d.w); }
+            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nL++; v = __dadd_rn(v, -s.w); }
         }
         if (s.openR) {
             int m = depth;
             if (d.max_steps > 0 && (double)m > s.Kb) m = (int)s.Kb;
             double v = s.R;
-            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nR++; v = __dadd_rn(v, d.w); }
+            for (int i = 0; i < m; ++i) { s.cand[n++] = v; s.nR++; v = __dadd_rn(v, s.w); }
         }
         pneed = 1.0 - s.pexp;
     }
@@ -1066,8 +1072,8 @@ __device__ __forceinline__ void start_coordinate(const Dev &d, ChainState &s, do
     s.sdrawn = 0; s.npass = 0;
     if (nU < base_draws(d)) { s.status = CGG_E_STREAM; return; }
     s.ylev = __dadd_rn(log(U[0]), s.fx0);                // y <- log(runif(1)) + f(x)
-    s.L = __dadd_rn(s.x0, -__dmul_rn(U[1], d.w));        // L <- x - runif(1) * w
-    s.R = __dadd_rn(s.L, d.w);                           // R <- L + w
+    s.L = __dadd_rn(s.x0, -__dmul_rn(U[1], s.w));        // L <- x - runif(1) * w
+    s.R = __dadd_rn(s.L, s.w);                           // R <- L + w
     s.ref_evals += 1;                                    // qslice's f(x0)
     if (d.max_steps < 0) { s.openL = s.openR = 1; s.Jb = s.Kb = 0.0; }
     else if (d.max_steps > 0) {
@@ -1123,7 +1129,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
             s.ref_evals++;
             if (f != f) { s.status = CGG_E_NAN; return false; }
             if (s.ylev < f) {
-                s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true;
+                s.L = __dadd_rn(s.L, -s.w); s.stepouts++; expanded = true;
                 if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; }
             } else s.openL = 0;
         }
@@ -1134,7 +1140,7 @@ __device__ __forceinline__ bool process_results(const Dev &d, int c, ChainState 
             s.ref_evals++;
             if (f != f) { s.status = CGG_E_NAN; return false; }
             if (s.ylev < f) {
-                s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true;
+                s.R = __dadd_rn(s.R, s.w); s.stepouts++; expanded = true;
                 if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; }
             } else s.openR = 0;
         }
@@ -1189,7 +1195,7 @@ enum JetOutcome : int { JET_EXACT = 0, JET_ACCEPTED = 1, JET_RETRY = 2 };
 // evaluations and the comparisons remain on the chain's critical cycle.
 // Lane roles of the first round: lanes 0..3 test L0 - i w, lanes 4..7 test R0 + i w, lanes 8..31 are the first 24 shrink
 // proposals drawn from the bracket (L0, R0) -- valid iff stepping out does not move it, the common case.
-__device__ __forceinline__ void jet_prepare(const Dev &d, int c, int lane, int j, uint64_t cursor, double x0, JetLane &jl, JetScal &sc) {
+__device__ __forceinline__ void jet_prepare(const Dev &d, int c, int lane, int j, uint64_t cursor, double x0, double w, JetLane &jl, JetScal &sc) {
     sc.x0 = x0; sc.cursor = cursor; sc.j = j;
     double uA = 0.5, uB = 0.5;
     const bool okA = draw_uniform(d, c, cursor + lane, uA);
@@ -1199,8 +1205,8 @@ __device__ __forceinline__ void jet_prepare(const Dev &d, int c, int lane, int j
     jl.uA = uA; jl.uB = uB;
     const double u0 = __shfl_sync(0xffffffffu, uA, 0), u1 = __shfl_sync(0xffffffffu, uA, 1), u2 = __shfl_sync(0xffffffffu, uA, 2);
     sc.logu = log(u0);                                    // y <- log(runif(1)) + f(x)
-    sc.L0 = __dadd_rn(x0, -__dmul_rn(u1, d.w));           // L <- x - runif(1) * w
-    sc.R0 = __dadd_rn(sc.L0, d.w);                        // R <- L + w
+    sc.L0 = __dadd_rn(x0, -__dmul_rn(u1, w));             // L <- x - runif(1) * w
+    sc.R0 = __dadd_rn(sc.L0, w);                          // R <- L + w
     sc.prior_x0 = prior_logdens(d.prior, x0);
     if (d.max_steps < 0) { sc.openL = sc.openR = 1; sc.Jb = sc.Kb = 0.0; }
     else if (d.max_steps > 0) {
@@ -1223,7 +1229,7 @@ __device__ __forceinline__ void jet_prepare(const Dev &d, int c, int lane, int j
         const bool left = lane < JET_R1_SO;
         const int i = left ? lane : lane - JET_R1_SO;
         double v = left ? sc.L0 : sc.R0;
-        const double step = left ? -d.w : d.w;
+        const double step = left ? -w : w;
         for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
         xi = v; li = sc.L0; ri = sc.R0;
     }
@@ -1258,7 +1264,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     // ---- the update's draws and first-round points: prepared while the pass was running, or now
     JetLane jl; JetScal sc;
     if (pre && pre->valid && pre->sc.j == s.j && pre->sc.cursor == s.cursor && pre->sc.x0 == x0) jet_pre_load(pre, lane, jl, sc);
-    else jet_prepare(d, c, lane, s.j, s.cursor, x0, jl, sc);
+    else jet_prepare(d, c, lane, s.j, s.cursor, x0, s.w, jl, sc);
     CGG_TICK(14);      // uniforms and points at hand
     const int base = base_draws(d);
     // start of the update (qslice::slice_stepping_out up to the first f(L) test; R/mcmcglm.R:258-261)
@@ -1276,7 +1282,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     // verdict on candidate v with log-prior pv; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
     auto verdict = [&](double v, double pv, bool &in, bool &out, double &fnew) {
         double B;
-        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B, light);
+        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B, light, d.jet_ce);
         B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
         if (light) {
             const double t = dl + (pv - prior_x0);
@@ -1300,10 +1306,10 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
             if (!tin && !tout) return false;
             s.ref_evals++;
             if (left) {           // while (y < f(L)) L <- L - w   [&& J > 0 when max is finite]
-                if (tin) { s.L = __dadd_rn(s.L, -d.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; } }
+                if (tin) { s.L = __dadd_rn(s.L, -s.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Jb -= 1.0; if (!(s.Jb > 0.0)) s.openL = 0; } }
                 else s.openL = 0;
             } else {
-                if (tin) { s.R = __dadd_rn(s.R, d.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; } }
+                if (tin) { s.R = __dadd_rn(s.R, s.w); s.stepouts++; expanded = true; if (d.max_steps > 0) { s.Kb -= 1.0; if (!(s.Kb > 0.0)) s.openR = 0; } }
                 else s.openR = 0;
             }
         }
@@ -1326,7 +1332,7 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
             const bool left = lane < 16;
             const int i = lane & 15;
             double v = left ? s.L : s.R;
-            const double step = left ? -d.w : d.w;
+            const double step = left ? -s.w : s.w;
             for (int t = 0; t < i; ++t) v = __dadd_rn(v, step);
             bool in2 = false, out2 = false; double f2;
             if (left ? s.openL : s.openR) verdict(v, prior_logdens(d.prior, v), in2, out2, f2);
@@ -1395,7 +1401,7 @@ __device__ __forceinline__ void decider_prephase(const Dev &d, int c, DeciderCac
     if (!want) { if (lane == 0) dc->pre.valid = 0; __syncwarp(); return; }
     if (dc->pre.valid && dc->pre.sc.j == dc->s.j && dc->pre.sc.cursor == dc->s.cursor && dc->pre.sc.x0 == dc->beta_j) return;   // (a retry of the same update)
     JetLane jl; JetScal sc;
-    jet_prepare(d, c, lane, dc->s.j, dc->s.cursor, dc->beta_j, jl, sc);
+    jet_prepare(d, c, lane, dc->s.j, dc->s.cursor, dc->beta_j, dc->s.w, jl, sc);
     jet_pre_store(&dc->pre, lane, jl, sc);
 }
 

@@ -9,7 +9,8 @@
 // and h = delta / cs
 //     sum_i l(eta_i + xs_i h) = sum_{k=0..D} M_k h^k / k!  +  R_D(h),     M_k = sum_i xs_i^k l^(k)(eta_i; y_i),
 //     |R_D(h)| <= |h|^(D+1)/(D+1)! * sum_i |xs_i|^(D+1) sup|l^(D+1)|.
-// The pass accumulates M_0..M_D (M_0 with the very row routine the exact passes use, so it IS the exact
+// The pass accumulates M_0..M_D (M_0 with the row routine the exact passes use -- poisson: the same expression with a
+// branch-free exp that agrees with libdevice's to ~2 ulp of mu, inside the bound's rounding envelope -- so it is the
 // f(x0) the reference's first evaluation returns) plus the few sums the error bound needs.  jet_eval() returns
 // the surrogate value and a bound B on |surrogate - what an exact fp64 pass would return|; the decider
 // accepts / rejects a candidate from the surrogate only when the comparison with the slice level holds with
@@ -33,7 +34,9 @@ constexpr int JET_NV = CGG_KMAX + 2;       // same number of accumulators as a c
 constexpr int CS_STRIDE = 12;              // per-column statistics: {cs, 1/cs, S_1..S_8, max|x|, C1 = sum xs (y - 1/2)}
 constexpr double JET_AMAX = 8.0;           // the enclosure is only used for |h| <= JET_AMAX (binomial, poisson)
 constexpr double JET_EPS = 1.1102230246251565e-16;   // 2^-53
-constexpr double JET_CROUND = 256.0;       // rounding allowance of one accumulated moment, in units of eps * sum|terms|
+constexpr double JET_CROUND = 256.0;       // least rounding allowance of one accumulated moment, in units of eps * sum|terms|: the engine
+                                           // passes jet_eval the larger of this and what the summation depth of the run needs (Dev::jet_ce:
+                                           // rows per lane + the warp / CTA / grid folds; n > ~1.4e7 rows per GPU exceed 256)
 constexpr int JET_DL = 3;                  // order of the binomial LIGHT pass
 constexpr double JET_LIGHT_EPS = 2e-11;    // absolute error of sigmoid-derived quantities (ua, v, v ua) in a light pass: the reciprocal
                                            // seed is taken from the high word of 1 + T (>= 2^-19.5 relative), one Newton step squares it;
@@ -250,10 +253,10 @@ __device__ __forceinline__ double rform_noise_sum(unsigned risk_key, unsigned ro
 // two exact evaluations.  B is +Inf (or NaN) when the enclosure does not apply: the caller must treat any comparison
 // that is not strictly decided as undecided.
 __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV], const double *cst, double n, double inv_sd,
-                                           double delta, double fmag, double &B, bool light = false) {
+                                           double delta, double fmag, double &B, bool light = false, double ce_in = 0.0) {
     const double h = delta * cst[1];
     const double a = fabs(h);
-    const double ce = JET_CROUND * JET_EPS;
+    const double ce = fmax(ce_in, JET_CROUND * JET_EPS);
     if (family == CGG_GAUSSIAN) {
         const double dl = h * fma(0.5 * h, m[2], m[1]);
         // moments: sum|xs z|/sd <= sqrt(S_2 * 2|M_0|)/sd, |M_2|
@@ -300,7 +303,7 @@ __device__ __forceinline__ double jet_eval(int family, const double (&m)[JET_NV]
     const double a2 = a * a, a4 = a2 * a2;
     const double bt = ea * (a4 * a2 * a) * JET_IFACT[7] * m[7] * (1.0 + 1e-6);
     // every term of every moment, of the exact passes and of their t-rounding is bounded by e^a (1 + 2a) (|y| + mu)(|eta| + 1)
-    const double brnd = (JET_CROUND + 100.0) * JET_EPS * ea * (1.0 + 2.0 * a) * m[8];
+    const double brnd = (ce + 100.0 * JET_EPS) * ea * (1.0 + 2.0 * a) * m[8];
     B = 1.01 * (bt + brnd);
     if (!(a <= JET_AMAX) || m[9] != 0.0) B = INFINITY;
     return dl;

@@ -173,13 +173,22 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 // request its first tiles now, before this pair's sums are reduced and delivered
                 const bool was_pref = pair_prefetched;
                 pair_prefetched = false;
+                // which pair comes next, and in which round
+                int c2 = -1; unsigned long long nround = round;
+                if (d.C >= 6) {                   // with one or two pairs the next decision is never there yet: the look would only cost
+                    if (c + 2 >= d.C) { c2 = 0; nround = round + 1; }           // this is the last item of the round
+                    else if (c + 3 < d.C) { c2 = c + 2; }                      // another pair follows
+                    if (c2 == c) c2 = -1;                                      // (a single chain follows: it needs the ring)
+                }
+                // One warp of the CTA (a different one every pass) fetches the next pair's control blocks right after its own
+                // first tiles were requested -- its round trips to L2 overlap the tiles' -- so that by the time the CTA's
+                // warps finish this pair, the blocks are in shared memory and every warp can request the next pair's first
+                // tiles at once (a look at the END of the pass only served the warps that finished after the fetch: 25 %).
+                auto early = [&]() {
+                    if (c2 >= 0 && warp == (int)((round + (unsigned long long)(c >> 1)) % NWARPS)) pair_lookahead(d, sh, c2, nround, lane);
+                };
                 auto after = [&]() {
-                    if (d.C < 6) return;          // with one or two pairs the next decision is never there yet: the look would only cost
-                    int c2; unsigned long long nround;
-                    if (c + 2 >= d.C) { c2 = 0; nround = round + 1; }           // this was the last item of the round
-                    else if (c + 3 < d.C) { c2 = c + 2; nround = round; }      // another pair follows
-                    else return;                                               // a single chain follows: it needs the ring
-                    if (c2 == c) return;
+                    if (c2 < 0) return;
                     if (!pair_lookahead(d, sh, c2, nround, lane)) return;
                     const double *nA = sh.ctl + c2 * CTL_WORDS;
                     if (!pair_batchable(nA, nA + CTL_WORDS)) return;
@@ -187,8 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     ns.prologue(false);
                     pair_prefetched = true;
                 };
-                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, after, acc, acc2);
-                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, after, acc, acc2);
+                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, early, after, acc, acc2);
+                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, early, after, acc, acc2);
                 any = true;
                 n_pref += pair_prefetched ? 1 : 0;
                 long long tC = prof ? clock64() : 0;
@@ -593,7 +602,7 @@ __global__ void jet_debug_kernel(Dev d, int c, int j, int K, int light, double f
     if (lane < K) {
         double B;
         const double fmag = light ? fmag_light : fabs(m[0]);
-        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, d.n_total, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B, light != 0);
+        const double dl = jet_eval(d.family, m, d.colstat + (int64_t)j * CS_STRIDE, d.n_total, d.inv_sd, __dadd_rn(cand[lane], -x0), fmag, B, light != 0, d.jet_ce);
         out[lane] = light ? dl : (m[0] + dl) + (d.sharded ? 0.0 : d.ll_const);
         out[K + lane] = B * d.jet_bscale + 8.0 * JET_EPS * (fmag + fabs(dl));
     }
@@ -688,6 +697,8 @@ struct cgg_handle {
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
     ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr; size_t gather_cap = 0;
     double local_ll_const = 0.0;
+    std::vector<double> w_chain;          // per-chain slice widths (cgg_set_chain_w); default cfg.w
+    std::vector<ChainState> last_cs;      // the chains' counters after the last cgg_run (cgg_get_chain_stats)
 };
 
 extern "C" const char *cgg_last_error(void) { return g_err.c_str(); }
@@ -815,6 +826,13 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (G < 1) G = 1;
     d.G = (int)G;
     d.lde = (d.n + 31) / 32 * 32;
+    {   // rounding allowance of an accumulated moment: one rounding per add along the longest chain of additions a value goes
+        // through -- the rows a lane owns, then the warp, CTA and (row-sharded: rank) folds; the grid fold is exact (limb
+        // accumulators / fixed-point accumulators).  Twice that, and never less than JET_CROUND.
+        const double depth = std::ceil((double)d.n / ((double)d.G * NWARPS * 32.0)) + 5.0 + NWARPS + 64.0;
+        d.jet_ce = std::max(JET_CROUND, 2.0 * depth) * JET_EPS;
+    }
+    h->w_chain.assign(C, cfg->w);
 
     // stream-ordered pool allocations (the pool keeps freed memory cached, see above): creating and destroying a handle
     // costs no device-wide synchronising cudaMalloc / cudaFree
@@ -1278,6 +1296,28 @@ extern "C" int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, co
     return CGG_OK;
 }
 
+extern "C" int cgg_set_chain_w(cgg_handle *h, const double *w_host) {
+    if (!h || !w_host) return fail(CGG_E_ARG, "cgg_set_chain_w: NULL argument");
+    for (int c = 0; c < h->d.C; ++c)
+        if (!(w_host[c] > 0.0) || !std::isfinite(w_host[c])) return fail(CGG_E_ARG, "cgg_set_chain_w: w[%d] must be positive and finite", c);
+    h->w_chain.assign(w_host, w_host + h->d.C);
+    return CGG_OK;
+}
+
+extern "C" int cgg_get_chain_stats(cgg_handle *h, int32_t chain, cgg_stats *out) {
+    if (!h || !out) return fail(CGG_E_ARG, "cgg_get_chain_stats: NULL argument");
+    if (chain < 0 || chain >= h->d.C) return fail(CGG_E_ARG, "cgg_get_chain_stats: chain %d out of range", chain);
+    if ((int)h->last_cs.size() != h->d.C) return fail(CGG_E_STATE, "cgg_get_chain_stats: no cgg_run yet");
+    const ChainState &cs = h->last_cs[chain];
+    memset(out, 0, sizeof *out);
+    out->updates = cs.updates; out->passes = cs.passes; out->chain_passes = cs.chain_passes; out->commit_passes = cs.commit_passes;
+    out->cand_evals = cs.cand_evals; out->ref_evals = cs.ref_evals; out->stepouts = cs.stepouts; out->shrinks = cs.shrinks;
+    out->coarse_evals = cs.coarse_evals; out->coarse_undecided = cs.coarse_undecided;
+    out->jet_passes = cs.jet_passes; out->jet_fallbacks = cs.jet_fallbacks; out->jet_retries = cs.jet_retries;
+    out->algorithmic_bytes = 8.0 * (double)h->d.n * (3.0 * (double)cs.chain_passes + 2.0 * (double)cs.commit_passes);
+    return CGG_OK;
+}
+
 extern "C" void *cgg_stream(cgg_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 extern "C" int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads) {
@@ -1342,6 +1382,8 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         cs[c].ref_evals = cs[c].stepouts = cs[c].shrinks = cs[c].passes = cs[c].coarse_evals = cs[c].coarse_undecided = 0;
         cs[c].jet_passes = cs[c].jet_fallbacks = cs[c].jet_retries = 0;
         cs[c].fine_next = 0; cs[c].jet_skip = 0;
+        cs[c].w = h->w_chain[c];
+        d.replay_origin[c] = cs[c].cursor;
         ctl[c].commit_j = -1;
     }
     Hdr hdr;
@@ -1485,6 +1527,11 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         if (cs[c].status != CGG_OK && bad == CGG_OK) { bad = cs[c].status; bad_chain = c; }
     }
     if (d.jet_light && d.family == CGG_BINOMIAL) std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);   // carried f(x0) is a surrogate value
+    h->last_cs = cs;
+    // a chain that failed on the device stopped in the middle of an update (its beta may be ahead of its eta): it has to
+    // be initialised again before it can run (cgg_init_chain / cgg_set_state)
+    for (int c = 0; c < C; ++c)
+        if (cs[c].status != CGG_OK || hdr.abort) { h->chain_init[c] = 0; h->fx_valid[c] = 0; h->fx_mag[c] = 0; }
     st.launches = launches; st.sweep_ms = ms;
     st.algorithmic_bytes = 8.0 * (double)d.n * (3.0 * (double)st.chain_passes + 2.0 * (double)st.commit_passes);
     if (stats) *stats = st;

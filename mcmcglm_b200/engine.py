@@ -164,6 +164,19 @@ class Engine:
         L.check(rc)
         return samples, d
 
+    def set_chain_w(self, w):
+        """Per-chain slice widths (one engine run serves a whole tuning sweep); w: n_chains values."""
+        w = _f64(w)
+        if w.shape != (self.n_chains,):
+            raise L.CggError(L.E_ARG, f"w has shape {w.shape}, expected {(self.n_chains,)}")
+        L.check(self._lib.cgg_set_chain_w(self._h, w.ctypes.data_as(_dp)))
+
+    def chain_stats(self, chain):
+        """Counters of one chain from the last run (ref_evals = qslice's nEvaluations)."""
+        st = L.Stats()
+        L.check(self._lib.cgg_get_chain_stats(self._h, chain, C.byref(st)))
+        return st.as_dict()
+
     def launch_shape(self):
         a, b = C.c_int32(), C.c_int32()
         L.check(self._lib.cgg_launch_shape(self._h, C.byref(a), C.byref(b)))

@@ -73,3 +73,35 @@ def test_g3_logistic_recovers_truth_and_chains_agree():
     se = S.reshape(-1, 4).std(0)
     assert np.all(np.abs(m - m.mean(0)) < 0.35 * se)     # chains agree within Monte-Carlo error
     assert np.all(np.abs(m.mean(0) - bt) < 4 * se)       # and sit on the generating coefficients
+
+
+def test_tuning_sweep_is_one_engine_run_with_per_chain_w():
+    """mcmcglm_across_tuningparams (R/slice_utilities.R:43-85): the values of w become the chains of one engine run.
+    Each chain must be exactly the chain a single run with that w produces (same Philox substream, same start), and
+    the evaluation counts qslice reports per value (dropped by the reference at R/mcmcglm.R:261) come back per value."""
+    X, y, _ = synth("binomial", 3000, 4, seed=4)
+    m = oracle.make_model("binomial", **PRIOR_CASES["normal"])
+    ws = [0.05, 0.2, 0.5, 1.5, 4.0]
+    rng = np.random.default_rng(9)
+    beta0 = 0.3 * rng.standard_normal((len(ws), 4))
+    from mcmcglm_b200 import Engine
+    with Engine(3000, 4, family="binomial", w=123.0, n_chains=len(ws), K=8, seed=21, **PRIOR_CASES["normal"]) as e:
+        e.set_data(X, y)
+        e.set_chain_w(ws)
+        for c in range(len(ws)):
+            e.init_chain(c, beta0[c])
+        S, st = e.run(25)
+        per = [e.chain_stats(c) for c in range(len(ws))]
+    for c, w in enumerate(ws):
+        ref = oracle.run_chain(m, X, y, beta0[c], w=w, n_iter=25, seed=21, chain=c)
+        assert np.max(np.abs(S[c] - ref["samples"])) <= 1e-9, w
+        assert per[c]["ref_evals"] == ref["n_eval"] and per[c]["stepouts"] == ref["n_stepout"] and per[c]["shrinks"] == ref["n_shrink"]
+    assert sum(p_["ref_evals"] for p_ in per) == st["ref_evals"]
+    assert per[0]["stepouts"] > per[-1]["stepouts"] and per[-1]["shrinks"] > per[0]["shrinks"]     # narrow w steps out, wide w shrinks
+    # and through the front door
+    dat = pd.DataFrame({"Y": y, "A": X[:, 1], "B": X[:, 2], "C": X[:, 3]})
+    fits = mg.mcmcglm_across_tuningparams(ws, tuning_parameter_name="w", formula="Y ~ .", family="binomial", data=dat,
+                                          n_samples=40, burnin=5, seed=3)
+    assert [f.w for f in fits] == ws and all(len(mg.samples(f)) == 41 for f in fits)
+    assert all(f.stats["nEvaluations"] > 0 for f in fits)
+    assert not np.array_equal(mg.samples(fits[0]).iloc[:, :4].to_numpy(), mg.samples(fits[1]).iloc[:, :4].to_numpy())
