@@ -55,7 +55,10 @@ enum { CGG_PRIOR_NORMAL = 0, CGG_PRIOR_LAPLACE = 1, CGG_PRIOR_STUDENT_T = 2 };
 /* how the sweep is driven on the device */
 enum {
     CGG_DRIVER_PERSISTENT = 0, /* one cooperative kernel runs all sweeps; per-chain flags, no grid barrier */
-    CGG_DRIVER_STEPWISE = 1    /* one launch per pass; the last CTA to finish decides */
+    CGG_DRIVER_STEPWISE = 1,   /* one launch per pass; the last CTA to finish decides */
+    CGG_DRIVER_CLUSTER = 2     /* small n: one thread-block cluster per chain, sums exchanged through distributed shared
+                                  memory, every CTA runs the chain's decisions itself (no global synchronisation).
+                                  CGG_DRIVER_PERSISTENT selects it by itself for n <= 2^18 rows (CGG_SMALLN=0 disables) */
 };
 /* how rows are distributed */
 enum {
@@ -68,6 +71,7 @@ enum {
 #define CGG_FLAG_NO_PREFILTER 1 /* score every candidate in fp64 (the fp32 pre-filter never changes results, only cost) */
 #define CGG_FLAG_NO_JET 2       /* decide every candidate from an exact pass over the rows (jet passes never change
                                    results, only cost: one pass per update instead of one per few candidates) */
+#define CGG_FLAG_NO_CLUSTER 8   /* CGG_DRIVER_PERSISTENT: always the grid-wide kernel, also for small n (tests; never changes results) */
 #define CGG_FLAG_NO_JET_LIGHT 4 /* binomial: every jet pass also evaluates the exact f(x0) (light passes skip it because
                                    the slice tests only involve differences f(v) - f(x0); never changes results) */
 

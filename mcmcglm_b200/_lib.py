@@ -12,11 +12,12 @@ OK, E_ARG, E_UNSUPPORTED, E_CUDA, E_NAN, E_STREAM, E_NOTERM, E_STATE, E_COMM = 0
 GAUSSIAN, BINOMIAL, POISSON = 0, 1, 2
 LINK_IDENTITY, LINK_LOGIT, LINK_LOG = 0, 1, 2
 PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2
-DRIVER_PERSISTENT, DRIVER_STEPWISE = 0, 1
+DRIVER_PERSISTENT, DRIVER_STEPWISE, DRIVER_CLUSTER = 0, 1, 2
 MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 FLAG_NO_PREFILTER = 1
 FLAG_NO_JET = 2
 FLAG_NO_JET_LIGHT = 4
+FLAG_NO_CLUSTER = 8
 JET_NV = KMAX + 2
 
 # every symbol include/cggibbs.h declares

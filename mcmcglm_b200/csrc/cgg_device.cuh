@@ -122,7 +122,8 @@ struct Dev {
     double jet_ce;             // rounding allowance of one accumulated moment, relative to the sum of its terms' magnitudes (cgg_create: from the summation depth)
     uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
     PriorParams prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, pad_;   // pair: chains 2k, 2k+1 share a pass when they can
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache;   // pair: chains 2k, 2k+1 share a pass when they can;
+                                                                                                  // colcache: tiles per slot of the per-warp X-column cache (0: off)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -221,7 +222,8 @@ struct ChainStream {
         y = d.y; eta = d.eta + (int64_t)c * d.lde;
         // with pair passes on, both chains of a pair use the even chain's rotation in EVERY kind of pass (PairStream does the
         // same), so a chain's eta rows keep their owner warp when it moves between pair passes and single passes
-        W = W_; vw = (wid + (long long)(d.pair ? (c & ~1) : c) * (W / d.C)) % W; n_tiles = d.n_tiles; n = d.n;
+        // ... and with the X-column cache on (ColCache) there is no rotation at all: a warp's cached tiles serve every pair
+        W = W_; vw = d.colcache ? wid : (wid + (long long)(d.pair ? (c & ~1) : c) * (W / d.C)) % W; n_tiles = d.n_tiles; n = d.n;
         slot0 = ring + (uint32_t)lane * 16u;
     }
     __device__ __forceinline__ void issue(long long T, int stage, int lane) const {
@@ -482,6 +484,21 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
 // X_commit tiles are staged once and serve both chains (the chains of a GPU run in lock-step in the stationary regime),
 // the per-tile loop overhead and the pipeline fill are paid once, and the two chains' rows are independent work for the
 // scheduler.  Ring stage layout: [eta_A, eta_B, y, X_j, X_commit] x 512 B.
+// The X-column cache.  The tiles a warp owns are the same rows for every chain and every column (when the cache is on the
+// tile -> warp map has no per-chain rotation), and its share of one column is small: n = 1e6 rows over 1176 warps is 14
+// tiles = 7 KB.  Every warp therefore keeps TWO columns of its rows in shared memory, tagged with their column index:
+// the column being sampled (filled by the first pair pass that walks it, served to the other pairs of the GPU) and the
+// previous one, which is the next passes' X_commit.  In the lock-step stationary regime a column is then read from L2
+// ONCE per warp instead of 8 times (4 pair passes as X_j, 4 as X_commit), which matters because with eta pinned in L2 the
+// kernel is bound by L2 bandwidth (~8 TB/s measured): per pair pass 2 eta reads + 2 eta writes remain, instead of 5 reads
+// + 2 writes.  Private to the warp: a lane only ever reads back the 16-byte slots it filled itself, so -- like the
+// staging ring -- it needs no barrier.  A miss (chains out of step, an exact pass in between) just streams as before.
+struct ColCache {
+    uint32_t base;             // shared-space address of this warp's cache + this lane's 16 bytes; slot s, tile t at base + (s * cap + t) * 512
+    int cap;                   // tiles per slot; 0: the cache is off
+    int tag0, tag1;            // column held (completely) by slot 0 / slot 1; -1: none
+    int fill_col, fill_slot;   // a fill in progress (begun by a prologue that was issued early); -1: none
+};
 struct PairStream {      // running pointers of a pair pass: the tile to be issued next
     const double *pa, *pb, *py, *px, *pc;
     const double *pa_last, *pa_end;
@@ -489,73 +506,107 @@ struct PairStream {      // running pointers of a pair pass: the tile to be issu
     const double *xj, *xc;
     long long vw;
     int64_t step;
-    int cj;
+    int cj, j;
     uint32_t sbase;
-    __device__ __forceinline__ PairStream(const Dev &d, int c0, const double *cwA, long long wid, long long W, int lane, uint32_t ring) {
+    uint32_t xj_slot, xc_slot; // cache slots serving X_j / X_commit (this lane's column)
+    int sj;                    // cache slot index of X_j (-1: staged through the ring)
+    int t_issue;               // index (within this warp's tiles) of the tile to be issued next
+    bool need_y, xj_ring, xc_ring, fillJ;
+    __device__ __forceinline__ PairStream(const Dev &d, int c0, const double *cwA, long long wid, long long W, int lane, uint32_t ring, ColCache &cc, bool with_y) {
         const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
-        const int j = (int)(w0 & 0xffffffffLL);
+        j = (int)(w0 & 0xffffffffLL);
         cj = (int)(w1 & 0xffffffffLL);
         etaA = d.eta + (int64_t)c0 * d.lde; etaB = etaA + d.lde;
         xj = d.X + (int64_t)j * d.ldx; xc = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
-        vw = (wid + (long long)(c0 & ~1) * (W / d.C)) % W;      // == ChainStream's rotation of c0 and of c0 + 1 (d.pair is on)
+        vw = d.colcache ? wid : (wid + (long long)(c0 & ~1) * (W / d.C)) % W;      // == ChainStream's map of c0 and of c0 + 1 (d.pair is on)
         sbase = ring + (uint32_t)lane * 16u;
         step = W * TILE_ROWS;
         const int64_t i0 = vw * TILE_ROWS + 2 * lane;
         pa = etaA + i0; pb = etaB + i0; py = d.y + i0; px = xj + i0; pc = xc + i0;
         pa_last = etaA + (d.n - 1);
         pa_end = etaA + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
+        need_y = with_y; t_issue = 0;
+        // ---- where X_j and X_commit come from
+        sj = -1; fillJ = false; xj_ring = true; xc_ring = cj >= 0; xj_slot = xc_slot = 0;
+        if (cc.cap > 0) {
+            xj_ring = false;
+            if (cc.tag0 == j) sj = 0;
+            else if (cc.tag1 == j) sj = 1;
+            else if (cc.fill_col == j) { sj = cc.fill_slot; fillJ = true; }
+            else {                                     // miss: fill the slot that does not hold the commit column
+                sj = (cj >= 0 && cc.tag0 == cj) ? 1 : 0;
+                if (sj == 0) cc.tag0 = -1; else cc.tag1 = -1;
+                cc.fill_col = j; cc.fill_slot = sj; fillJ = true;
+            }
+            xj_slot = cc.base + (uint32_t)(sj * cc.cap) * 512u;
+            if (cj >= 0) {
+                const int sc = (cc.tag0 == cj) ? 0 : ((cc.tag1 == cj) ? 1 : -1);
+                if (sc >= 0) { xc_ring = false; xc_slot = cc.base + (uint32_t)(sc * cc.cap) * 512u; }
+            }
+        }
     }
     __device__ __forceinline__ void issue_next(unsigned st) {
         if (pa < pa_last) {
             const uint32_t sa = sbase + st * (RING_OPS * 512u);
             cp_async16(sa, pa); cp_async16(sa + 512u, pb);
-            cp_async16(sa + 1024u, py); cp_async16(sa + 1536u, px);
-            if (cj >= 0) cp_async16(sa + 2048u, pc);
+            if (need_y) cp_async16(sa + 1024u, py);
+            if (xj_ring) cp_async16(sa + 1536u, px);
+            else if (fillJ) cp_async16(xj_slot + (uint32_t)t_issue * 512u, px);
+            if (xc_ring) cp_async16(sa + 2048u, pc);
         }
         cp_async_commit();
         pa += step; pb += step; py += step; px += step; pc += step;
+        ++t_issue;
     }
     // first RING_D - 1 tiles: may be issued early (cross-pair prefetch); `skip`: they already were
     __device__ __forceinline__ void prologue(bool skip) {
-        if (skip) { const int64_t adv = (RING_D - 1) * step; pa += adv; pb += adv; py += adv; px += adv; pc += adv; return; }
+        if (skip) { const int64_t adv = (RING_D - 1) * step; pa += adv; pb += adv; py += adv; px += adv; pc += adv; t_issue += RING_D - 1; return; }
 #pragma unroll
         for (int s = 0; s < RING_D - 1; ++s) issue_next((unsigned)s);
+    }
+    // the pass is over (all copies have landed): a filled column becomes a cached one
+    __device__ __forceinline__ void finish(ColCache &cc) const {
+        if (fillJ) { if (sj == 0) cc.tag0 = j; else cc.tag1 = j; cc.fill_col = -1; }
     }
 };
 
 template <int FAMILY, bool FULL, class EARLY, class AFTER>
 __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const double *cwA, const double *cwB, long long wid, long long W,
-                                               int lane, uint32_t ring, const double2 *tab, bool prefetched, EARLY &&after_prologue,
+                                               int lane, uint32_t ring, const double2 *tab, bool prefetched, ColCache &cc, EARLY &&after_prologue,
                                                AFTER &&after_tiles, double (&mA)[NV], double (&mB)[NV]) {
     const double cdA = cwA[2], cdB = cwB[2], cscale = cwA[CTL_WORDS - 1];
     const int64_t n = d.n;
-    PairStream ps(d, c0, cwA, wid, W, lane, ring);
+    constexpr bool WITH_Y = FAMILY != CGG_BINOMIAL || FULL;        // a binomial light pass never looks at y (C1 carries it)
+    PairStream ps(d, c0, cwA, wid, W, lane, ring, cc, WITH_Y);
     const int cj = ps.cj;
     double *etaA = ps.etaA, *etaB = ps.etaB;
     constexpr uint32_t STAGE = RING_OPS * 512u;
-    static_assert(RING_OPS >= 5, "a pair pass stages five operands");
+    static_assert(RING_OPS >= 5, "a pair pass stages up to five operands");
 #pragma unroll
     for (int k = 0; k < NV; ++k) { mA[k] = 0.0; mB[k] = 0.0; }
     unsigned riskA = 0, riskB = 0, rows = 0;
     ps.prologue(prefetched);
     after_prologue();     // the first tiles are on their way: a good moment for a (blocking) look at the next pair's decision
     unsigned stage = 0;
+    uint32_t t_off = 0;   // byte offset of the tile being scored inside a cache slot
     auto score_tile = [&](unsigned st, int64_t off) {
         const uint32_t s = ps.sbase + st * STAGE;
         double2 ea = lds2(s), eb = lds2(s + 512u);
         if (cj >= 0) {
-            const double2 cv = lds2(s + 2048u);
+            const double2 cv = ps.xc_ring ? lds2(s + 2048u) : lds2(ps.xc_slot + t_off);
             ea.x = eta_shift(ea.x, cv.x, cdA); ea.y = eta_shift(ea.y, cv.y, cdA);
             eb.x = eta_shift(eb.x, cv.x, cdB); eb.y = eta_shift(eb.y, cv.y, cdB);
             *reinterpret_cast<double2 *>(etaA + off) = ea;
             *reinterpret_cast<double2 *>(etaB + off) = eb;
         }
-        const double2 yy = lds2(s + 1024u);
-        double2 xs = lds2(s + 1536u);
+        double2 yy = make_double2(0.0, 0.0);
+        if (WITH_Y) yy = lds2(s + 1024u);
+        double2 xs = ps.xj_ring ? lds2(s + 1536u) : lds2(ps.xj_slot + t_off);
         xs.x *= cscale; xs.y *= cscale;
         rows += 2;
         JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
         JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
+        t_off += 512u;
     };
 #if CGG_PAIR_TPI == 2
     for (; ps.pa < ps.pa_end; ) {
@@ -581,6 +632,7 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     }
 #endif
     cp_async_wait<0>();
+    ps.finish(cc);
     if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
         const int64_t t = n - 1;
         const long long Tl = t / TILE_ROWS;
@@ -706,8 +758,10 @@ struct CtaShared {                       // views into dynamic shared memory, si
     int *lock;                           // [C] elected poller of the chain's version flag
     double *sacc;                        // [NWARPS][KMAX][32] per-lane running sums of the chain pass in flight
     uint32_t ring0;                      // shared-space address of warp 0's ring
+    uint32_t cache0;                     // shared-space address of warp 0's X-column cache (behind everything else)
     __device__ __forceinline__ CtaShared(unsigned char *base, int C) {
         ring0 = (uint32_t)__cvta_generic_to_shared(base);
+        cache0 = ring0 + (uint32_t)((bytes(C) + 15) / 16 * 16);
         sacc = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
         part = sacc + NWARPS * KMAX * 32;
         ctl = part + (size_t)C * NWARPS * NV;
@@ -715,7 +769,7 @@ struct CtaShared {                       // views into dynamic shared memory, si
         cnt = reinterpret_cast<int *>(ver + C);
         lock = cnt + C;
     }
-    static size_t bytes(int C) {
+    __host__ __device__ static size_t bytes(int C) {
         return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * NWARPS * KMAX * 32 +
                (size_t)C * (sizeof(double) * (NWARPS * NV + CTL_WORDS) + sizeof(unsigned long long) + 2 * sizeof(int));
     }
@@ -1420,7 +1474,9 @@ __device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
     return v;
 }
 enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
-__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, DeciderCache *dc = nullptr) {
+// vals_in (with SRC_SLOTS): the pass's sums are handed over by the caller (cluster driver) instead of read from the limbs.
+__device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, DeciderCache *dc = nullptr,
+                                         const double *vals_in = nullptr) {
     const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
     // ---- control block, state, beta/shat of j and j+1: from the deciding warp's shared-memory cache if it has them,
@@ -1446,7 +1502,10 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     double jm[NV];        // the pass's sums, identical in every lane (slots source: all of them; else only for a jet pass)
     if (src == SRC_SLOTS) {
         const int nvals = jetpass ? jet_nvals(d.family, ((unsigned)ct.coarse_mask & JET_FULL) == 0u) : (cmask ? nc + 2 : nc);
-        if (!limbs_take(d, c, nvals, lane, dc->prev, jm)) return DEC_NOT_READY;  // some CTA's sums are still on their way: nothing was changed
+        if (vals_in) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) jm[k] = (k < nvals) ? vals_in[k] : 0.0;
+        } else if (!limbs_take(d, c, nvals, lane, dc->prev, jm)) return DEC_NOT_READY;  // some CTA's sums are still on their way: nothing was changed
     } else if (jetpass) {
         const double mv = (lane < NV) ? (from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
 #pragma unroll

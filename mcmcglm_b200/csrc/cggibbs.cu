@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     };
     double acc2[NV];
     bool pair_prefetched = false;
+    ColCache cc;        // this warp's X-column cache (pair passes); lives for the launch
+    cc.cap = d.colcache; cc.base = sh.cache0 + (uint32_t)warp * (uint32_t)(2 * d.colcache) * 512u + (uint32_t)lane * 16u;
+    cc.tag0 = cc.tag1 = -1; cc.fill_col = cc.fill_slot = -1;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
         for (int c = 0; c < d.C; ++c) {
@@ -192,12 +195,13 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     if (!pair_lookahead(d, sh, c2, nround, lane)) return;
                     const double *nA = sh.ctl + c2 * CTL_WORDS;
                     if (!pair_batchable(nA, nA + CTL_WORDS)) return;
-                    PairStream ns(d, c2, nA, wid, W, lane, ring);
+                    const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(nA[1]) >> 32)) & JET_FULL);
+                    PairStream ns(d, c2, nA, wid, W, lane, ring, cc, full2);
                     ns.prologue(false);
                     pair_prefetched = true;
                 };
-                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, early, after, acc, acc2);
-                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, early, after, acc, acc2);
+                if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
+                else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
                 any = true;
                 n_pref += pair_prefetched ? 1 : 0;
                 long long tC = prof ? clock64() : 0;
@@ -250,6 +254,108 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         // per-warp view: [16 + 4096 + 32*128*4 + (cta * NWARPS + warp) * 2 + {wait, tiles}]
         d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 0] = (unsigned long long)t_wait;
     }
+}
+
+// K3s (cluster driver, small n).  One thread-block CLUSTER per chain, no communication through global memory at all: the
+// S CTAs of a cluster split the chain's rows (the same tile -> warp ownership as everywhere else), every CTA sends its
+// sums of a pass into the shared memory of ALL CTAs of its cluster (distributed shared memory), one cluster barrier, and
+// then every CTA adds the S parts in rank order and runs the chain's decision ITSELF -- S identical, deterministic copies
+// of the state machine instead of one decision that has to be published, polled for and fetched.  With n = 1e5 a pass is
+// ~1-2 us of streaming, so the grid-wide protocol of the persistent driver (decider CTA, limb accumulators, version flags:
+// ~10 us per update and chain) is all latency; here an update is pass + barrier + decision.  The global side effects of a
+// decision (beta, slice-width estimate, sample store) are written by every CTA with identical values, so each CTA reads
+// back what it wrote itself.  Chains do not interact: C clusters run concurrently (or in waves), no cooperative launch.
+constexpr int CLUSTER_MAX = 16;
+struct ClusterShared {
+    double *sacc, *part, *xs, *ctl, *vals;
+    DeciderCache *dc;
+    uint32_t ring0;
+    __device__ __forceinline__ ClusterShared(unsigned char *base) {
+        ring0 = (uint32_t)__cvta_generic_to_shared(base);
+        sacc = reinterpret_cast<double *>(base + NWARPS * RING_BYTES_PER_WARP);
+        part = sacc + NWARPS * KMAX * 32;              // [NWARPS][NV] the warps' partial sums
+        xs = part + NWARPS * NV;                       // [2][CLUSTER_MAX][NV] every CTA's sums of the pass, double-buffered by pass parity
+        ctl = xs + 2 * CLUSTER_MAX * NV;               // [CTL_WORDS] the control block of the coming pass
+        vals = ctl + CTL_WORDS;                        // [NV] the pass's totals
+        dc = reinterpret_cast<DeciderCache *>(vals + NV + 1);
+    }
+    static size_t bytes() {
+        return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * (NWARPS * KMAX * 32 + NWARPS * NV + 2 * CLUSTER_MAX * NV + CTL_WORDS + NV + 2) + sizeof(DeciderCache) + 16;
+    }
+};
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t local_smem_addr, unsigned rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+template <int FAMILY>
+__global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_constant__ Dev d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double2 s_l1p[MATH_TAB_N];
+    ClusterShared sh(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int S = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+    const int c = (int)blockIdx.x / S;                 // one cluster per chain
+    load_l1p_table(s_l1p);
+    for (int i = threadIdx.x; i < CTL_WORDS; i += THREADS) sh.ctl[i] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + i);
+    if (threadIdx.x == 0) { sh.dc->valid = 0; sh.dc->pref_j = -1; sh.dc->pre.valid = 0; }
+    __syncthreads();
+    // warp 0 is the CTA's decider (it prepares the coming decision while the other warps stream the rows); warps 1.. are the workers
+    constexpr int NWORK = NWARPS - 1;
+    const long long wid = (long long)rank * NWORK + (warp - 1), W = (long long)S * NWORK;
+    const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
+    const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(sh.xs);
+    double acc[NV];
+    for (unsigned long long pass = 0;; ++pass) {
+        int nc = 0;
+        if (warp > 0) {
+            int j;
+            bool prefetched = false;
+            NoLookAhead nola;
+            nc = worker_pass<FAMILY>(d, c, sh.ctl, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j, prefetched, 0, &nola);
+            if (nc > 0 && lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) if (k < nc) sh.part[warp * NV + k] = acc[k];
+            }
+        } else {
+            // what worker_pass will return for this control block (the decider does not stream)
+            const long long w0 = __double_as_longlong(sh.ctl[0]), w1 = __double_as_longlong(sh.ctl[1]);
+            const int j = (int)(w0 & 0xffffffffLL), ncand = (int)(w0 >> 32), cj = (int)(w1 & 0xffffffffLL);
+            const unsigned cmask = (unsigned)(w1 >> 32);
+            nc = (j < 0) ? -1 : ((cmask & JET_BIT) ? jet_nvals(FAMILY, !(cmask & JET_FULL)) : ((ncand == 0 && cj < 0) ? 0 : ncand));
+            if (nc >= 0 && sh.dc->valid) { decider_prefetch(d, c, sh.dc, lane); decider_prephase(d, c, sh.dc, lane); }
+        }
+        if (nc < 0) break;                             // the chain has finished (every thread of the cluster sees the same block)
+        __syncthreads();
+        // CTA fold in warp order, then the CTA's sums go to slot [parity][rank] of every CTA of the cluster
+        const int par = (int)(pass & 1ULL);
+        if (warp == 0 && lane < nc) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 1; w < NWARPS; ++w) v += sh.part[w * NV + lane];
+            for (int r = 0; r < S; ++r) st_cluster_f64(xs_addr + (uint32_t)(((par * CLUSTER_MAX + rank) * NV + lane) * 8), (unsigned)r, v);
+        }
+        cluster_barrier();
+        if (warp == 0) {
+            if (lane < NV) {
+                double v = 0.0;
+                if (lane < nc) for (int r = 0; r < S; ++r) v += sh.xs[(par * CLUSTER_MAX + r) * NV + lane];       // rank order: identical in every CTA
+                sh.vals[lane] = v;
+            }
+            __syncwarp();
+            decide_chain(&d, c, lane, -1, SRC_SLOTS, sh.dc, sh.vals);
+            if (lane < CTL_WORDS) sh.ctl[lane] = reinterpret_cast<const double *>(&sh.dc->ct)[lane];
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    cluster_barrier();      // nobody leaves while a peer may still write into its shared memory
 }
 
 // Stepwise driver: one pass of every chain per launch; the last CTA to finish decides.
@@ -697,6 +803,8 @@ struct cgg_handle {
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
     ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr; size_t gather_cap = 0;
     double local_ll_const = 0.0;
+    int cluster_S = 0;                    // > 0: the cluster driver runs the sweeps, with this many CTAs per chain
+    size_t cluster_smem = 0;
     std::vector<double> w_chain;          // per-chain slice widths (cgg_set_chain_w); default cfg.w
     std::vector<ChainState> last_cs;      // the chains' counters after the last cgg_run (cgg_get_chain_stats)
 };
@@ -704,14 +812,17 @@ struct cgg_handle {
 extern "C" const char *cgg_last_error(void) { return g_err.c_str(); }
 extern "C" int cgg_abi_version(void) { return CGG_ABI_VERSION; }
 
-static void *kernel_ptr(int family, int which) {
-    switch (family * 2 + which) {
-    case CGG_GAUSSIAN * 2 + 0: return (void *)sweep_persistent_kernel<CGG_GAUSSIAN>;
-    case CGG_GAUSSIAN * 2 + 1: return (void *)pass_kernel<CGG_GAUSSIAN>;
-    case CGG_BINOMIAL * 2 + 0: return (void *)sweep_persistent_kernel<CGG_BINOMIAL>;
-    case CGG_BINOMIAL * 2 + 1: return (void *)pass_kernel<CGG_BINOMIAL>;
-    case CGG_POISSON * 2 + 0: return (void *)sweep_persistent_kernel<CGG_POISSON>;
-    default: return (void *)pass_kernel<CGG_POISSON>;
+static void *kernel_ptr(int family, int which) {     // which: 0 persistent sweep, 1 single pass, 2 cluster sweep
+    switch (family * 3 + which) {
+    case CGG_GAUSSIAN * 3 + 0: return (void *)sweep_persistent_kernel<CGG_GAUSSIAN>;
+    case CGG_GAUSSIAN * 3 + 1: return (void *)pass_kernel<CGG_GAUSSIAN>;
+    case CGG_GAUSSIAN * 3 + 2: return (void *)sweep_cluster_kernel<CGG_GAUSSIAN>;
+    case CGG_BINOMIAL * 3 + 0: return (void *)sweep_persistent_kernel<CGG_BINOMIAL>;
+    case CGG_BINOMIAL * 3 + 1: return (void *)pass_kernel<CGG_BINOMIAL>;
+    case CGG_BINOMIAL * 3 + 2: return (void *)sweep_cluster_kernel<CGG_BINOMIAL>;
+    case CGG_POISSON * 3 + 0: return (void *)sweep_persistent_kernel<CGG_POISSON>;
+    case CGG_POISSON * 3 + 1: return (void *)pass_kernel<CGG_POISSON>;
+    default: return (void *)sweep_cluster_kernel<CGG_POISSON>;
     }
 }
 
@@ -759,9 +870,10 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (!(cfg->prior_sigma > 0.0)) return fail(CGG_E_ARG, "cgg_create: prior scale must be positive");
     if (cfg->prior == CGG_PRIOR_STUDENT_T && !(cfg->prior_df > 0.0)) return fail(CGG_E_ARG, "cgg_create: student-t df must be positive");
     if (cfg->family == CGG_GAUSSIAN && !(cfg->sd > 0.0)) return fail(CGG_E_ARG, "cgg_create: gaussian sd must be positive");
-    if (cfg->driver != CGG_DRIVER_PERSISTENT && cfg->driver != CGG_DRIVER_STEPWISE) return fail(CGG_E_ARG, "cgg_create: unknown driver");
+    if (cfg->driver != CGG_DRIVER_PERSISTENT && cfg->driver != CGG_DRIVER_STEPWISE && cfg->driver != CGG_DRIVER_CLUSTER) return fail(CGG_E_ARG, "cgg_create: unknown driver");
     if (cfg->mode != CGG_MODE_CHAINS && cfg->mode != CGG_MODE_ROW_SHARDED) return fail(CGG_E_ARG, "cgg_create: unknown mode");
     if (cfg->mode == CGG_MODE_ROW_SHARDED && cfg->driver != CGG_DRIVER_STEPWISE) return fail(CGG_E_ARG, "cgg_create: row-sharded mode requires the stepwise driver");
+    if (cfg->driver == CGG_DRIVER_CLUSTER && cfg->n > (1LL << 22)) return fail(CGG_E_ARG, "cgg_create: the cluster driver is for small n (<= 2^22 rows per chain)");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(CGG_E_CUDA, "cgg_create: no CUDA device available (this engine has no CPU fallback)");
@@ -806,7 +918,19 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     }
     h->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    h->smem = CtaShared::bytes(C);
+    h->smem = (CtaShared::bytes(C) + 15) / 16 * 16;
+    {   // X-column cache of the pair passes (cgg_device.cuh: ColCache): two columns of every warp's rows in shared memory,
+        // if they fit next to the rings.  Needs the grid size, i.e. a first guess of G = all SMs but the deciders'.
+        const char *e4 = getenv("CGG_COLCACHE");
+        const bool want = (e4 ? atoi(e4) != 0 : true) && d.pair && !d.sharded && cfg->driver == CGG_DRIVER_PERSISTENT;
+        const int64_t n_tiles = (cfg->n + TILE_ROWS - 1) / TILE_ROWS;
+        const int64_t Wg = (int64_t)(prop.multiProcessorCount - 1) * NWARPS;
+        const int64_t tpw = (n_tiles + Wg - 1) / Wg;
+        const size_t need = (size_t)NWARPS * 2 * (size_t)tpw * 512;
+        const size_t room = (size_t)prop.sharedMemPerBlockOptin > h->smem + 2048 ? (size_t)prop.sharedMemPerBlockOptin - h->smem - 2048 : 0;
+        d.colcache = (want && Wg > 0 && n_tiles >= Wg && need <= room) ? (int)tpw : 0;
+        h->smem += (size_t)NWARPS * 2 * (size_t)d.colcache * 512;
+    }
     CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_ptr(cfg->family, 0), THREADS, h->smem));
@@ -825,7 +949,43 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (G > 250) G = 250;      // the limb accumulators count arrivals in 8 bits (cgg_device.cuh: LimbAcc)
     if (G < 1) G = 1;
     d.G = (int)G;
+    if (d.colcache && (int64_t)d.colcache * (int64_t)d.G * NWARPS < d.n_tiles) d.colcache = 0;    // (fewer CTAs than assumed: a warp's tiles would not fit)
     d.lde = (d.n + 31) / 32 * 32;
+    {   // small n: one cluster per chain instead of the grid-wide protocol
+        const char *e3 = getenv("CGG_SMALLN");
+        const bool allow = e3 ? atoi(e3) != 0 : true;
+        const bool want = cfg->driver == CGG_DRIVER_CLUSTER || (cfg->driver == CGG_DRIVER_PERSISTENT && allow && !(cfg->flags & CGG_FLAG_NO_CLUSTER) && !d.sharded && cfg->n <= (1LL << 18));
+        if (want) {
+            // CTAs per chain: enough that a worker warp owns a handful of tiles, at most 16 (8 is the portable limit)
+            const int64_t per = (int64_t)TILE_ROWS * (NWARPS - 1) * 12;
+            int S = 1;
+            while (S < CLUSTER_MAX && (int64_t)S * per < cfg->n) S *= 2;
+            if (getenv("CGG_CLUSTER")) S = std::max(1, std::min(CLUSTER_MAX, atoi(getenv("CGG_CLUSTER"))));
+            void *kf = kernel_ptr(cfg->family, 2);
+            h->cluster_smem = ClusterShared::bytes();
+            cudaError_t ce = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cluster_smem);
+            if (ce == cudaSuccess && S > 8) ce = cudaFuncSetAttribute(kf, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            for (; ce == cudaSuccess && S >= 1; S /= 2) {      // the largest cluster the device can schedule
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof lc);
+                lc.gridDim = dim3(S); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = h->cluster_smem;
+                cudaLaunchAttribute at;
+                at.id = cudaLaunchAttributeClusterDimension;
+                at.val.clusterDim.x = S; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                lc.attrs = &at; lc.numAttrs = 1;
+                int ncl = 0;
+                if (S == 1 || (cudaOccupancyMaxActiveClusters(&ncl, kf, &lc) == cudaSuccess && ncl > 0)) break;
+                cudaGetLastError();
+            }
+            if (ce != cudaSuccess || S < 1) {
+                cudaGetLastError();
+                if (cfg->driver == CGG_DRIVER_CLUSTER) { delete h; return fail(CGG_E_CUDA, "cgg_create: the device cannot run the cluster driver"); }
+            } else {
+                h->cluster_S = S;
+                d.pair = 0; d.coarse = 0;       // one chain per cluster; the pre-filter's clamp flags live in global memory
+            }
+        }
+    }
     {   // rounding allowance of an accumulated moment: one rounding per add along the longest chain of additions a value goes
         // through -- the rows a lane owns, then the warp, CTA and (row-sharded: rank) folds; the grid fold is exact (limb
         // accumulators / fixed-point accumulators).  Twice that, and never less than JET_CROUND.
@@ -1322,7 +1482,7 @@ extern "C" void *cgg_stream(cgg_handle *h) { return h ? (void *)h->stream : null
 
 extern "C" int cgg_launch_shape(cgg_handle *h, int32_t *ctas, int32_t *threads) {
     if (!h) return fail(CGG_E_ARG, "cgg_launch_shape: NULL handle");
-    if (ctas) *ctas = h->d.G + (h->cfg.driver == CGG_DRIVER_PERSISTENT ? 1 : 0);   // + the decider CTA
+    if (ctas) *ctas = h->cluster_S > 0 ? h->d.C * h->cluster_S : h->d.G + (h->cfg.driver == CGG_DRIVER_PERSISTENT ? 1 : 0);   // + the decider CTA
     if (threads) *threads = THREADS;
     return CGG_OK;
 }
@@ -1411,7 +1571,20 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     uint64_t launches = 0;
     CK(cudaEventRecord(h->ev0, h->stream));
     d.iter_stop = n_iter;
-    if (h->cfg.driver == CGG_DRIVER_PERSISTENT) {
+    if (h->cluster_S > 0) {
+        Dev dd = d;
+        dd.G = h->cluster_S;
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(C * h->cluster_S); lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = h->cluster_smem; lc.stream = h->stream;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = h->cluster_S; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        lc.attrs = &at; lc.numAttrs = 1;
+        void *args[] = {&dd};
+        CK(cudaLaunchKernelExC(&lc, kernel_ptr(h->cfg.family, 2), args));
+        ++launches;
+    } else if (h->cfg.driver == CGG_DRIVER_PERSISTENT) {
         // With pair passes a long run is cut into launches of a few iterations: every launch starts all chains at
         // coordinate 0 of the same iteration, which brings the chains of a pair back together after an exact-pass
         // hand-over has cost one of them extra passes (inside a launch nothing re-aligns them).  A launch boundary costs

@@ -8,7 +8,8 @@ FAMILIES = {"gaussian": (L.GAUSSIAN, L.LINK_IDENTITY), "binomial": (L.BINOMIAL, 
             "poisson": (L.POISSON, L.LINK_LOG)}
 LINKS = {"identity": L.LINK_IDENTITY, "logit": L.LINK_LOGIT, "log": L.LINK_LOG}
 PRIORS = {"normal": L.PRIOR_NORMAL, "laplace": L.PRIOR_LAPLACE, "student_t": L.PRIOR_STUDENT_T}
-DRIVERS = {"persistent": L.DRIVER_PERSISTENT, "stepwise": L.DRIVER_STEPWISE}
+# "persistent": the engine picks the grid-wide kernel or, for small n, one cluster per chain; "grid" / "cluster" force one
+DRIVERS = {"persistent": L.DRIVER_PERSISTENT, "grid": L.DRIVER_PERSISTENT, "cluster": L.DRIVER_CLUSTER, "stepwise": L.DRIVER_STEPWISE}
 
 _dp = C.POINTER(C.c_double)
 
@@ -55,7 +56,7 @@ class Engine:
                        mode=L.MODE_ROW_SHARDED if row_sharded else L.MODE_CHAINS, chain_offset=chain_offset,
                        seed=seed, spec_tau=spec_tau, rows_per_cta_min=rows_per_cta_min,
                        flags=((0 if prefilter else L.FLAG_NO_PREFILTER) | (0 if jet else L.FLAG_NO_JET)
-                              | (0 if jet_light else L.FLAG_NO_JET_LIGHT)),
+                              | (0 if jet_light else L.FLAG_NO_JET_LIGHT) | (L.FLAG_NO_CLUSTER if driver == "grid" else 0)),
                        jet_bound_scale=jet_bound_scale)
         h = C.c_void_p()
         L.check(self._lib.cgg_create(C.byref(cfg), C.byref(h)))

@@ -23,13 +23,16 @@ def _chains(family, prior, X, y, beta0, iters, U, **kw):
 
 
 def _check(family, prior, X, y, beta0, iters, w=0.5, max_steps=-1, seed=3, oracle_chains=None):
+    """Both sweep drivers -- the grid-wide persistent kernel and one cluster per chain (what small n gets by default) --
+    with jet passes and with exact passes only: four runs, one chain."""
     C = beta0.shape[0]
     U = np.random.default_rng(seed).random((C, 4000 + 60 * iters * X.shape[1]))
-    S, st = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps)
-    Sx, stx = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps, jet=False)
-    assert np.array_equal(S, Sx)
-    for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
-        assert st[k] == stx[k], k
+    S, st = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps, driver="grid")
+    for driver, jet in (("grid", False), ("cluster", True), ("cluster", False)):
+        Sx, stx = _chains(family, prior, X, y, beta0, iters, U, w=w, max_steps=max_steps, jet=jet, driver=driver)
+        assert np.array_equal(S, Sx), (driver, jet)
+        for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
+            assert st[k] == stx[k], (driver, jet, k)
     m = oracle.make_model(family, sd=1.0, **PRIOR_CASES[prior])
     for c in (range(C) if oracle_chains is None else oracle_chains):
         ref = oracle.run_chain(m, X, y, beta0[c], w=w, n_iter=iters, max_steps=max_steps, replay_u=U[c])
@@ -56,7 +59,7 @@ def test_single_column(family, prior):
 
 @pytest.mark.parametrize("C", [13, 32])
 def test_more_chains_than_deciding_warps(C):
-    # 12 deciding warps per GPU: with more chains a warp decides several of them
+    # 8 deciding warps per GPU: with more chains a warp decides several of them
     X, y, bt = synth("binomial", 2500, 3, seed=8)
     beta0 = 0.3 * np.random.default_rng(1).standard_normal((C, 3))
     st = _check("binomial", "laplace", X, y, beta0, 8, w=0.4, oracle_chains=(0, 11, 12, C - 1))
@@ -108,7 +111,7 @@ def test_pair_passes_and_chunked_launches_change_nothing(monkeypatch):
     def run(pair, chunk):
         monkeypatch.setenv("CGG_PAIR", str(pair))
         monkeypatch.setenv("CGG_CHUNK", str(chunk))
-        return _chains("binomial", "laplace", X, y, beta0, 23, U, w=0.5)
+        return _chains("binomial", "laplace", X, y, beta0, 23, U, w=0.5, driver="grid")
     S0, st0 = run(0, 1000)
     for pair, chunk in ((1, 1000), (1, 3), (1, 1), (0, 2)):
         S, st = run(pair, chunk)

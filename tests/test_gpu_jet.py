@@ -104,7 +104,7 @@ def _same_chain(a, b):
     ("binomial", "laplace", 0.5, -1), ("poisson", "student_t", 0.5, -1), ("gaussian", "normal", 0.05, -1),
     ("binomial", "normal", 0.02, 5), ("poisson", "laplace", 0.01, 3), ("gaussian", "student_t", 0.3, 0),
     ("binomial", "student_t", 3.0, -1), ("gaussian", "laplace", 0.002, -1)])
-@pytest.mark.parametrize("driver", ["persistent", "stepwise"])
+@pytest.mark.parametrize("driver", ["grid", "cluster", "stepwise"])
 def test_jet_chain_is_bit_identical_to_the_exact_chain(family, prior, w, max_steps, driver):
     n, p, C, iters = 3001, 5, 3, 40
     X, y, bt = synth(family, n, p, seed=21)

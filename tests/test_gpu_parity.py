@@ -85,7 +85,7 @@ def test_update_eta_bit_exact():
         assert np.array_equal(eta_gpu, eta) and beta[1] == 0.1 and beta[3] == -0.2
 
 
-@pytest.mark.parametrize("driver", ["persistent", "stepwise"])
+@pytest.mark.parametrize("driver", ["grid", "cluster", "stepwise"])
 @pytest.mark.parametrize("K,tau", [(1, 0.0), (8, 0.0), (8, 0.5), (3, 0.3)])
 def test_g2_readme_golden_replay(driver, K, tau):
     """The reference's README run (seed 42) replayed on the GPU from R's recorded runif stream."""
@@ -113,7 +113,7 @@ def test_g2_readme_golden_replay(driver, K, tau):
 @pytest.mark.parametrize("family,prior,w,max_steps", [
     ("binomial", "laplace", 0.5, -1), ("poisson", "student_t", 0.5, -1), ("gaussian", "normal", 0.05, -1),
     ("binomial", "normal", 0.02, 5), ("poisson", "laplace", 0.01, 3), ("gaussian", "student_t", 0.3, 0)])
-@pytest.mark.parametrize("driver", ["persistent", "stepwise"])
+@pytest.mark.parametrize("driver", ["grid", "cluster", "stepwise"])
 def test_g2_replay_and_philox_vs_oracle(family, prior, w, max_steps, driver):
     n, p, C, iters = 3001, 5, 3, 40
     X, y, bt = synth(family, n, p, seed=21)
@@ -175,7 +175,7 @@ def test_g2_cfg2_shape_full_grid_pair_passes():
     rng = np.random.default_rng(6)
     beta0 = bt + 0.02 * rng.standard_normal((C, p))
     m = oracle.make_model("binomial", **PRIOR_CASES["normal"])
-    with _engine("binomial", "normal", X, w=0.5, n_chains=C, K=8, spec_tau=0.12, seed=3) as e:
+    with _engine("binomial", "normal", X, w=0.5, n_chains=C, K=8, spec_tau=0.12, seed=3, driver="grid") as e:
         e.set_data(X, y)
         for c in range(C):
             e.init_chain(c, beta0[c])
@@ -191,6 +191,32 @@ def test_g2_cfg2_shape_full_grid_pair_passes():
             assert st["uniforms_used"][c] == ref["uniforms_used"]
             ne += ref["n_eval"]
         assert st["ref_evals"] == ne
+
+
+def test_g2_cfg2_shape_cluster_driver():
+    """The same workload on the driver it gets by default (n <= 2^18: one thread-block cluster per chain, sums exchanged
+    through distributed shared memory, every CTA of a cluster decides for itself)."""
+    n, p, C, iters = 100_000, 100, 4, 2
+    X, y, bt = synth("binomial", n, p, seed=12)
+    rng = np.random.default_rng(6)
+    beta0 = bt + 0.02 * rng.standard_normal((C, p))
+    m = oracle.make_model("binomial", **PRIOR_CASES["normal"])
+    with _engine("binomial", "normal", X, w=0.5, n_chains=C, K=8, spec_tau=0.12, seed=3) as e:
+        e.set_data(X, y)
+        for c in range(C):
+            e.init_chain(c, beta0[c])
+        ctas, _ = e.launch_shape()
+        assert ctas % C == 0 and 2 <= ctas // C <= 16        # C clusters
+        S, st = e.run(iters)
+        assert st["jet_passes"] >= 0.9 * st["updates"] and st["launches"] == 1
+        for c in (0, 3):
+            ref = oracle.run_chain(m, X, y, beta0[c], w=0.5, n_iter=iters, seed=3, chain=c)
+            assert ref["rc"] == 0
+            assert np.max(np.abs(S[c] - ref["samples"])) <= ATOL_G2, c
+            assert st["uniforms_used"][c] == ref["uniforms_used"]
+            assert e.chain_stats(c)["ref_evals"] == ref["n_eval"]
+            beta, eta = e.state(c)
+            assert np.max(np.abs(eta - ref["eta"])) <= 1e-9
 
 
 def test_chunked_runs_continue_the_chain():
