@@ -217,6 +217,20 @@ int cgg_set_exchange(cgg_handle *h, cgg_exchange_fn fn, void *user);
 #define CGG_NCCL_ID_BYTES 128
 int cgg_nccl_unique_id(char out[CGG_NCCL_ID_BYTES]);
 int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, const char id[CGG_NCCL_ID_BYTES]);
+/* Row-sharded handles on CGG_DRIVER_PERSISTENT: the exchange of a pass's sums stays INSIDE the persistent kernel.  Every
+ * rank owns a mailbox in its device memory; after a pass the deciding warp of each rank stores the rank's sums into every
+ * peer's mailbox (peer memory: NVLink / NVSwitch, system-scope stores of self-validating words), polls its own mailbox and
+ * adds the ranks' parts in rank order: bit-identical totals, hence identical decisions, on every rank; no collective call,
+ * no host round trip, no extra launch per pass.
+ *   cgg_p2p_mailbox  allocates this handle's mailbox for `world` ranks (<= 8); returns its device pointer and / or its CUDA
+ *                    IPC handle (64 bytes), which the host code hands to the other ranks by whatever means it has.
+ *   cgg_p2p_connect  maps the peers' mailboxes: dev_ptrs[r] (nullable array; a pointer valid in THIS process, e.g. another
+ *                    handle on the same device) or else ipc_handles + 64 r (another process).  Entry `rank` is ignored.
+ * Column statistics of the jet passes are still reduced once at cgg_set_data through cgg_comm_init_nccl / cgg_set_exchange. */
+#define CGG_IPC_HANDLE_BYTES 64
+int cgg_p2p_mailbox(cgg_handle *h, int32_t world, void **dev_ptr, char ipc_handle[CGG_IPC_HANDLE_BYTES]);
+int cgg_p2p_connect(cgg_handle *h, int32_t rank, int32_t world, void *const *dev_ptrs, const char *ipc_handles);
+
 /* CUDA stream (cudaStream_t) the handle launches on, for callers that time with their own events */
 void *cgg_stream(cgg_handle *h);
 /* Grid used by the sweep kernels: CTAs and threads per CTA (for launch accounting) */

@@ -25,7 +25,7 @@ EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cg
            "cgg_set_data_device", "cgg_init_chain", "cgg_set_state", "cgg_log_potential", "cgg_update_eta", "cgg_run",
            "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms",
            "cgg_nccl_unique_id", "cgg_comm_init_nccl", "cgg_debug_coarse_error", "cgg_debug_jet", "cgg_debug_light_error", "cgg_set_chain_w",
-           "cgg_get_chain_stats"]
+           "cgg_get_chain_stats", "cgg_p2p_mailbox", "cgg_p2p_connect"]
 
 
 class Config(C.Structure):
@@ -94,6 +94,8 @@ def load():
     L.cgg_debug_jet.argtypes = [vp, i32, i64, i32, i32, dp, dp, dp, dp]
     L.cgg_debug_light_error.argtypes = [i32, dp]
     L.cgg_set_chain_w.argtypes = [vp, dp]
+    L.cgg_p2p_mailbox.argtypes = [vp, i32, C.POINTER(vp), C.c_char_p]
+    L.cgg_p2p_connect.argtypes = [vp, i32, i32, C.POINTER(vp), C.c_char_p]
     L.cgg_get_chain_stats.argtypes = [vp, i32, C.POINTER(Stats)]
     L.cgg_debug_row_terms.argtypes = [i32, i32, i64, dp, dp, C.c_double, dp]
     L.cgg_stream.argtypes = [vp]

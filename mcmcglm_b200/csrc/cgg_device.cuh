@@ -120,6 +120,11 @@ struct Dev {
     int64_t max_steps;
     double inv_sd, ll_const, w, tau, coarse_theta, jet_bscale, n_total;   // n_total: rows of all shards (error bounds); w: default slice width (ChainState::w is what the chains use)
     double jet_ce;             // rounding allowance of one accumulated moment, relative to the sum of its terms' magnitudes (cgg_create: from the summation depth)
+    // row-sharded persistent driver: peer mailboxes (one per rank, each [C][world][NV] stamped 16-byte entries); mbox[r] is rank r's
+    // mailbox as mapped into THIS process (peer memory over NVLink, or the same device), nullptr: the exchange is not through mailboxes
+    unsigned long long *mbox[8];
+    uint32_t mbox_stamp0;      // stamps already used by earlier runs of this handle (all ranks agree: they run identical passes)
+    int32_t rank;
     uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
     PriorParams prior;
     int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache;   // pair: chains 2k, 2k+1 share a pass when they can;
@@ -1448,6 +1453,50 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     return JET_ACCEPTED;
 }
 
+// Row-sharded persistent driver: the ranks' totals of a pass, exchanged through peer-mapped mailboxes and added in RANK
+// ORDER, so that every rank decides from bit-identical sums.  Each value travels as two self-validating 64-bit words
+// {stamp32 : half32} (cf. LimbAcc: a 64-bit element of a vector access cannot be torn), written straight into every
+// peer's memory with system-scope stores -- NVLink on an NVSwitch box -- and polled for locally: no collective call, no
+// host, no extra launch; the pass -> exchange -> decision loop never leaves the persistent kernel.  stamp = number of
+// the pass since the handle was created (never reset: nothing has to be cleared between runs).
+struct __align__(16) MboxEntry { unsigned long long w0, w1; };
+__device__ __forceinline__ void mbox_store(MboxEntry *dst, double v, unsigned stamp) {
+    const unsigned long long s = (unsigned long long)stamp << 32;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(s | (unsigned)__double2loint(v)), "l"(s | (unsigned)__double2hiint(v)) : "memory");
+}
+__device__ __forceinline__ bool mbox_load(const MboxEntry *src, unsigned stamp, double &v) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+    v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+    return (unsigned)(w0 >> 32) == stamp && (unsigned)(w1 >> 32) == stamp;
+}
+// vals[0..nvals): in: this rank's sums (identical in every lane); out: the totals over the ranks.  false: timed out.
+__device__ __forceinline__ bool mbox_exchange(const Dev &d, int c, int nvals, unsigned stamp, int lane, double (&vals)[NV]) {
+    const int nv = nvals < 1 ? 1 : nvals;
+    // my values to everybody (lane k sends value k to every rank, my own mailbox included)
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) mine = (lane == k) ? vals[k] : mine;
+    if (lane < nv)
+        for (int r = 0; r < d.world; ++r)
+            mbox_store(reinterpret_cast<MboxEntry *>(d.mbox[r]) + ((size_t)c * d.world + d.rank) * NV + lane, mine, stamp);
+    // everybody's values from my mailbox, added in rank order by the lane of the value
+    const MboxEntry *my = reinterpret_cast<const MboxEntry *>(d.mbox[d.rank]) + (size_t)c * d.world * NV;
+    const unsigned long long t0 = globaltimer_ns();
+    double tot = 0.0;
+    for (unsigned spins = 0;; ++spins) {
+        bool ok = true;
+        tot = 0.0;
+        if (lane < nv)
+            for (int r = 0; r < d.world; ++r) { double v; ok = mbox_load(my + (size_t)r * NV + lane, stamp, v) && ok; tot += v; }
+        if (__all_sync(0xffffffffu, ok)) break;
+        if ((spins & 1023u) == 1023u && globaltimer_ns() - t0 > 4000000000ULL) return false;      // a peer never showed up
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) vals[k] = __shfl_sync(0xffffffffu, tot, k);
+    return true;
+}
+
 // Persistent driver, right after a decision was published and the next column's beta / statistics were prefetched: if the
 // pass now in flight is a jet pass that starts a fresh update, prepare that update (jet_prepare) while the rows stream.
 __device__ __forceinline__ void decider_prephase(const Dev &d, int c, DeciderCache *dc, int lane) {
@@ -1473,10 +1522,10 @@ __device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
     for (int r = 0; r < d.world; ++r) v += __ldcg(d.gathered + (size_t)r * d.C * NV + idx);
     return v;
 }
-enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2 };
 // vals_in (with SRC_SLOTS): the pass's sums are handed over by the caller (cluster driver) instead of read from the limbs.
+enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2, DEC_ABORT = 3 };
 __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, DeciderCache *dc = nullptr,
-                                         const double *vals_in = nullptr) {
+                                         const double *vals_in = nullptr, unsigned pass_no = 0) {
     const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
     // ---- control block, state, beta/shat of j and j+1: from the deciding warp's shared-memory cache if it has them,
@@ -1506,6 +1555,14 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
 #pragma unroll
             for (int k = 0; k < NV; ++k) jm[k] = (k < nvals) ? vals_in[k] : 0.0;
         } else if (!limbs_take(d, c, nvals, lane, dc->prev, jm)) return DEC_NOT_READY;  // some CTA's sums are still on their way: nothing was changed
+        if (d.sharded && d.mbox[0]) {
+            // row-sharded: this shard's additive constant joins its sums (M_0 of a jet pass that delivers it, every candidate
+            // sum of an exact pass), then the ranks' sums are exchanged and added in rank order
+            const bool has_m0 = jetpass && (d.family != CGG_BINOMIAL || ((unsigned)ct.coarse_mask & JET_FULL) != 0u);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) if (jetpass ? (k == 0 && has_m0) : (k < nc)) jm[k] += d.ll_const;
+            if (!mbox_exchange(d, c, nvals, d.mbox_stamp0 + pass_no + 1u, lane, jm)) return DEC_ABORT;
+        }
     } else if (jetpass) {
         const double mv = (lane < NV) ? (from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane)) : 0.0;
 #pragma unroll
@@ -1524,7 +1581,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (lane < nc) {
         double ll;
         if (src == SRC_SLOTS) {
-            ll = pick(lane) + d.ll_const;
+            ll = pick(lane) + (d.sharded ? 0.0 : d.ll_const);       // (row-sharded: the constants travelled with the sums)
             if (cmask) { aflags = __ldcg(&d.acc[c * NV + lane].flags); d.acc[c * NV + lane].flags = 0u; }   // clamp-proximity flag of the pre-filter
         } else ll = from_xbuf ? xbuf_value(d, c * NV + lane) : acc_take(d.acc + c * NV + lane, &aflags) + d.ll_const;
         f = ll + (s.prior_rest + prior_logdens(d.prior, s.cand[lane]));

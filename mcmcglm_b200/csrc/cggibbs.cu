@@ -61,8 +61,9 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             all_fin = false;
             const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
             const long long td0 = d.prof ? clock64() : 0;
-            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c);     // reads the limb accumulators itself: one load per lane
+            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c, nullptr, (unsigned)v);     // reads the limb accumulators itself: one load per lane
             if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
+            if (oc == DEC_ABORT) { if (lane == 0) { d.hdr->abort = 1; fence_gpu(); } return; }   // a peer rank never delivered
             const bool fin = oc == DEC_FINISHED;
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
             if (!fin) {                                              // after publishing: off the chain's critical path
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     };
     double acc2[NV];
     bool pair_prefetched = false;
+    int pf_j = -1, pf_cj = -1; bool pf_full = false;      // what the pair prologue issued ahead of time was issued for
     ColCache cc;        // this warp's X-column cache (pair passes); lives for the launch
     cc.cap = d.colcache; cc.base = sh.cache0 + (uint32_t)warp * (uint32_t)(2 * d.colcache) * 512u + (uint32_t)lane * 16u;
     cc.tag0 = cc.tag1 = -1; cc.fill_col = cc.fill_slot = -1;
@@ -167,7 +169,18 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             }
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
-            if (pair_prefetched && !pair) { cp_async_wait<0>(); pair_prefetched = false; }    // (cannot happen: the blocks were checked)
+            if (pair_prefetched) {
+                // the first tiles of this pass were requested ahead of time, possibly from a PREDICTED control block (same kind of
+                // pass, next column): they are only good if the real block says the same
+                bool good = pair;
+                if (good) {
+                    const double *cwA = sh.ctl + c * CTL_WORDS;
+                    const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
+                    const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                    good = (int)(w0 & 0xffffffffLL) == pf_j && (int)(w1 & 0xffffffffLL) == pf_cj && full == pf_full;
+                }
+                if (!good) { cp_async_wait<0>(); pair_prefetched = false; ++n_notready; }
+            }
             if (pair && prefetched) { cp_async_wait<0>(); prefetched = false; }               // a single-pass prefetch of chain c: other ring layout
             if (pair) {
                 const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
@@ -192,10 +205,27 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 };
                 auto after = [&]() {
                     if (c2 < 0) return;
-                    if (!pair_lookahead(d, sh, c2, nround, lane)) return;
+                    double pred[2];
                     const double *nA = sh.ctl + c2 * CTL_WORDS;
-                    if (!pair_batchable(nA, nA + CTL_WORDS)) return;
-                    const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(nA[1]) >> 32)) & JET_FULL);
+                    if (pair_lookahead(d, sh, c2, nround, lane)) {
+                        if (!pair_batchable(nA, nA + CTL_WORDS)) return;
+                    } else {
+                        // The next pair's decision is not published yet (this CTA is ahead of the slowest ones).  Its first
+                        // tiles do not depend on the decision's VALUE, only on which pass comes: in the stationary regime
+                        // that is a jet pass of the same kind on the next column, applying the update of the column just
+                        // sampled.  Request them from that prediction; the real block is compared with it before use.
+                        const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
+                        const int jp = (int)(w0 & 0xffffffffLL);
+                        const unsigned mk = (unsigned)(w1 >> 32);
+                        if (!(mk & JET_BIT) || jp < 0 || (long long)jp >= (long long)d.p) return;
+                        const int jn = (jp + 1 == (int)d.p) ? 0 : jp + 1;
+                        pred[0] = __longlong_as_double((long long)(unsigned)jn);                                  // ncand = 0
+                        pred[1] = __longlong_as_double(((long long)mk << 32) | (long long)(unsigned)jp);            // commit column = the one just sampled
+                        nA = pred;
+                    }
+                    const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
+                    const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                    pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2;
                     PairStream ns(d, c2, nA, wid, W, lane, ring, cc, full2);
                     ns.prologue(false);
                     pair_prefetched = true;
@@ -277,10 +307,10 @@ struct ClusterShared {
         xs = part + NWARPS * NV;                       // [2][CLUSTER_MAX][NV] every CTA's sums of the pass, double-buffered by pass parity
         ctl = xs + 2 * CLUSTER_MAX * NV;               // [CTL_WORDS] the control block of the coming pass
         vals = ctl + CTL_WORDS;                        // [NV] the pass's totals
-        dc = reinterpret_cast<DeciderCache *>(vals + NV + 1);
+        dc = reinterpret_cast<DeciderCache *>((reinterpret_cast<uintptr_t>(vals + NV) + 127) & ~(uintptr_t)127);
     }
     static size_t bytes() {
-        return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * (NWARPS * KMAX * 32 + NWARPS * NV + 2 * CLUSTER_MAX * NV + CTL_WORDS + NV + 2) + sizeof(DeciderCache) + 16;
+        return (size_t)NWARPS * RING_BYTES_PER_WARP + sizeof(double) * (NWARPS * KMAX * 32 + NWARPS * NV + 2 * CLUSTER_MAX * NV + CTL_WORDS + NV + 2) + sizeof(DeciderCache) + 256;
     }
 };
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -803,6 +833,8 @@ struct cgg_handle {
     cgg_exchange_fn xfn = nullptr; void *xuser = nullptr;
     ncclComm_t comm = nullptr; int world = 1, rank = 0; double *gather_dev = nullptr; size_t gather_cap = 0;
     double local_ll_const = 0.0;
+    MboxEntry *mbox_own = nullptr; size_t mbox_bytes = 0; void *mbox_peer[8] = {nullptr}; bool mbox_ipc[8] = {false}; bool p2p_ready = false;
+    uint32_t mbox_stamp = 0;               // passes exchanged through the mailboxes so far (all ranks agree)
     int cluster_S = 0;                    // > 0: the cluster driver runs the sweeps, with this many CTAs per chain
     size_t cluster_smem = 0;
     std::vector<double> w_chain;          // per-chain slice widths (cgg_set_chain_w); default cfg.w
@@ -872,7 +904,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (cfg->family == CGG_GAUSSIAN && !(cfg->sd > 0.0)) return fail(CGG_E_ARG, "cgg_create: gaussian sd must be positive");
     if (cfg->driver != CGG_DRIVER_PERSISTENT && cfg->driver != CGG_DRIVER_STEPWISE && cfg->driver != CGG_DRIVER_CLUSTER) return fail(CGG_E_ARG, "cgg_create: unknown driver");
     if (cfg->mode != CGG_MODE_CHAINS && cfg->mode != CGG_MODE_ROW_SHARDED) return fail(CGG_E_ARG, "cgg_create: unknown mode");
-    if (cfg->mode == CGG_MODE_ROW_SHARDED && cfg->driver != CGG_DRIVER_STEPWISE) return fail(CGG_E_ARG, "cgg_create: row-sharded mode requires the stepwise driver");
+    if (cfg->mode == CGG_MODE_ROW_SHARDED && cfg->driver == CGG_DRIVER_CLUSTER) return fail(CGG_E_ARG, "cgg_create: row-sharded mode runs on the persistent (peer mailboxes) or the stepwise driver");
     if (cfg->driver == CGG_DRIVER_CLUSTER && cfg->n > (1LL << 22)) return fail(CGG_E_ARG, "cgg_create: the cluster driver is for small n (<= 2^22 rows per chain)");
 
     int ndev = 0;
@@ -1073,6 +1105,8 @@ extern "C" void cgg_destroy(cgg_handle *h) {
     if (h->y_owned) cudaFreeAsync(h->y_owned, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->gather_dev);
+    for (int r = 0; r < 8; ++r) if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
+    cudaFree(h->mbox_own);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     delete h->hdr_pinned;
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1456,6 +1490,47 @@ extern "C" int cgg_comm_init_nccl(cgg_handle *h, int32_t rank, int32_t world, co
     return CGG_OK;
 }
 
+extern "C" int cgg_p2p_mailbox(cgg_handle *h, int32_t world, void **dev_ptr, char ipc_handle[CGG_IPC_HANDLE_BYTES]) {
+    if (!h || world < 1 || world > 8) return fail(CGG_E_ARG, "cgg_p2p_mailbox: world must be in 1..8");
+    if (!h->d.sharded) return fail(CGG_E_STATE, "cgg_p2p_mailbox: handle was not created with CGG_MODE_ROW_SHARDED");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->mbox_own) {
+        h->mbox_bytes = sizeof(MboxEntry) * (size_t)h->d.C * (size_t)world * NV;
+        CK(cudaMalloc((void **)&h->mbox_own, h->mbox_bytes));       // (not from the pool: must be exportable)
+        CK(cudaMemset(h->mbox_own, 0, h->mbox_bytes));              // stamp 0 = never written
+        CK(cudaDeviceSynchronize());
+    }
+    if (dev_ptr) *dev_ptr = h->mbox_own;
+    if (ipc_handle) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == CGG_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t ih;
+        CK(cudaIpcGetMemHandle(&ih, h->mbox_own));
+        memcpy(ipc_handle, &ih, sizeof ih);
+    }
+    h->world = world;
+    return CGG_OK;
+}
+
+extern "C" int cgg_p2p_connect(cgg_handle *h, int32_t rank, int32_t world, void *const *dev_ptrs, const char *ipc_handles) {
+    if (!h || (!dev_ptrs && !ipc_handles)) return fail(CGG_E_ARG, "cgg_p2p_connect: NULL argument");
+    if (!h->mbox_own || world != h->world || rank < 0 || rank >= world) return fail(CGG_E_STATE, "cgg_p2p_connect: call cgg_p2p_mailbox(world) first, with the same world");
+    CK(cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->mbox_peer[r] = h->mbox_own; continue; }
+        if (dev_ptrs && dev_ptrs[r]) { h->mbox_peer[r] = dev_ptrs[r]; continue; }         // same process (tests: two shards on one device)
+        if (!ipc_handles) return fail(CGG_E_ARG, "cgg_p2p_connect: no pointer and no IPC handle for rank %d", r);
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, ipc_handles + (size_t)r * CGG_IPC_HANDLE_BYTES, sizeof ih);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(CGG_E_COMM, "cgg_p2p_connect: cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
+        h->mbox_peer[r] = p; h->mbox_ipc[r] = true;
+    }
+    h->rank = rank;
+    h->p2p_ready = true;
+    return CGG_OK;
+}
+
 extern "C" int cgg_set_chain_w(cgg_handle *h, const double *w_host) {
     if (!h || !w_host) return fail(CGG_E_ARG, "cgg_set_chain_w: NULL argument");
     for (int c = 0; c < h->d.C; ++c)
@@ -1496,7 +1571,9 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     const int C = d.C;
     for (int c = 0; c < C; ++c)
         if (!h->chain_init[c]) return fail(CGG_E_STATE, "cgg_run: chain %d not initialised (cgg_init_chain)", c);
-    if (d.sharded && !h->xfn && !h->comm) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
+    const bool mailboxes = d.sharded && h->cfg.driver == CGG_DRIVER_PERSISTENT;
+    if (mailboxes && !h->p2p_ready) return fail(CGG_E_STATE, "cgg_run: a row-sharded handle on the persistent driver exchanges through peer mailboxes (cgg_p2p_mailbox + cgg_p2p_connect)");
+    if (d.sharded && !mailboxes && !h->xfn && !h->comm) return fail(CGG_E_STATE, "cgg_run: row-sharded handle has no exchange (cgg_comm_init_nccl or cgg_set_exchange)");
     CK(cudaSetDevice(h->cfg.device));
     const bool light = d.jet_light && d.family == CGG_BINOMIAL;
     for (int c = 0; c < C; ++c) {
@@ -1598,6 +1675,10 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
             }
             Dev dd = d;
             dd.iter_stop = std::min(done + chunk, n_iter);
+            if (mailboxes) {
+                for (int r = 0; r < 8; ++r) dd.mbox[r] = (unsigned long long *)h->mbox_peer[r];
+                dd.world = h->world; dd.rank = h->rank; dd.mbox_stamp0 = h->mbox_stamp;
+            }
             void *args[] = {&dd};
             CK(cudaLaunchCooperativeKernel(kernel_ptr(h->cfg.family, 0), dim3(d.G + 1), dim3(THREADS), args, h->smem, h->stream));
             ++launches;
@@ -1701,6 +1782,11 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     }
     if (d.jet_light && d.family == CGG_BINOMIAL) std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);   // carried f(x0) is a surrogate value
     h->last_cs = cs;
+    if (mailboxes) {       // stamps are per-chain pass numbers offset by a common base: move the base past every chain's count
+        uint64_t mx = 0;
+        for (int c = 0; c < C; ++c) mx = std::max<uint64_t>(mx, cs[c].passes);
+        h->mbox_stamp += (uint32_t)mx + 2u;
+    }
     // a chain that failed on the device stopped in the middle of an update (its beta may be ahead of its eta): it has to
     // be initialised again before it can run (cgg_init_chain / cgg_set_state)
     for (int c = 0; c < C; ++c)

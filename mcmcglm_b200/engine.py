@@ -190,6 +190,20 @@ class Engine:
         """Row-sharded mode: join the NCCL communicator identified by the 128-byte id (see multigpu.init_nccl)."""
         L.check(self._lib.cgg_comm_init_nccl(self._h, rank, world, id_bytes))
 
+    def p2p_mailbox(self, world):
+        """Row-sharded + persistent driver: allocates this rank's mailbox; returns (device pointer, 64-byte IPC handle)."""
+        ptr = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        L.check(self._lib.cgg_p2p_mailbox(self._h, world, C.byref(ptr), buf))
+        return ptr.value, buf.raw
+
+    def p2p_connect(self, rank, world, dev_ptrs=None, ipc_handles=None):
+        """Maps the peers' mailboxes: dev_ptrs (same process) or the concatenated IPC handles (other processes)."""
+        arr = None
+        if dev_ptrs is not None:
+            arr = (C.c_void_p * world)(*[C.c_void_p(p) if p else None for p in dev_ptrs])
+        L.check(self._lib.cgg_p2p_connect(self._h, rank, world, arr, b"".join(ipc_handles) if ipc_handles is not None else None))
+
     def set_exchange(self, fn):
         """fn(device_ptr:int, count:int, stream_ptr:int) -> int; kept alive by the engine."""
         def tramp(user, buf, count, stream):

@@ -66,3 +66,13 @@ def init_nccl(engine, rank, world, group=None):
     obj = [nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0, group=group)
     engine.comm_init_nccl(rank, world, obj[0])
+
+
+def init_p2p(engine, rank, world, group=None):
+    """Connects the peer mailboxes of a row-sharded engine on the persistent driver: every rank exports the CUDA IPC handle
+    of its mailbox, torch.distributed carries the 64 bytes, every rank maps the others' (NVLink peer memory)."""
+    import torch.distributed as dist
+    _, handle = engine.p2p_mailbox(world)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    engine.p2p_connect(rank, world, ipc_handles=handles)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "cggibbs.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(cgg_[a-z_]+)\s*\(", src)) - {"cgg_exchange_fn"})
+    return sorted(set(re.findall(r"\b(cgg_[a-z0-9_]+)\s*\(", src)) - {"cgg_exchange_fn"})
 
 
 def test_library_exports_every_declared_symbol():
