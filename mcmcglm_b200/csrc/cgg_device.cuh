@@ -601,16 +601,22 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
             const double2 cv = ps.xc_ring ? lds2(s + 2048u) : lds2(ps.xc_slot + t_off);
             ea.x = eta_shift(ea.x, cv.x, cdA); ea.y = eta_shift(ea.y, cv.y, cdA);
             eb.x = eta_shift(eb.x, cv.x, cdB); eb.y = eta_shift(eb.y, cv.y, cdB);
+#ifndef CGG_DIAG_NOSTORE      // (diagnostic builds only: what does the write-back cost?  results are wrong without it)
             *reinterpret_cast<double2 *>(etaA + off) = ea;
             *reinterpret_cast<double2 *>(etaB + off) = eb;
+#endif
         }
         double2 yy = make_double2(0.0, 0.0);
         if (WITH_Y) yy = lds2(s + 1024u);
         double2 xs = ps.xj_ring ? lds2(s + 1536u) : lds2(ps.xj_slot + t_off);
         xs.x *= cscale; xs.y *= cscale;
         rows += 2;
+#ifdef CGG_DIAG_NOMATH        // (diagnostic builds only: what does the row math cost?)
+        mA[1] += ea.x + ea.y + xs.x + yy.x; mB[1] += eb.x + eb.y + xs.y + yy.y;
+#else
         JetRow<FAMILY>::template add2<FULL>(yy, ea, xs, d.inv_sd, tab, mA, riskA);
         JetRow<FAMILY>::template add2<FULL>(yy, eb, xs, d.inv_sd, tab, mB, riskB);
+#endif
         t_off += 512u;
     };
 #if CGG_PAIR_TPI == 2

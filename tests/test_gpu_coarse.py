@@ -26,6 +26,7 @@ def _run(X, y, beta0, prefilter, w=0.5, iters=30, seed=4, theta=None, **kw):
         os.environ.pop("CGG_COARSE_THETA", None)
     try:
         n, p = X.shape
+        kw.setdefault("driver", "grid")     # the pre-filter belongs to the grid-wide kernels (the cluster driver scores everything in fp64)
         with Engine(n, p, family="binomial", w=w, n_chains=beta0.shape[0], K=8, seed=seed, prefilter=prefilter, jet=False,   # this file tests the exact-pass path
                     **PRIOR_CASES["laplace"], **kw) as e:
             e.set_data(X, y)

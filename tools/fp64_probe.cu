@@ -11,6 +11,18 @@ __global__ void k_dfma(double *out, int iters) {
     for (int i = 0; i < iters; ++i) { a = fma(a, b, c); d = fma(d, b, c); e = fma(e, b, c); f = fma(f, b, c); }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a + d + e + f;
 }
+// dependent-issue latency of one warp: a single chain of DFMAs / of IMADs, clock64 around it
+__global__ void k_latency(long long *out, int iters) {
+    double a = threadIdx.x * 1e-9, b = 1.0000001, c = 1e-7;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) a = fma(a, b, c);
+    long long t1 = clock64();
+    int x = threadIdx.x, y = 3, z = 7;
+    for (int i = 0; i < iters; ++i) x = x * y + z;
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t1; }
+    if (a == 12345.0 && x == 7) out[2] = 1;
+}
 template <int FAM>
 __global__ void k_term(double *out, int iters) {
     __shared__ double2 tab[MATH_TAB_N];
@@ -72,6 +84,12 @@ int main() {
     printf(" \"term_poisson_per_s_16warps\": %.4g,\n", thr1 * iters * 2 / (ms * 1e-3));
     ms = timeit([&] { k_term<CGG_BINOMIAL><<<pr.multiProcessorCount * 2, 512>>>(out, iters); });
     printf(" \"term_binomial_per_s_32warps\": %.4g,\n", thr1 * 2 * iters * 2 / (ms * 1e-3));
+    {
+        long long *lo; cudaMalloc(&lo, 64); cudaMemset(lo, 0, 64);
+        k_latency<<<1, 32>>>(lo, 4096); cudaDeviceSynchronize();
+        long long h[3]; cudaMemcpy(h, lo, sizeof h, cudaMemcpyDeviceToHost);
+        printf(" \"dfma_dependent_latency_cycles\": %.2f,\n \"imad_dependent_latency_cycles\": %.2f,\n", h[0] / 4096.0, h[1] / 4096.0);
+    }
     size_t bytes = 4ull << 30; double2 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
     ms = timeit([&] { k_read<<<pr.multiProcessorCount * 16, T>>>(buf, out, bytes / 16); });
     printf(" \"stream_read_GBps\": %.4g}\n", bytes / (ms * 1e-3) / 1e9);
