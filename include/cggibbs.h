@@ -46,12 +46,17 @@ typedef enum cgg_status {
     CGG_E_COMM = -8         /* collective layer failure (row-sharded mode) */
 } cgg_status;
 
-/* family$family / family$link of the reference (R/family_data_processing.R:3-16).  Only the
- * canonical pairs are implemented: gaussian+identity, binomial+logit, poisson+log. */
-enum { CGG_GAUSSIAN = 0, CGG_BINOMIAL = 1, CGG_POISSON = 2 };
-enum { CGG_LINK_IDENTITY = 0, CGG_LINK_LOGIT = 1, CGG_LINK_LOG = 2 };
-/* beta_prior: iid distributional::dist_normal / dist_laplace / dist_student_t (R/glm_utils.R:108-110) */
-enum { CGG_PRIOR_NORMAL = 0, CGG_PRIOR_LAPLACE = 1, CGG_PRIOR_STUDENT_T = 2 };
+/* family$family / family$link of the reference (R/family_data_processing.R:3-16).  Implemented pairs: gaussian+identity,
+ * binomial+logit, poisson+log (all drivers, jet passes) and -- exact passes on the stepwise driver -- binomial+probit
+ * (vignettes/pospkg.Rmd:88-108) and negative binomial+log (MASS::negative.binomial; the reference's log-density is
+ * dnbinom(size = 1) whatever theta is, R/glm_utils.R:55-57). */
+enum { CGG_GAUSSIAN = 0, CGG_BINOMIAL = 1, CGG_POISSON = 2, CGG_NEGATIVE_BINOMIAL = 3 };
+enum { CGG_LINK_IDENTITY = 0, CGG_LINK_LOGIT = 1, CGG_LINK_LOG = 2, CGG_LINK_PROBIT = 3 };
+/* beta_prior: distributional::dist_normal(mu, sigma) / dist_laplace(mu, sigma) / dist_student_t(df, mu, sigma) /
+ * dist_gamma(shape, rate) / dist_exponential(rate) (R/glm_utils.R:108-110).  For gamma prior_mu = shape, prior_sigma = rate;
+ * for exponential prior_sigma = rate.  A LIST of priors (R/glm_utils.R:113-115) is built with cgg_add_prior. */
+enum { CGG_PRIOR_NORMAL = 0, CGG_PRIOR_LAPLACE = 1, CGG_PRIOR_STUDENT_T = 2, CGG_PRIOR_GAMMA = 3, CGG_PRIOR_EXPONENTIAL = 4 };
+#define CGG_MAX_PRIORS 8
 /* how the sweep is driven on the device */
 enum {
     CGG_DRIVER_PERSISTENT = 0, /* one cooperative kernel runs all sweeps; per-chain flags, no grid barrier */
@@ -71,6 +76,8 @@ enum {
 #define CGG_FLAG_NO_PREFILTER 1 /* score every candidate in fp64 (the fp32 pre-filter never changes results, only cost) */
 #define CGG_FLAG_NO_JET 2       /* decide every candidate from an exact pass over the rows (jet passes never change
                                    results, only cost: one pass per update instead of one per few candidates) */
+#define CGG_FLAG_NAIVE 16       /* linear_predictor_calc = "naive" (R/glm_utils.R:206-208): eta is recomputed as X %*% beta, O(n p), before every
+                                   pass over the rows instead of being updated in O(n); stepwise driver.  Same chain up to the rounding of eta */
 #define CGG_FLAG_NO_CLUSTER 8   /* CGG_DRIVER_PERSISTENT: always the grid-wide kernel, also for small n (tests; never changes results) */
 #define CGG_FLAG_NO_JET_LIGHT 4 /* binomial: every jet pass also evaluates the exact f(x0) (light passes skip it because
                                    the slice tests only involve differences f(v) - f(x0); never changes results) */
@@ -132,6 +139,12 @@ int cgg_abi_version(void);
 /* Replaces the front half of mcmcglm() that builds state (R/mcmcglm.R:171-198). */
 int cgg_create(const cgg_config *cfg, cgg_handle **out);
 void cgg_destroy(cgg_handle *h);
+
+/* A list of priors (log_prior_density.list, R/glm_utils.R:113-115): the reference evaluates EVERY prior of the list at
+ * EVERY coordinate and sums everything (quirk Q6), i.e. the coordinates are iid with density prod_k prior_k.  cfg.prior is
+ * the first component; each call appends one (up to CGG_MAX_PRIORS in total): (a, b, c) = (mu, sigma, df) for normal /
+ * laplace / student-t, (shape, rate, -) for gamma, (-, rate, -) for exponential.  Call before cgg_init_chain. */
+int cgg_add_prior(cgg_handle *h, int32_t kind, double a, double b, double c);
 
 /* X = model.matrix, Y = model.response (R/mcmcglm.R:176-178).  Host buffers, copied to HBM. */
 int cgg_set_data(cgg_handle *h, const double *X_host, int64_t ldx, const double *y_host);

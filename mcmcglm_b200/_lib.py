@@ -9,15 +9,17 @@ SO_PATH = os.path.join(_HERE, "csrc", "libcggibbs.so")
 ABI_VERSION = 2
 KMAX = 8
 OK, E_ARG, E_UNSUPPORTED, E_CUDA, E_NAN, E_STREAM, E_NOTERM, E_STATE, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7, -8
-GAUSSIAN, BINOMIAL, POISSON = 0, 1, 2
-LINK_IDENTITY, LINK_LOGIT, LINK_LOG = 0, 1, 2
-PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T = 0, 1, 2
+GAUSSIAN, BINOMIAL, POISSON, NEGATIVE_BINOMIAL = 0, 1, 2, 3
+LINK_IDENTITY, LINK_LOGIT, LINK_LOG, LINK_PROBIT = 0, 1, 2, 3
+PRIOR_NORMAL, PRIOR_LAPLACE, PRIOR_STUDENT_T, PRIOR_GAMMA, PRIOR_EXPONENTIAL = 0, 1, 2, 3, 4
+MAX_PRIORS = 8
 DRIVER_PERSISTENT, DRIVER_STEPWISE, DRIVER_CLUSTER = 0, 1, 2
 MODE_CHAINS, MODE_ROW_SHARDED = 0, 1
 FLAG_NO_PREFILTER = 1
 FLAG_NO_JET = 2
 FLAG_NO_JET_LIGHT = 4
 FLAG_NO_CLUSTER = 8
+FLAG_NAIVE = 16
 JET_NV = KMAX + 2
 
 # every symbol include/cggibbs.h declares
@@ -25,7 +27,7 @@ EXPORTS = ["cgg_last_error", "cgg_abi_version", "cgg_create", "cgg_destroy", "cg
            "cgg_set_data_device", "cgg_init_chain", "cgg_set_state", "cgg_log_potential", "cgg_update_eta", "cgg_run",
            "cgg_get_state", "cgg_get_fx", "cgg_set_exchange", "cgg_stream", "cgg_launch_shape", "cgg_debug_row_terms",
            "cgg_nccl_unique_id", "cgg_comm_init_nccl", "cgg_debug_coarse_error", "cgg_debug_jet", "cgg_debug_light_error", "cgg_set_chain_w",
-           "cgg_get_chain_stats", "cgg_p2p_mailbox", "cgg_p2p_connect"]
+           "cgg_get_chain_stats", "cgg_p2p_mailbox", "cgg_p2p_connect", "cgg_add_prior"]
 
 
 class Config(C.Structure):
@@ -94,6 +96,7 @@ def load():
     L.cgg_debug_jet.argtypes = [vp, i32, i64, i32, i32, dp, dp, dp, dp]
     L.cgg_debug_light_error.argtypes = [i32, dp]
     L.cgg_set_chain_w.argtypes = [vp, dp]
+    L.cgg_add_prior.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double]
     L.cgg_p2p_mailbox.argtypes = [vp, i32, C.POINTER(vp), C.c_char_p]
     L.cgg_p2p_connect.argtypes = [vp, i32, i32, C.POINTER(vp), C.c_char_p]
     L.cgg_get_chain_stats.argtypes = [vp, i32, C.POINTER(Stats)]

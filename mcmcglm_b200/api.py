@@ -39,7 +39,14 @@ class Dist:
             return self.mu + self.sigma * rng.standard_normal(n)
         if self.kind == "laplace":
             return rng.laplace(self.mu, self.sigma, n)
+        if self.kind == "gamma":                    # mu = shape, sigma = rate
+            return rng.gamma(self.mu, 1.0 / self.sigma, n)
+        if self.kind == "exponential":              # sigma = rate
+            return rng.exponential(1.0 / self.sigma, n)
         return self.mu + self.sigma * rng.standard_t(self.df, n)
+
+    def engine_tuple(self):
+        return (self.kind, self.mu, self.sigma, self.df)
 
 
 def dist_normal(mu=0.0, sigma=1.0):
@@ -52,6 +59,16 @@ def dist_laplace(mu=0.0, sigma=1.0):
 
 def dist_student_t(df, mu=0.0, sigma=1.0):
     return Dist("student_t", float(mu), float(sigma), float(df))
+
+
+def dist_gamma(shape, rate):
+    """distributional::dist_gamma(shape, rate) (vignettes/pospkg.Rmd:190-237): support (0, Inf), log-density -Inf outside."""
+    return Dist("gamma", float(shape), float(rate))
+
+
+def dist_exponential(rate):
+    """distributional::dist_exponential(rate)"""
+    return Dist("exponential", 0.0, float(rate))
 
 
 # ------------------------------------------------------------------------------ families (stats::)
@@ -73,7 +90,14 @@ def poisson(link="log"):
     return Family("poisson", link)
 
 
-_FAMILY_BY_NAME = {"gaussian": gaussian, "binomial": binomial, "poisson": poisson}
+def negative_binomial(theta=1.0, link="log"):
+    """MASS::negative.binomial(theta) (vignettes/pospkg.Rmd:132-156).  Like the reference, whose log-density is
+    dnbinom(Y, size = 1, mu = mu) whatever theta is (R/glm_utils.R:55-57), theta is accepted and ignored."""
+    return Family("negative_binomial", link)
+
+
+_FAMILY_BY_NAME = {"gaussian": gaussian, "binomial": binomial, "poisson": poisson, "negative_binomial": negative_binomial}
+_LINKS_OF = {"gaussian": ("identity",), "binomial": ("logit", "probit"), "poisson": ("log",), "negative_binomial": ("log",)}
 
 
 def check_family(family):
@@ -201,26 +225,62 @@ def _r_num(p):
     return s[:-2] if s.endswith(".0") else s
 
 
+class ParamList(list):
+    """param_list of the returned object: a list of {beta, eta, mu} with R-style (partly missing) names."""
+
+    def __init__(self, items, names):
+        super().__init__(items)
+        self.names = names
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            return super().__getitem__(self.names.index(k))
+        return super().__getitem__(k)
+
+
+def _linkinv(fam, eta):
+    """family$linkinv(eta) as stats computes it (R/mcmcglm.R:216, :269): only needed for param_list's `mu`, a value the
+    slice path never reads (quirk Q8); evaluated on the host from the eta the engine returns."""
+    eps = np.finfo(float).eps
+    if fam.link == "identity":
+        return eta.copy()
+    if fam.link == "logit":
+        e = np.where(eta < -30, eps, np.where(eta > 30, 1 / eps, np.exp(np.clip(eta, -30, 30))))
+        return e / (1 + e)
+    if fam.link == "probit":
+        from scipy.special import ndtr
+        return ndtr(np.clip(eta, -8.125890664701906, 8.125890664701906))
+    with np.errstate(over="ignore"):
+        return np.maximum(np.exp(eta), eps)
+
+
 # ------------------------------------------------------------------------------ the front door
 def _engine_kwargs(family, beta_prior, log_likelihood_extra_args):
     fam = check_family(family)
-    if fam.family not in ("gaussian", "binomial", "poisson"):
-        raise L.CggError(L.E_UNSUPPORTED, f"family {fam.family!r} is not supported by the GPU engine")
-    if isinstance(beta_prior, (list, tuple)):
-        raise L.CggError(L.E_UNSUPPORTED, "a list of per-coordinate priors is not supported by the GPU engine "
-                         "(only one iid prior: dist_normal, dist_laplace, dist_student_t)")
-    if not isinstance(beta_prior, Dist):
-        raise L.CggError(L.E_UNSUPPORTED, f"prior {beta_prior!r} is not supported by the GPU engine "
-                         "(supported: dist_normal, dist_laplace, dist_student_t)")
+    if fam.family not in _LINKS_OF:
+        raise L.CggError(L.E_UNSUPPORTED, f"family {fam.family!r} is not supported by the GPU engine (supported: {sorted(_LINKS_OF)})")
+    if fam.link not in _LINKS_OF[fam.family]:
+        raise L.CggError(L.E_UNSUPPORTED, f"link {fam.link!r} is not supported for family {fam.family!r} "
+                         f"(supported: {_LINKS_OF[fam.family]})")
+    # a list of priors: the reference sums EVERY prior at EVERY coordinate (R/glm_utils.R:113-115, quirk Q6) and draws
+    # coordinate j of the start from prior j (R/mcmcglm.R:200-207)
+    plist = list(beta_prior) if isinstance(beta_prior, (list, tuple)) else [beta_prior]
+    for pr in plist:
+        if not isinstance(pr, Dist):
+            raise L.CggError(L.E_UNSUPPORTED, f"prior {pr!r} is not supported by the GPU engine "
+                             "(supported: dist_normal, dist_laplace, dist_student_t, dist_gamma, dist_exponential and lists of them)")
+    if len(plist) > L.MAX_PRIORS:
+        raise L.CggError(L.E_UNSUPPORTED, f"a list of more than {L.MAX_PRIORS} priors is not supported by the GPU engine")
     sd = float((log_likelihood_extra_args or {}).get("sd", 1.0))
-    return fam, dict(family=fam.family, link=fam.link, sd=sd, prior=beta_prior.kind, prior_mu=beta_prior.mu,
-                     prior_sigma=beta_prior.sigma, prior_df=beta_prior.df)
+    p0 = plist[0]
+    return fam, dict(family=fam.family, link=fam.link, sd=sd, prior=p0.kind, prior_mu=p0.mu, prior_sigma=p0.sigma, prior_df=p0.df,
+                     more_priors=tuple(pr.engine_tuple() for pr in plist[1:]))
 
 
 def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likelihood_extra_args=None,
             linear_predictor_calc="update", sample_method="slice_sampling", qslice_fun=slice_stepping_out,
             n_samples=500, burnin=100, *, n_chains=1, device=0, K=8, seed=None, beta_init=None,
-            replay_uniforms=None, driver="persistent", _w_per_chain=None, **tuning):
+            replay_uniforms=None, driver="persistent", keep_param_list=False, _w_per_chain=None, **tuning):
     """mcmcglm() of R/mcmcglm.R:147-299 on the GPU engine.  `**tuning` is the reference's `...` (forwarded
     to qslice_fun: `w`, `max`).  Keyword-only arguments after `burnin` are engine extensions.
     """
@@ -240,9 +300,6 @@ def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likeliho
     if sample_method == "normal-normal":
         raise L.CggError(L.E_UNSUPPORTED, "sample_method = 'normal-normal' (the reference's closed-form test "
                          "sampler, R/sampling.R) is not part of the GPU path")
-    if linear_predictor_calc == "naive":
-        raise L.CggError(L.E_UNSUPPORTED, "linear_predictor_calc = 'naive' is not part of the GPU path "
-                         "(the engine always uses the O(n) CGGibbs update)")
     if qslice_fun is not slice_stepping_out:
         raise L.CggError(L.E_UNSUPPORTED, "only qslice::slice_stepping_out is implemented on the GPU; "
                          f"got {getattr(qslice_fun, '__name__', qslice_fun)!r}")
@@ -254,19 +311,46 @@ def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likeliho
     n, p = X.shape
     rng = np.random.default_rng(seed)
     if beta_init is None:                                                     # :200-213
-        beta0 = np.stack([beta_prior.generate(p, rng) for _ in range(n_chains)])
+        if isinstance(beta_prior, (list, tuple)):                             # list: coordinate j from prior j, :200-207
+            if len(beta_prior) != p:
+                raise ValueError("The list length of the `beta_prior` specification needs to match the number of parameters "
+                                 "in the model (potentially including intercept)")
+            beta0 = np.stack([np.array([pr.generate(1, rng)[0] for pr in beta_prior]) for _ in range(n_chains)])
+        else:
+            beta0 = np.stack([beta_prior.generate(p, rng) for _ in range(n_chains)])
     else:
         beta0 = np.broadcast_to(np.asarray(beta_init, dtype=np.float64), (n_chains, p)).copy()
     mx = tuning.get("max", np.inf)
     eng_seed = int(rng.integers(0, 2 ** 63 - 1)) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 63))
-    with Engine(n, p, w=float(tuning["w"]), max_steps=-1 if np.isinf(mx) else int(mx), n_chains=n_chains, K=K,
-                device=device, driver=driver, seed=eng_seed, **ekw) as e:
+    if np.isfinite(mx) and (mx != np.floor(mx)):
+        raise L.CggError(L.E_ARG, "slice_stepping_out: a finite `max` must be a whole number")
+    max_steps = -1 if np.isinf(mx) else max(int(mx), 0)                       # qslice: a finite max <= 0 means "no stepping out"
+    param_list = None
+    with Engine(n, p, w=float(tuning["w"]), max_steps=max_steps, n_chains=n_chains, K=K,
+                device=device, driver=driver, seed=eng_seed, naive=(linear_predictor_calc == "naive"), **ekw) as e:
         e.set_data(X, Y)
         if _w_per_chain is not None:                                          # a tuning sweep: every chain its own w
             e.set_chain_w(_w_per_chain)
         for c in range(n_chains):
             e.init_chain(c, beta0[c])                                         # :215 init_eta = X %*% init_beta
-        S, st = e.run(n_samples, replay_u=replay_uniforms)                    # :226-274
+        if not keep_param_list:
+            S, st = e.run(n_samples, replay_u=replay_uniforms)                # :226-274
+        else:
+            # param_list (R/mcmcglm.R:183-189, :269, :287): beta, eta and mu of chain 1 after EVERY iteration -- (n_samples + 1)
+            # n-vectors twice over (quirk Q4), so it is opt-in here; the engine is run one iteration at a time and read back
+            if replay_uniforms is not None:
+                raise L.CggError(L.E_ARG, "keep_param_list cannot be combined with replay_uniforms")
+            b, eta = e.state(0)
+            param_list = [dict(beta=b, eta=eta, mu=_linkinv(fam, eta))]
+            parts, st = [], None
+            for _ in range(n_samples):
+                Sk, stk = e.run(1)
+                parts.append(Sk)
+                b, eta = e.state(0)
+                param_list.append(dict(beta=b, eta=eta, mu=_linkinv(fam, eta)))
+                st = stk if st is None else {k: (st[k] + v if isinstance(v, (int, float)) else [a + b_ for a, b_ in zip(st[k], v)] if k != "uniforms_used" else v)
+                                             for k, v in stk.items()}
+            S = np.concatenate(parts, axis=1)
         st["per_chain"] = [e.chain_stats(c) for c in range(n_chains)]
     import pandas as pd
     chains = np.concatenate([beta0[:, None, :], S], axis=1)                   # row 0 = the prior draw, :222
@@ -274,9 +358,16 @@ def mcmcglm(formula, family="gaussian", data=None, beta_prior=None, log_likeliho
     df["iteration"] = np.arange(n_samples + 1)
     df["burnin"] = df["iteration"] <= burnin + 1                              # :197-198 (quirk Q1)
     beta_mean = df.loc[~df["burnin"], names].mean().to_frame().T              # :276-280 (quirk Q3)
-    call = (f"mcmcglm(formula = {formula}, family = \"{fam.family}\", data = <data>, beta_prior = {beta_prior.kind}"
-            f"({beta_prior.mu:g}, {beta_prior.sigma:g}), " + ", ".join(f"{k} = {v}" for k, v in tuning.items()) + ")")
-    return McmcGlm(beta_samples=df, beta_mean=beta_mean, data=data, model_matrix=X, param_list=None, family=fam,
+    pdesc = ", ".join(f"{q.kind}({q.mu:g}, {q.sigma:g})" for q in (beta_prior if isinstance(beta_prior, (list, tuple)) else [beta_prior]))
+    call = (f"mcmcglm(formula = {formula}, family = \"{fam.family}\", data = <data>, beta_prior = {pdesc}, "
+            + ", ".join(f"{k} = {v}" for k, v in tuning.items()) + ")")
+    if param_list is not None:
+        # names as the reference builds them (R/mcmcglm.R:183-189): `ifelse` with a scalar test keeps only "burnin1", so the
+        # names run out before the list does and the remaining entries are unnamed (NA) -- quirk Q4
+        nm = ["init"] + (["burnin1"] if burnin != 0 else []) + [f"iteration{i}" for i in range(1, n_samples - burnin + 1)]
+        nm = (nm + [None] * (n_samples + 1))[:n_samples + 1]
+        param_list = ParamList(param_list, nm)
+    return McmcGlm(beta_samples=df, beta_mean=beta_mean, data=data, model_matrix=X, param_list=param_list, family=fam,
                    formula=formula, call=call, burnin=burnin, sample_method=sample_method, qslice_fun=qslice_fun,
                    tuning=dict(tuning), chains=chains, stats=st)
 
@@ -286,8 +377,8 @@ def log_potential_from_betaj(new_beta_j, j, current_beta, current_eta, Y, X, fam
                              linear_predictor_calc="update", device=0, **extra):
     """log_potential_from_betaj of R/glm_utils.R:187-218 evaluated by the GPU kernel (K1).
     `j` is 1-based, as in the reference.  `new_beta_j` may be a scalar or an array of candidates."""
-    if linear_predictor_calc != "update":
-        raise L.CggError(L.E_UNSUPPORTED, "linear_predictor_calc = 'naive' is not part of the GPU path")
+    if linear_predictor_calc not in ("update", "naive"):
+        raise ValueError("'arg' should be one of 'update', 'naive'")
     _, ekw = _engine_kwargs(family, beta_prior, {"sd": extra.get("sd", 1.0)})
     X = np.asarray(X, dtype=np.float64)
     n, p = X.shape
@@ -295,7 +386,10 @@ def log_potential_from_betaj(new_beta_j, j, current_beta, current_eta, Y, X, fam
         raise IndexError("j is 1-based and must be in 1..ncol(X)")
     with Engine(n, p, w=1.0, n_chains=1, device=device, driver="stepwise", **ekw) as e:
         e.set_data(X, Y)
-        e.set_state(0, current_beta, current_eta)
+        if linear_predictor_calc == "naive":     # R/glm_utils.R:206-208: new_eta <- X %*% new_beta; current_eta is not used
+            e.init_chain(0, current_beta)        # eta = X %*% current_beta on the device (K4), then eta + X_j (b - beta_j)
+        else:
+            e.set_state(0, current_beta, current_eta)
         out = e.log_potential(0, j - 1, new_beta_j)
     return float(out[0]) if np.ndim(new_beta_j) == 0 else out
 
@@ -348,3 +442,54 @@ def mcmcglm_across_tuningparams(*values, tuning_parameter_name="w", parallelise=
                                call=fit.call.replace(f"w = {chunk[0]}", f"w = {v}"), burnin=fit.burnin, sample_method=fit.sample_method,
                                qslice_fun=fit.qslice_fun, tuning={**fit.tuning, "w": v}, chains=fit.chains[c:c + 1], stats=st))
     return out
+
+
+# ------------------------------------------------------------------------------ runtime comparison (R/measure_performance.R)
+def generate_normal_data(n_vars, n=100, beta=None, sd=1.0, rng=None):
+    """generate_normal_data of R/measure_performance.R:46-63: gaussian response, intercept + (n_vars - 1) N(0, 1) columns."""
+    import pandas as pd
+    rng = np.random.default_rng() if rng is None else rng
+    beta = np.ones(n_vars) if beta is None else np.asarray(beta, dtype=np.float64)
+    Xs = rng.standard_normal((n, n_vars - 1))
+    y = beta[0] + Xs @ beta[1:] + sd * rng.standard_normal(n)
+    d = pd.DataFrame(Xs, columns=[f"X{i}" for i in range(1, n_vars)])
+    d.insert(0, "Y", y)
+    return d
+
+
+def compare_eta_comptime(formula, family="gaussian", data=None, beta_prior=None, log_likelihood_extra_args=None,
+                         sample_method="slice_sampling", qslice_fun=slice_stepping_out, n_samples=500, burnin=100, **tuning):
+    """compare_eta_comptime of R/measure_performance.R:3-42: the same mcmcglm() call timed with linear_predictor_calc =
+    "update" (the O(n) CGGibbs update) and "naive" (eta recomputed from scratch, O(n p)); one row per method."""
+    import time
+    import pandas as pd
+    beta_prior = dist_normal(0, 1) if beta_prior is None else beta_prior
+    lla = {"sd": 1} if log_likelihood_extra_args is None else log_likelihood_extra_args
+    rows = []
+    for calc in ("update", "naive"):
+        t0 = time.perf_counter()
+        m = mcmcglm(formula, family, data, beta_prior, lla, calc, sample_method, qslice_fun, n_samples, burnin,
+                    driver="stepwise", **tuning)
+        rows.append({"time": time.perf_counter() - t0, "linear_predictor_calc": calc, "n_vars": m.model_matrix.shape[1],
+                     "n_samples": n_samples, "beta_mean": getattr(beta_prior, "mu", None), "beta_variance": getattr(beta_prior, "sigma", 1.0) ** 2,
+                     "family": m.family.family, **lla, "qslice_fun": "qslice::slice_stepping_out", **tuning})
+    return pd.DataFrame(rows)
+
+
+def compare_eta_comptime_across_nvars(n_vars, n=100, beta_prior=None, log_likelihood_extra_args=None, sample_method="slice_sampling",
+                                      qslice_fun=slice_stepping_out, n_samples=500, burnin=100, parallelise=False, n_cores=None,
+                                      rng=None, **tuning):
+    """compare_eta_comptime_across_nvars of R/measure_performance.R:113-151 (the experiment of vignettes/performance.Rmd:31-41):
+    for every number of variables, simulate gaussian data and time "update" against "naive".  w defaults to 0.5 like the
+    reference's; parallelise / n_cores are accepted and ignored (one GPU)."""
+    import pandas as pd
+    if qslice_fun is slice_stepping_out and not tuning:
+        tuning = {"w": 0.5}
+    out = []
+    for nv in np.atleast_1d(n_vars):
+        d = generate_normal_data(int(nv), n=n, rng=rng)
+        out.append(compare_eta_comptime("Y ~ .", "gaussian", d, beta_prior, log_likelihood_extra_args, sample_method, qslice_fun,
+                                        n_samples, burnin, **tuning))
+    res = pd.concat(out, ignore_index=True)
+    res["parallelised"] = bool(parallelise)
+    return res

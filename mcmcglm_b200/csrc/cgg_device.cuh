@@ -126,7 +126,7 @@ struct Dev {
     uint32_t mbox_stamp0;      // stamps already used by earlier runs of this handle (all ranks agree: they run identical passes)
     int32_t rank;
     uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
-    PriorParams prior;
+    PriorSet prior;
     int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache;   // pair: chains 2k, 2k+1 share a pass when they can;
                                                                                                   // colcache: tiles per slot of the per-warp X-column cache (0: off)
 };

@@ -225,6 +225,18 @@ template <> struct JetRow<CGG_POISSON> {
     }
 };
 
+// negative binomial and binomial-probit: exact passes only (the engine never asks for a jet pass); stubs so that the pass
+// templates instantiate
+template <int FAMILY> struct JetRowNone {
+    static constexpr unsigned RISK_KEY = 0u;       // "every row is a risk": an enclosure would never apply
+    template <bool FULL>
+    static __device__ __forceinline__ void add1(double, double, double, double, const double2 *, double (&)[JET_NV], unsigned &) {}
+    template <bool FULL>
+    static __device__ __forceinline__ void add2(double2, double2, double2, double, const double2 *, double (&)[JET_NV], unsigned &) {}
+};
+template <> struct JetRow<CGG_KF_NEGBIN> : JetRowNone<CGG_KF_NEGBIN> {};
+template <> struct JetRow<CGG_KF_PROBIT> : JetRowNone<CGG_KF_PROBIT> {};
+
 // A binomial LIGHT pass delivers five values, compactly: m1, m2, m3, the noise sum (canonical slot 8), the risk-row count
 // (canonical slot 9).  pack: canonical -> compact (worker, before the reduction); unpack: compact -> canonical (decider).
 constexpr int JET_NVL = 5;

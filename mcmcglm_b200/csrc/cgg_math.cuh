@@ -79,11 +79,15 @@ __device__ __forceinline__ double poly_l1p_q(double v, double v2) {
     return fma(qo, v, qe);
 }
 // z0 / z1: the row's response is 0 (s = eta): R's log(q) form applies above kRFormLo (see rform_log1p_rho)
+// LOGIT (default): stats' logit clamp at |s| > 30.  !LOGIT (negative binomial, log link): plain softplus for any s; for
+// |s| > 64 the correction log1p(exp(-|s|)) < 2e-28 is evaluated at 64 (it cannot change the sum).
+template <bool LOGIT = true>
 __device__ __forceinline__ void softplus2(double s0, double s1, const double2 *tab, double &o0, double &o1, bool z0 = false, bool z1 = false) {
     const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to nearest integer
     double a0 = fabs(s0), a1 = fabs(s1);
-    a0 = (a0 > 30.0) ? kLogitClampEta : a0;
-    a1 = (a1 > 30.0) ? kLogitClampEta : a1;
+    const double b0 = a0, b1 = a1;              // |s| as it enters the result
+    if (LOGIT) { a0 = (a0 > 30.0) ? kLogitClampEta : a0; a1 = (a1 > 30.0) ? kLogitClampEta : a1; }
+    else { a0 = (a0 > 64.0) ? 64.0 : a0; a1 = (a1 > 64.0) ? 64.0 : a1; }
     const double kd0 = fma(-a0, 1.4426950408889634, SHIFT), kd1 = fma(-a1, 1.4426950408889634, SHIFT);
     const double kf0 = kd0 - SHIFT, kf1 = kd1 - SHIFT;
     double r0 = fma(kf0, -6.93147180369123816490e-01, -a0), r1 = fma(kf1, -6.93147180369123816490e-01, -a1);
@@ -100,8 +104,9 @@ __device__ __forceinline__ void softplus2(double s0, double s1, const double2 *t
     const double w0 = v0 * v0, w1 = v1 * v1;
     const double q0 = poly_l1p_q(v0, w0), q1 = poly_l1p_q(v1, w1);
     const double l0 = tb0.y + fma(w0, q0, v0), l1 = tb1.y + fma(w1, q1, v1);
-    o0 = ((s0 > 0.0) ? a0 : 0.0) + l0;
-    o1 = ((s1 > 0.0) ? a1 : 0.0) + l1;
+    o0 = ((s0 > 0.0) ? (LOGIT ? a0 : b0) : 0.0) + l0;
+    o1 = ((s1 > 0.0) ? (LOGIT ? a1 : b1) : 0.0) + l1;
+    if (!LOGIT) return;
     const bool f0 = z0 && s0 > kRFormLo && s0 <= 30.0, f1 = z1 && s1 > kRFormLo && s1 <= 30.0;
     if (f0 || f1) {     // rare once a chain is near its stationary region (|eta| of a few units)
         if (f0) o0 -= rform_log1p_rho(t0, scale2(fma(-po0, r0, pe0), -__double2loint(kd0)));
@@ -179,6 +184,44 @@ template <> struct RowPair<CGG_POISSON> {
     }
 };
 
+// Kernel-side family codes beyond the header's: binomial with the probit link is a family of its own here
+constexpr int CGG_KF_NEGBIN = CGG_NEGATIVE_BINOMIAL;   // 3
+constexpr int CGG_KF_PROBIT = 4;
+constexpr double kProbitThresh = 8.125890664701906;    // -qnorm(.Machine$double.eps): stats' probit link clamps eta to +-this
+
+// negative binomial, log link (R/glm_utils.R:55-57): dnbinom(y, size = 1, mu = pmax(exp(eta'), eps), log = TRUE)
+//   = y log(mu) - (y + 1) log(1 + mu) = y l - (y + 1) softplus(l),  l = log(mu) = max(eta', log eps);  exp overflow -> -Inf
+template <> struct RowPair<CGG_KF_NEGBIN> {
+    double y0, y1, e0, e1, x0, x1;
+    __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) : y0(y.x), y1(y.y), e0(e.x), e1(e.y), x0(x.x), x1(x.y) {}
+    __device__ __forceinline__ double term(double dk, double, const double2 *tab) const {
+        double l0 = eta_shift(e0, x0, dk), l1 = eta_shift(e1, x1, dk);
+        l0 = (l0 < kLogEps) ? kLogEps : l0; l1 = (l1 < kLogEps) ? kLogEps : l1;
+        double o0, o1;
+        softplus2<false>(l0, l1, tab, o0, o1);
+        const double v0 = (l0 > 709.782712893384) ? -INFINITY : fma(y0, l0, -(y0 + 1.0) * o0);
+        const double v1 = (l1 > 709.782712893384) ? -INFINITY : fma(y1, l1, -(y1 + 1.0) * o1);
+        return v0 + v1;
+    }
+};
+
+// binomial, probit link (vignettes/pospkg.Rmd:88-108): dbinom(y, 1, p, log = TRUE) with p = pnorm(clamped eta'), q = 1 - p as
+// R forms it; dbinom_raw's branches -bd0(1, p) - q (q < 0.1) and -bd0(1, q) - p (p < 0.1) equal log(p) = log1p(-q) and
+// log(q) = log1p(-p) evaluated without cancellation.
+__device__ __forceinline__ double probit_term(double y, double eta) {
+    const double t = (eta < -kProbitThresh) ? -kProbitThresh : ((eta > kProbitThresh) ? kProbitThresh : eta);   // NaN stays NaN
+    const double p = normcdf(t), q = 1.0 - p;
+    if (y > 0.5) return (q < 0.1) ? log1p(-q) : log(p);
+    return (p < 0.1) ? log1p(-p) : log(q);
+}
+template <> struct RowPair<CGG_KF_PROBIT> {
+    double y0, y1, e0, e1, x0, x1;
+    __device__ __forceinline__ RowPair(double2 y, double2 e, double2 x) : y0(y.x), y1(y.y), e0(e.x), e1(e.y), x0(x.x), x1(x.y) {}
+    __device__ __forceinline__ double term(double dk, double, const double2 *) const {
+        return probit_term(y0, eta_shift(e0, x0, dk)) + probit_term(y1, eta_shift(e1, x1, dk));
+    }
+};
+
 // Single-row form (odd last row of a matrix, diagnostics): the pair with a neutral second row removed.
 template <int FAMILY>
 __device__ __forceinline__ double row_term(double y, double eta, double inv_sd, const double2 *tab) {
@@ -188,6 +231,13 @@ __device__ __forceinline__ double row_term(double y, double eta, double inv_sd, 
         const double s = (y > 0.5) ? -eta : eta;
         softplus2(s, s, tab, o0, o1, !(y > 0.5), false);
         return -o0;
+    }
+    if (FAMILY == CGG_KF_PROBIT) return probit_term(y, eta);
+    if (FAMILY == CGG_KF_NEGBIN) {
+        const double l = (eta < kLogEps) ? kLogEps : eta;
+        double o0, o1;
+        softplus2<false>(l, l, tab, o0, o1);
+        return (l > 709.782712893384) ? -INFINITY : fma(y, l, -(y + 1.0) * o0);
     }
     double le = (eta < kLogEps) ? kLogEps : eta;
     const double mu = exp(le);
@@ -211,11 +261,28 @@ struct PriorParams {
 };
 
 // distributional::density(beta_prior, x, log = TRUE) for one coordinate (R/glm_utils.R:109)
-__device__ __forceinline__ double prior_logdens(const PriorParams &pp, double x) {
+__device__ __forceinline__ double prior_logdens1(const PriorParams &pp, double x) {
     double z = (x - pp.mu) * pp.inv_sigma;
     if (pp.kind == CGG_PRIOR_NORMAL) return pp.c0 - 0.5 * z * z;        // -(ln sqrt(2pi) + z^2/2 + log sigma)
     if (pp.kind == CGG_PRIOR_LAPLACE) return pp.c0 - fabs(z);           // -log(2 sigma) - |x - mu| / sigma
-    return pp.c0 - 0.5 * (pp.df + 1.0) * log1p(z * z / pp.df);          // dt(z, df, log=TRUE) - log(sigma)
+    if (pp.kind == CGG_PRIOR_STUDENT_T) return pp.c0 - 0.5 * (pp.df + 1.0) * log1p(z * z / pp.df);   // dt(z, df, log=TRUE) - log(sigma)
+    if (x != x) return x;
+    if (pp.kind == CGG_PRIOR_GAMMA) {                                   // dgamma(x, shape = mu, rate = sigma, log = TRUE); c0 = shape log(rate) - lgamma(shape)
+        if (x < 0.0) return -INFINITY;
+        if (x == 0.0) return (pp.mu < 1.0) ? INFINITY : ((pp.mu > 1.0) ? -INFINITY : pp.c0);
+        return pp.c0 + (pp.mu - 1.0) * log(x) - pp.sigma * x;
+    }
+    return (x < 0.0) ? -INFINITY : pp.c0 - pp.sigma * x;                // dexp(x, rate = sigma, log = TRUE); c0 = log(rate)
+}
+// A list of priors: every component at every coordinate, summed (log_prior_density.list, R/glm_utils.R:113-115, quirk Q6)
+struct PriorSet {
+    PriorParams comp[CGG_MAX_PRIORS];
+    int n, pad;
+};
+__device__ __forceinline__ double prior_logdens(const PriorSet &ps, double x) {
+    double v = prior_logdens1(ps.comp[0], x);
+    for (int k = 1; k < ps.n; ++k) v += prior_logdens1(ps.comp[k], x);
+    return v;
 }
 
 // Philox4x32-10 (Salmon et al. 2011); same definition as oracle.c:orc_philox_uniform.

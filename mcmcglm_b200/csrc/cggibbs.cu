@@ -494,6 +494,15 @@ __global__ void __launch_bounds__(THREADS) init_eta_kernel(Dev d, int c) {
     }
 }
 
+// linear_predictor_calc = "naive" (R/glm_utils.R:206-208): the reference then forms new_eta <- X %*% new_beta for every
+// evaluation, O(n p) instead of the O(n) update.  The engine's naive mode recomputes eta = X beta from scratch (K4) before
+// every pass over the rows; an accepted value is already in beta, so the deferred eta update of that chain is dropped.
+__global__ void naive_drop_commit_kernel(Dev d) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    d.ctl[c].commit_j = -1; d.ctl[c].commit_delta = 0.0;
+}
+
 // K2 stand-alone: eta <- eta + X_j * diff (R/glm_utils.R:126-132)
 __global__ void __launch_bounds__(THREADS) axpy_eta_kernel(Dev d, int c, int64_t j, double diff) {
     const double *xj = d.X + j * d.ldx;
@@ -522,6 +531,8 @@ __global__ void row_terms_kernel(int family, int64_t n, const double *y, const d
         double v;
         if (family == CGG_GAUSSIAN) v = RowPair<CGG_GAUSSIAN>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
         else if (family == CGG_BINOMIAL) v = RowPair<CGG_BINOMIAL>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
+        else if (family == CGG_KF_NEGBIN) v = RowPair<CGG_KF_NEGBIN>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
+        else if (family == CGG_KF_PROBIT) v = RowPair<CGG_KF_PROBIT>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
         else v = RowPair<CGG_POISSON>(yy, ee, xx).term(0.0, inv_sd, s_l1p);
         out[i] = 0.5 * v;
     }
@@ -599,11 +610,11 @@ __global__ void __launch_bounds__(THREADS) scan_y_kernel(Dev d, double *partial,
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * THREADS) {
         const double y = d.y[i];
         if (d.family == CGG_GAUSSIAN) nbad += !isfinite(y);
-        else if (d.family == CGG_BINOMIAL) nbad += !(y == 0.0 || y == 1.0);
-        else {
+        else if (d.family == CGG_BINOMIAL || d.family == CGG_KF_PROBIT) nbad += !(y == 0.0 || y == 1.0);
+        else {       // poisson, negative binomial: counts
             const bool ok = isfinite(y) && y >= 0.0 && y == floor(y);
             nbad += !ok;
-            if (ok) acc += lgamma(y + 1.0);
+            if (ok && d.family == CGG_POISSON) acc += lgamma(y + 1.0);
         }
     }
     acc = warp_sum(acc);
@@ -841,6 +852,25 @@ struct cgg_handle {
     std::vector<ChainState> last_cs;      // the chains' counters after the last cgg_run (cgg_get_chain_stats)
 };
 
+// one component of the prior; returns false (with the message set) if the parameters are invalid
+static bool make_prior(int kind, double a, double b, double c, PriorParams &pp) {
+    pp.kind = kind; pp.mu = a; pp.sigma = b; pp.df = c; pp.c0 = 0.0; pp.inv_sigma = 1.0;
+    if (kind < CGG_PRIOR_NORMAL || kind > CGG_PRIOR_EXPONENTIAL) {
+        fail(CGG_E_UNSUPPORTED, "unsupported prior %d; supported: normal, laplace, student_t, gamma, exponential", kind);
+        return false;
+    }
+    if (!(b > 0.0) || !std::isfinite(b)) { fail(CGG_E_ARG, "prior scale / rate must be positive"); return false; }
+    if (kind == CGG_PRIOR_STUDENT_T && !(c > 0.0)) { fail(CGG_E_ARG, "student-t df must be positive"); return false; }
+    if (kind == CGG_PRIOR_GAMMA && !(a > 0.0)) { fail(CGG_E_ARG, "gamma shape must be positive"); return false; }
+    pp.inv_sigma = 1.0 / b;
+    if (kind == CGG_PRIOR_NORMAL) pp.c0 = -(kLnSqrt2Pi + log(b));
+    else if (kind == CGG_PRIOR_LAPLACE) pp.c0 = -log(2.0 * b);
+    else if (kind == CGG_PRIOR_STUDENT_T) pp.c0 = lgamma(0.5 * (c + 1.0)) - lgamma(0.5 * c) - 0.5 * log(c * M_PI) - log(b);
+    else if (kind == CGG_PRIOR_GAMMA) pp.c0 = a * log(b) - lgamma(a);
+    else pp.c0 = log(b);
+    return true;
+}
+
 extern "C" const char *cgg_last_error(void) { return g_err.c_str(); }
 extern "C" int cgg_abi_version(void) { return CGG_ABI_VERSION; }
 
@@ -854,7 +884,10 @@ static void *kernel_ptr(int family, int which) {     // which: 0 persistent swee
     case CGG_BINOMIAL * 3 + 2: return (void *)sweep_cluster_kernel<CGG_BINOMIAL>;
     case CGG_POISSON * 3 + 0: return (void *)sweep_persistent_kernel<CGG_POISSON>;
     case CGG_POISSON * 3 + 1: return (void *)pass_kernel<CGG_POISSON>;
-    default: return (void *)sweep_cluster_kernel<CGG_POISSON>;
+    case CGG_POISSON * 3 + 2: return (void *)sweep_cluster_kernel<CGG_POISSON>;
+    case CGG_KF_NEGBIN * 3 + 1: return (void *)pass_kernel<CGG_KF_NEGBIN>;       // exact passes, stepwise driver only
+    case CGG_KF_PROBIT * 3 + 1: return (void *)pass_kernel<CGG_KF_PROBIT>;
+    default: return nullptr;
     }
 }
 
@@ -895,16 +928,21 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (cfg->K < 1 || cfg->K > CGG_KMAX) return fail(CGG_E_ARG, "cgg_create: K must be in 1..%d", CGG_KMAX);
     if (!(cfg->w > 0.0) || !std::isfinite(cfg->w)) return fail(CGG_E_ARG, "cgg_create: slice width w must be positive and finite");
     const bool fam_ok = (cfg->family == CGG_GAUSSIAN && cfg->link == CGG_LINK_IDENTITY) ||
-                        (cfg->family == CGG_BINOMIAL && cfg->link == CGG_LINK_LOGIT) ||
-                        (cfg->family == CGG_POISSON && cfg->link == CGG_LINK_LOG);
-    if (!fam_ok) return fail(CGG_E_UNSUPPORTED, "cgg_create: unsupported family/link pair (%d, %d); supported: gaussian/identity, binomial/logit, poisson/log", cfg->family, cfg->link);
-    if (cfg->prior < CGG_PRIOR_NORMAL || cfg->prior > CGG_PRIOR_STUDENT_T) return fail(CGG_E_UNSUPPORTED, "cgg_create: unsupported prior %d; supported: normal, laplace, student_t", cfg->prior);
-    if (!(cfg->prior_sigma > 0.0)) return fail(CGG_E_ARG, "cgg_create: prior scale must be positive");
-    if (cfg->prior == CGG_PRIOR_STUDENT_T && !(cfg->prior_df > 0.0)) return fail(CGG_E_ARG, "cgg_create: student-t df must be positive");
+                        (cfg->family == CGG_BINOMIAL && (cfg->link == CGG_LINK_LOGIT || cfg->link == CGG_LINK_PROBIT)) ||
+                        (cfg->family == CGG_POISSON && cfg->link == CGG_LINK_LOG) ||
+                        (cfg->family == CGG_NEGATIVE_BINOMIAL && cfg->link == CGG_LINK_LOG);
+    if (!fam_ok) return fail(CGG_E_UNSUPPORTED, "cgg_create: unsupported family/link pair (%d, %d); supported: gaussian/identity, binomial/logit, binomial/probit, poisson/log, negative binomial/log", cfg->family, cfg->link);
+    // kernel-side family: binomial + probit is a family of its own; it and the negative binomial run exact passes on the stepwise driver
+    const int kf = (cfg->family == CGG_BINOMIAL && cfg->link == CGG_LINK_PROBIT) ? CGG_KF_PROBIT : cfg->family;
+    const bool exact_only = kf == CGG_KF_NEGBIN || kf == CGG_KF_PROBIT;
+    if (exact_only && cfg->mode == CGG_MODE_ROW_SHARDED) return fail(CGG_E_UNSUPPORTED, "cgg_create: binomial/probit and negative binomial are not available row-sharded");
+    PriorParams pp0;
+    if (!make_prior(cfg->prior, cfg->prior_mu, cfg->prior_sigma, cfg->prior_df, pp0)) { g_err = "cgg_create: " + g_err; return (cfg->prior < CGG_PRIOR_NORMAL || cfg->prior > CGG_PRIOR_EXPONENTIAL) ? CGG_E_UNSUPPORTED : CGG_E_ARG; }
     if (cfg->family == CGG_GAUSSIAN && !(cfg->sd > 0.0)) return fail(CGG_E_ARG, "cgg_create: gaussian sd must be positive");
     if (cfg->driver != CGG_DRIVER_PERSISTENT && cfg->driver != CGG_DRIVER_STEPWISE && cfg->driver != CGG_DRIVER_CLUSTER) return fail(CGG_E_ARG, "cgg_create: unknown driver");
     if (cfg->mode != CGG_MODE_CHAINS && cfg->mode != CGG_MODE_ROW_SHARDED) return fail(CGG_E_ARG, "cgg_create: unknown mode");
     if (cfg->mode == CGG_MODE_ROW_SHARDED && cfg->driver == CGG_DRIVER_CLUSTER) return fail(CGG_E_ARG, "cgg_create: row-sharded mode runs on the persistent (peer mailboxes) or the stepwise driver");
+    if ((cfg->flags & CGG_FLAG_NAIVE) && cfg->mode == CGG_MODE_ROW_SHARDED) return fail(CGG_E_UNSUPPORTED, "cgg_create: the naive linear-predictor mode is not available row-sharded");
     if (cfg->driver == CGG_DRIVER_CLUSTER && cfg->n > (1LL << 22)) return fail(CGG_E_ARG, "cgg_create: the cluster driver is for small n (<= 2^22 rows per chain)");
 
     int ndev = 0;
@@ -914,6 +952,10 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
 
     cgg_handle *h = new cgg_handle();
     h->cfg = *cfg;
+    h->cfg.family = kf;                                      // from here on: the kernel-side family
+    if (exact_only) { h->cfg.driver = CGG_DRIVER_STEPWISE; h->cfg.flags |= CGG_FLAG_NO_JET | CGG_FLAG_NO_CLUSTER; }
+    if (h->cfg.flags & CGG_FLAG_NAIVE) { h->cfg.driver = CGG_DRIVER_STEPWISE; h->cfg.flags |= CGG_FLAG_NO_CLUSTER; }   // host-launched GEMV before every pass
+    cfg = &h->cfg;
     memset(&h->d, 0, sizeof(Dev));
     Dev &d = h->d;
     const int C = cfg->n_chains;
@@ -933,11 +975,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
         d.pair = e ? atoi(e) : (C >= 4);
     }
     d.jet_light = d.jet && !(cfg->flags & CGG_FLAG_NO_JET_LIGHT);
-    d.prior.kind = cfg->prior; d.prior.mu = cfg->prior_mu; d.prior.sigma = cfg->prior_sigma; d.prior.df = cfg->prior_df;
-    d.prior.inv_sigma = 1.0 / cfg->prior_sigma;
-    if (cfg->prior == CGG_PRIOR_NORMAL) d.prior.c0 = -(kLnSqrt2Pi + log(cfg->prior_sigma));
-    else if (cfg->prior == CGG_PRIOR_LAPLACE) d.prior.c0 = -log(2.0 * cfg->prior_sigma);
-    else d.prior.c0 = lgamma(0.5 * (cfg->prior_df + 1.0)) - lgamma(0.5 * cfg->prior_df) - 0.5 * log(cfg->prior_df * M_PI) - log(cfg->prior_sigma);
+    d.prior.comp[0] = pp0; d.prior.n = 1;
 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -963,9 +1001,9 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
         d.colcache = (want && Wg > 0 && n_tiles >= Wg && need <= room) ? (int)tpw : 0;
         h->smem += (size_t)NWARPS * 2 * (size_t)d.colcache * 512;
     }
-    CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (!exact_only) CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CK(cudaFuncSetAttribute(kernel_ptr(cfg->family, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_ptr(cfg->family, 0), THREADS, h->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_ptr(cfg->family, exact_only ? 1 : 0), THREADS, h->smem));
     if (occ < 1) { delete h; return fail(CGG_E_CUDA, "cgg_create: sweep kernel does not fit on an SM"); }
     if (occ > 1) occ = 1;
     h->max_grid = occ * h->num_sms;
@@ -1364,7 +1402,7 @@ extern "C" int cgg_get_state(cgg_handle *h, int32_t chain, double *beta_host, do
 extern "C" int cgg_debug_row_terms(int32_t device, int32_t family, int64_t n, const double *y_host, const double *eta_host,
                                    double sd, double *out_host) {
     if (n <= 0 || !y_host || !eta_host || !out_host) return fail(CGG_E_ARG, "cgg_debug_row_terms: bad argument");
-    if (family < CGG_GAUSSIAN || family > CGG_POISSON) return fail(CGG_E_UNSUPPORTED, "cgg_debug_row_terms: unsupported family");
+    if (family < CGG_GAUSSIAN || family > CGG_KF_PROBIT) return fail(CGG_E_UNSUPPORTED, "cgg_debug_row_terms: unsupported family (0 gaussian, 1 binomial/logit, 2 poisson, 3 negative binomial, 4 binomial/probit)");
     CK(cudaSetDevice(device));
     double *dy = nullptr, *de = nullptr, *dout = nullptr;
     CK(cudaMalloc((void **)&dy, sizeof(double) * n));
@@ -1531,6 +1569,17 @@ extern "C" int cgg_p2p_connect(cgg_handle *h, int32_t rank, int32_t world, void 
     return CGG_OK;
 }
 
+extern "C" int cgg_add_prior(cgg_handle *h, int32_t kind, double a, double b, double c) {
+    if (!h) return fail(CGG_E_ARG, "cgg_add_prior: NULL handle");
+    if (h->d.prior.n >= CGG_MAX_PRIORS) return fail(CGG_E_UNSUPPORTED, "cgg_add_prior: at most %d priors in a list", CGG_MAX_PRIORS);
+    PriorParams pp;
+    if (!make_prior(kind, a, b, c, pp)) { g_err = "cgg_add_prior: " + g_err; return (kind < CGG_PRIOR_NORMAL || kind > CGG_PRIOR_EXPONENTIAL) ? CGG_E_UNSUPPORTED : CGG_E_ARG; }
+    h->d.prior.comp[h->d.prior.n++] = pp;
+    std::fill(h->fx_valid.begin(), h->fx_valid.end(), 0);
+    std::fill(h->fx_mag.begin(), h->fx_mag.end(), 0);
+    return CGG_OK;
+}
+
 extern "C" int cgg_set_chain_w(cgg_handle *h, const double *w_host) {
     if (!h || !w_host) return fail(CGG_E_ARG, "cgg_set_chain_w: NULL argument");
     for (int c = 0; c < h->d.C; ++c)
@@ -1687,6 +1736,12 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         const int batch = (d.sharded && !h->comm) ? 1 : 32;   // host callbacks are synchronous; NCCL and kernels queue up
         for (;;) {
             for (int i = 0; i < batch; ++i) {
+                if (h->cfg.flags & CGG_FLAG_NAIVE) {        // eta <- X %*% beta for every chain, O(n p), before every pass
+                    const int grid = (int)std::min<int64_t>((d.n / 2 + THREADS - 1) / THREADS + 1, 8 * h->num_sms);
+                    for (int c = 0; c < C; ++c) init_eta_kernel<<<grid, THREADS, 0, h->stream>>>(d, c);
+                    naive_drop_commit_kernel<<<(C + 31) / 32, 32, 0, h->stream>>>(d);
+                    launches += C + 1;
+                }
                 int rc = launch_pass(h, d.sharded ? 1 : 0);
                 if (rc) return rc;
                 ++launches;

@@ -5,9 +5,12 @@ import numpy as np
 from . import _lib as L
 
 FAMILIES = {"gaussian": (L.GAUSSIAN, L.LINK_IDENTITY), "binomial": (L.BINOMIAL, L.LINK_LOGIT),
-            "poisson": (L.POISSON, L.LINK_LOG)}
-LINKS = {"identity": L.LINK_IDENTITY, "logit": L.LINK_LOGIT, "log": L.LINK_LOG}
-PRIORS = {"normal": L.PRIOR_NORMAL, "laplace": L.PRIOR_LAPLACE, "student_t": L.PRIOR_STUDENT_T}
+            "poisson": (L.POISSON, L.LINK_LOG), "negative_binomial": (L.NEGATIVE_BINOMIAL, L.LINK_LOG)}
+LINKS = {"identity": L.LINK_IDENTITY, "logit": L.LINK_LOGIT, "log": L.LINK_LOG, "probit": L.LINK_PROBIT}
+PRIORS = {"normal": L.PRIOR_NORMAL, "laplace": L.PRIOR_LAPLACE, "student_t": L.PRIOR_STUDENT_T, "gamma": L.PRIOR_GAMMA,
+          "exponential": L.PRIOR_EXPONENTIAL}
+# kernel-side family codes (cgg_debug_row_terms): binomial with the probit link is a family of its own there
+ROW_TERM_FAMILIES = {"gaussian": 0, "binomial": 1, "poisson": 2, "negative_binomial": 3, "binomial_probit": 4}
 # "persistent": the engine picks the grid-wide kernel or, for small n, one cluster per chain; "grid" / "cluster" force one
 DRIVERS = {"persistent": L.DRIVER_PERSISTENT, "grid": L.DRIVER_PERSISTENT, "cluster": L.DRIVER_CLUSTER, "stepwise": L.DRIVER_STEPWISE}
 
@@ -23,7 +26,7 @@ def debug_row_terms(family, y, eta, sd=1.0, device=0):
     lib = L.load()
     y, eta = _f64(y).ravel(), _f64(eta).ravel()
     out = np.empty_like(y)
-    L.check(lib.cgg_debug_row_terms(device, FAMILIES[family][0], y.size, y.ctypes.data_as(_dp), eta.ctypes.data_as(_dp),
+    L.check(lib.cgg_debug_row_terms(device, ROW_TERM_FAMILIES[family], y.size, y.ctypes.data_as(_dp), eta.ctypes.data_as(_dp),
                                     float(sd), out.ctypes.data_as(_dp)))
     return out
 
@@ -34,7 +37,9 @@ class Engine:
     def __init__(self, n, p, family="gaussian", link=None, sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0,
                  prior_df=1.0, w=0.5, max_steps=-1, n_chains=1, K=8, device=0, driver="persistent", seed=0,
                  chain_offset=0, spec_tau=0.12, rows_per_cta_min=0, row_sharded=False, prefilter=True, jet=True,
-                 jet_light=True, jet_bound_scale=1.0):
+                 jet_light=True, jet_bound_scale=1.0, more_priors=(), naive=False):
+        """more_priors: further components of a LIST of priors (every component is evaluated at every coordinate, like the
+        reference does): tuples (kind, a, b, c) = (mu, sigma, df) | gamma (shape, rate, -) | exponential (-, rate, -)."""
         self._h = None
         self._lib = L.load()
         if family not in FAMILIES:
@@ -56,11 +61,16 @@ class Engine:
                        mode=L.MODE_ROW_SHARDED if row_sharded else L.MODE_CHAINS, chain_offset=chain_offset,
                        seed=seed, spec_tau=spec_tau, rows_per_cta_min=rows_per_cta_min,
                        flags=((0 if prefilter else L.FLAG_NO_PREFILTER) | (0 if jet else L.FLAG_NO_JET)
-                              | (0 if jet_light else L.FLAG_NO_JET_LIGHT) | (L.FLAG_NO_CLUSTER if driver == "grid" else 0)),
+                              | (0 if jet_light else L.FLAG_NO_JET_LIGHT) | (L.FLAG_NO_CLUSTER if driver == "grid" else 0)
+                              | (L.FLAG_NAIVE if naive else 0)),
                        jet_bound_scale=jet_bound_scale)
         h = C.c_void_p()
         L.check(self._lib.cgg_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        for kind, a, b, c in more_priors:
+            if kind not in PRIORS:
+                raise L.CggError(L.E_UNSUPPORTED, f"unsupported prior {kind!r}; supported: {sorted(PRIORS)}")
+            L.check(self._lib.cgg_add_prior(self._h, PRIORS[kind], float(a), float(b), float(c)))
         self.n, self.p, self.n_chains = n, p, n_chains
         self._keep = []
 

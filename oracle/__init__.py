@@ -15,16 +15,19 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
-GAUSSIAN, BINOMIAL, POISSON = 0, 1, 2
-NORMAL, LAPLACE, STUDENT_T = 0, 1, 2
-FAMILIES = {"gaussian": GAUSSIAN, "binomial": BINOMIAL, "poisson": POISSON}
-PRIORS = {"normal": NORMAL, "laplace": LAPLACE, "student_t": STUDENT_T}
+GAUSSIAN, BINOMIAL, POISSON, NEGBIN, BINOMIAL_PROBIT = 0, 1, 2, 3, 4
+NORMAL, LAPLACE, STUDENT_T, GAMMA, EXPONENTIAL = 0, 1, 2, 3, 4
+FAMILIES = {"gaussian": GAUSSIAN, "binomial": BINOMIAL, "poisson": POISSON, "negative_binomial": NEGBIN, "binomial_probit": BINOMIAL_PROBIT}
+PRIORS = {"normal": NORMAL, "laplace": LAPLACE, "student_t": STUDENT_T, "gamma": GAMMA, "exponential": EXPONENTIAL}
+MAX_PRIORS = 8
 OK, E_NAN, E_STREAM, E_NOTERM, E_ARG = 0, -1, -2, -3, -4
 
 
 class Model(C.Structure):
     _fields_ = [("family", C.c_int), ("sd", C.c_double), ("prior", C.c_int),
-                ("pmu", C.c_double), ("psigma", C.c_double), ("pdf", C.c_double)]
+                ("pmu", C.c_double), ("psigma", C.c_double), ("pdf", C.c_double),
+                ("n_more", C.c_int), ("more_prior", C.c_int * (MAX_PRIORS - 1)),
+                ("more_a", C.c_double * (MAX_PRIORS - 1)), ("more_b", C.c_double * (MAX_PRIORS - 1)), ("more_c", C.c_double * (MAX_PRIORS - 1))]
 
 
 class SliceStats(C.Structure):
@@ -50,7 +53,13 @@ def lib():
         for name in ("orc_stirlerr",):
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_double]
-        for name in ("orc_bd0", "orc_dpois_log", "orc_dt_log"):
+        L.orc_pnorm.restype = C.c_double
+        L.orc_pnorm.argtypes = [C.c_double]
+        L.orc_dnbinom_mu_log.restype = C.c_double
+        L.orc_dnbinom_mu_log.argtypes = [C.c_double] * 3
+        L.orc_dgamma_log.restype = C.c_double
+        L.orc_dgamma_log.argtypes = [C.c_double] * 3
+        for name in ("orc_bd0", "orc_dpois_log", "orc_dt_log", "orc_dexp_log"):
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_double, C.c_double]
         for name in ("orc_dnorm_log", "orc_dbinom_log"):
@@ -95,10 +104,17 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def make_model(family="gaussian", sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0, prior_df=1.0):
+def make_model(family="gaussian", sd=1.0, prior="normal", prior_mu=0.0, prior_sigma=1.0, prior_df=1.0, more_priors=()):
+    """more_priors: further components of a LIST of priors, each (kind, a, b, c) with (a, b, c) = (mu, sigma, df) for
+    normal / laplace / student_t, (shape, rate, -) for gamma, (-, rate, -) for exponential."""
     fam = FAMILIES[family] if isinstance(family, str) else int(family)
     pri = PRIORS[prior] if isinstance(prior, str) else int(prior)
-    return Model(fam, float(sd), pri, float(prior_mu), float(prior_sigma), float(prior_df))
+    m = Model(fam, float(sd), pri, float(prior_mu), float(prior_sigma), float(prior_df))
+    m.n_more = len(more_priors)
+    for k, (kind, a, b, c) in enumerate(more_priors):
+        m.more_prior[k] = PRIORS[kind] if isinstance(kind, str) else int(kind)
+        m.more_a[k], m.more_b[k], m.more_c[k] = float(a), float(b), float(c)
+    return m
 
 
 def _colmajor(X):

@@ -24,11 +24,16 @@
 #include <string.h>
 
 #define ORC_GAUSSIAN 0
-#define ORC_BINOMIAL 1
+#define ORC_BINOMIAL 1        /* binomial, logit link */
 #define ORC_POISSON  2
+#define ORC_NEGBIN   3        /* MASS::negative.binomial(theta), log link; the reference evaluates dnbinom(size = 1) (R/glm_utils.R:55-57) */
+#define ORC_BINOMIAL_PROBIT 4 /* binomial(link = "probit") (vignettes/pospkg.Rmd:88-108) */
 #define ORC_NORMAL    0
 #define ORC_LAPLACE   1
 #define ORC_STUDENT_T 2
+#define ORC_GAMMA       3     /* distributional::dist_gamma(shape, rate): a = shape, b = rate */
+#define ORC_EXPONENTIAL 4     /* distributional::dist_exponential(rate): b = rate */
+#define ORC_MAX_PRIORS 8
 
 #define ORC_OK            0
 #define ORC_E_NAN        -1   /* R would stop(): `while (NA)` / `if (NA)` */
@@ -41,10 +46,15 @@
 #define ORC_NEG_INF    (-INFINITY)
 
 typedef struct {
-    int family;      /* ORC_GAUSSIAN | ORC_BINOMIAL | ORC_POISSON */
+    int family;      /* ORC_GAUSSIAN | ORC_BINOMIAL | ORC_POISSON | ORC_NEGBIN | ORC_BINOMIAL_PROBIT */
     double sd;       /* log_likelihood_extra_args$sd (R/mcmcglm.R:151), gaussian only */
-    int prior;       /* ORC_NORMAL | ORC_LAPLACE | ORC_STUDENT_T */
+    int prior;       /* first (or only) prior: ORC_NORMAL | ORC_LAPLACE | ORC_STUDENT_T | ORC_GAMMA | ORC_EXPONENTIAL */
     double pmu, psigma, pdf;
+    /* a LIST of priors (R/glm_utils.R:113-115, quirk Q6): every prior of the list is evaluated at EVERY coordinate and all
+     * of it is summed, i.e. the coordinates are iid with density prod_k prior_k.  n_more further components after the first */
+    int n_more;
+    int more_prior[ORC_MAX_PRIORS - 1];
+    double more_a[ORC_MAX_PRIORS - 1], more_b[ORC_MAX_PRIORS - 1], more_c[ORC_MAX_PRIORS - 1];
 } orc_model;
 
 /* ------------------------------------------------------------------ nmath pieces */
@@ -201,6 +211,57 @@ double orc_dt_log(double x, double n) {
     return t - u - (M_LN_SQRT_2PI_ + l_x2n);
 }
 
+/* nmath/dnbinom.c: dnbinom_mu(x, size, mu, give_log = TRUE) */
+double orc_dnbinom_mu_log(double x, double size, double mu) {
+    if (isnan(x) || isnan(size) || isnan(mu)) return x + size + mu;
+    if (mu < 0 || size < 0) return NAN;
+    if (r_nonint(x)) return ORC_NEG_INF;
+    if (x < 0 || !isfinite(x)) return ORC_NEG_INF;
+    if (x == 0 && size == 0) return 0.;
+    x = nearbyint(x);
+    if (!isfinite(size)) return orc_dpois_log(x, mu);
+    if (x == 0) return size * (size < mu ? log(size / (size + mu)) : log1p(-mu / (size + mu)));
+    if (x < 1e-10 * size) {
+        double p = (size < mu ? log(size / (1 + size / mu)) : log(mu / (1 + mu / size)));
+        return x * p - mu - lgamma(x + 1) + log1p(x * (x - 1) / (2 * size));
+    } else {
+        double p = size / (size + x), ans = dbinom_raw_log(size, x + size, size / (size + mu), mu / (size + mu));
+        return log(p) + ans;
+    }
+}
+
+/* nmath/pnorm.c, lower tail: restated through the C library's erfc (nmath uses Cody's rational approximations; the two
+ * agree to ~1e-16 relative over the range stats' probit link allows, |x| <= 8.13) */
+double orc_pnorm(double x) { return 0.5 * erfc(-x * 0.70710678118654752440); }
+
+/* nmath/dgamma.c: dgamma(x, shape, scale, give_log = TRUE) */
+double orc_dgamma_log(double x, double shape, double scale) {
+    double pr;
+    if (isnan(x) || isnan(shape) || isnan(scale)) return x + shape + scale;
+    if (shape < 0 || scale <= 0) return NAN;
+    if (x < 0) return ORC_NEG_INF;
+    if (shape == 0) return (x == 0) ? INFINITY : ORC_NEG_INF;
+    if (x == 0) {
+        if (shape < 1) return INFINITY;
+        if (shape > 1) return ORC_NEG_INF;
+        return -log(scale);
+    }
+    if (shape < 1) {
+        pr = dpois_raw_log(shape, x / scale);
+        return pr + (isfinite(shape / x) ? log(shape / x) : log(shape) - log(x));
+    }
+    pr = dpois_raw_log(shape - 1, x / scale);
+    return pr - log(scale);
+}
+
+/* nmath/dexp.c: dexp(x, scale, give_log = TRUE) */
+double orc_dexp_log(double x, double scale) {
+    if (isnan(x) || isnan(scale)) return x + scale;
+    if (scale <= 0.0) return NAN;
+    if (x < 0.) return ORC_NEG_INF;
+    return (-x / scale) - log(scale);
+}
+
 /* ------------------------------------------------------------------ links (stats) */
 
 /* family$linkinv, R/glm_utils.R:210.  gaussian(): identity.  binomial(): stats/src/family.c
@@ -219,7 +280,18 @@ void orc_linkinv(int family, int64_t n, const double *eta, double *mu) {
             mu[i] = tmp / (1 + tmp);
         }
         break;
-    default:
+    case ORC_BINOMIAL_PROBIT: {
+        /* stats::binomial(link = "probit")$linkinv (make.link): thresh <- -qnorm(.Machine$double.eps);
+         * eta <- pmin(pmax(eta, -thresh), thresh); pnorm(eta) */
+        const double thresh = 8.125890664701906;
+        for (i = 0; i < n; ++i) {
+            double e = eta[i];
+            if (!isnan(e)) e = (e < -thresh) ? -thresh : ((e > thresh) ? thresh : e);
+            mu[i] = orc_pnorm(e);
+        }
+        break;
+    }
+    default:   /* poisson()$linkinv and MASS::negative.binomial()$linkinv (log link): pmax(exp(eta), .Machine$double.eps) */
         for (i = 0; i < n; ++i) {
             double e = exp(eta[i]);
             mu[i] = (e > DBL_EPSILON) ? e : DBL_EPSILON; /* pmax keeps NaN; exp never returns it for finite eta */
@@ -232,7 +304,8 @@ void orc_linkinv(int family, int64_t n, const double *eta, double *mu) {
 double orc_log_density(int family, double mu, double y, double sd) {
     switch (family) {
     case ORC_GAUSSIAN: return orc_dnorm_log(y, mu, sd);
-    case ORC_BINOMIAL: return orc_dbinom_log(y, 1.0, mu);
+    case ORC_BINOMIAL: case ORC_BINOMIAL_PROBIT: return orc_dbinom_log(y, 1.0, mu);
+    case ORC_NEGBIN:   return orc_dnbinom_mu_log(y, 1.0, mu);      /* R/glm_utils.R:55-57: size = 1 whatever theta is */
     default:           return orc_dpois_log(y, mu);
     }
 }
@@ -246,13 +319,21 @@ double orc_log_likelihood(int family, int64_t n, const double *mu, const double 
 
 /* distributional::density(<dist>, at, log = TRUE) for one coordinate (external, unpinned):
  * normal -> dnorm(at, mu, sigma, log=TRUE); laplace -> -log(2 sigma) - |at - mu| / sigma;
- * student_t(df, mu, sigma) -> dt((at - mu)/sigma, df, log=TRUE) - log(sigma) */
-double orc_prior_log_density1(const orc_model *m, double at) {
-    switch (m->prior) {
-    case ORC_NORMAL:  return orc_dnorm_log(at, m->pmu, m->psigma);
-    case ORC_LAPLACE: return -log(2 * m->psigma) - fabs(at - m->pmu) / m->psigma;
-    default:          return orc_dt_log((at - m->pmu) / m->psigma, m->pdf) - log(m->psigma);
+ * student_t(df, mu, sigma) -> dt((at - mu)/sigma, df, log=TRUE) - log(sigma); gamma(shape, rate) -> dgamma(at, shape, rate, log=TRUE);
+ * exponential(rate) -> dexp(at, rate, log=TRUE).  A list of priors sums its components at every coordinate (quirk Q6). */
+static double prior_component(int kind, double a, double b, double c, double at) {
+    switch (kind) {
+    case ORC_NORMAL:      return orc_dnorm_log(at, a, b);
+    case ORC_LAPLACE:     return -log(2 * b) - fabs(at - a) / b;
+    case ORC_STUDENT_T:   return orc_dt_log((at - a) / b, c) - log(b);
+    case ORC_GAMMA:       return orc_dgamma_log(at, a, 1.0 / b);      /* distributional: dgamma(x, shape, rate) */
+    default:              return orc_dexp_log(at, 1.0 / b);           /* distributional: dexp(x, rate) */
     }
+}
+double orc_prior_log_density1(const orc_model *m, double at) {
+    double v = prior_component(m->prior, m->pmu, m->psigma, m->pdf, at);
+    for (int k = 0; k < m->n_more; ++k) v += prior_component(m->more_prior[k], m->more_a[k], m->more_b[k], m->more_c[k], at);
+    return v;
 }
 
 /* log_prior_density.default, R/glm_utils.R:108-110: the prior is evaluated at ALL p coordinates

@@ -35,11 +35,17 @@ def test_unsupported_inputs_are_rejected_before_touching_cuda():
         Engine(10, 2, family="Gamma")
     assert e.value.code == _lib.E_UNSUPPORTED
     with pytest.raises(CggError) as e:
-        Engine(10, 2, family="binomial", link="probit")
+        Engine(10, 2, family="binomial", link="cloglog")
     assert e.value.code == _lib.E_UNSUPPORTED
     with pytest.raises(CggError) as e:
-        Engine(10, 2, prior="gamma")
+        Engine(10, 2, family="poisson", link="probit")          # a link the engine knows, on a family it does not go with
     assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(CggError) as e:
+        Engine(10, 2, prior="beta")
+    assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(CggError) as e:
+        Engine(10, 2, prior="gamma", prior_mu=-1.0)              # gamma shape must be positive
+    assert e.value.code == _lib.E_ARG
 
 
 def test_no_cpu_fallback():

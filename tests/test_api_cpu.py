@@ -25,8 +25,8 @@ def test_reference_guards():
 
 
 @pytest.mark.parametrize("kw", [
-    dict(family="Gamma"), dict(family=mg.binomial(link="probit")), dict(beta_prior=[mg.dist_normal()] * 3),
-    dict(beta_prior="gamma"), dict(sample_method="normal-normal"), dict(linear_predictor_calc="naive"),
+    dict(family="Gamma"), dict(family=mg.binomial(link="cloglog")), dict(family=mg.poisson(link="identity")),
+    dict(beta_prior=[mg.dist_normal()] * 9), dict(beta_prior="gamma"), dict(sample_method="normal-normal"),
     dict(qslice_fun=lambda **k: None)])
 def test_unsupported_inputs_are_rejected_not_emulated(kw):
     args = dict(formula="Y ~ .", family="gaussian", data=_dat(), w=0.5)
