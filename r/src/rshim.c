@@ -1,6 +1,7 @@
 /* rshim.c -- .Call layer between R and libcggibbs (include/cggibbs.h).  One function per C-ABI entry
  * point, nothing but SEXP unwrapping: all logic lives behind the C ABI where the ctypes tests reach it.
- * NOT compiled in this repository's CI image (no R headers there); see INTEGRATION.md. */
+ * EXPERIMENTAL: the image this repository is built in has no R, so this file has only ever been syntax-checked
+ * (tests/test_abi_cpu.py compiles it with -fsyntax-only against the stub headers in tests/r_stub); see INTEGRATION.md. */
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
@@ -46,6 +47,7 @@ SEXP C_cgg_create(SEXP cfg) {
     c.seed = (uint64_t)num(cfg, "seed", 0);
     c.spec_tau = num(cfg, "spec_tau", 0.12);
     c.flags = (int32_t)num(cfg, "flags", 0);
+    c.jet_bound_scale = 0.0;
     cgg_handle *h = NULL;
     chk(cgg_create(&c, &h));
     SEXP p = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
@@ -54,6 +56,16 @@ SEXP C_cgg_create(SEXP cfg) {
     return p;
 }
 
+/* one more prior of a list of priors (R/glm_utils.R:113-115): kind and its (a, b, c) */
+SEXP C_cgg_add_prior(SEXP p, SEXP kind, SEXP a, SEXP b, SEXP c) {
+    chk(cgg_add_prior(get_handle(p), Rf_asInteger(kind), Rf_asReal(a), Rf_asReal(b), Rf_asReal(c)));
+    return R_NilValue;
+}
+/* per-chain slice widths (mcmcglm_across_tuningparams as one engine run) */
+SEXP C_cgg_set_chain_w(SEXP p, SEXP w) {
+    chk(cgg_set_chain_w(get_handle(p), REAL(w)));
+    return R_NilValue;
+}
 /* X: the double model matrix (already column-major with ld = nrow), y: double vector */
 SEXP C_cgg_set_data(SEXP p, SEXP X, SEXP y) {
     chk(cgg_set_data(get_handle(p), REAL(X), (int64_t)Rf_nrows(X), REAL(y)));
@@ -88,8 +100,10 @@ SEXP C_cgg_get_state(SEXP p, SEXP chain, SEXP n, SEXP np) {
     UNPROTECT(3);
     return out;
 }
-/* replay_u: NULL, or a double matrix with one COLUMN per chain (runif draws recorded by the caller) */
+/* replay_u: NULL, or a double matrix with one COLUMN per chain: the runif draws of THIS call (the front end calls in
+ * chunks of a few iterations, so that the progress bar moves and Ctrl-C is honoured between chunks) */
 SEXP C_cgg_run(SEXP p, SEXP n_iter, SEXP n_chains, SEXP np, SEXP replay_u) {
+    R_CheckUserInterrupt();
     int C = Rf_asInteger(n_chains), P = Rf_asInteger(np);
     int64_t it = (int64_t)Rf_asReal(n_iter);
     SEXP smp = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C * it * P));   /* [chain][iteration][coef], row-major */
@@ -117,7 +131,8 @@ static const R_CallMethodDef call_methods[] = {
     {"C_cgg_init_chain", (DL_FUNC)&C_cgg_init_chain, 3},  {"C_cgg_set_state", (DL_FUNC)&C_cgg_set_state, 4},
     {"C_cgg_log_potential", (DL_FUNC)&C_cgg_log_potential, 4}, {"C_cgg_update_eta", (DL_FUNC)&C_cgg_update_eta, 4},
     {"C_cgg_get_state", (DL_FUNC)&C_cgg_get_state, 4},    {"C_cgg_run", (DL_FUNC)&C_cgg_run, 5},
-    {"C_cgg_destroy", (DL_FUNC)&C_cgg_destroy, 1},        {NULL, NULL, 0}};
+    {"C_cgg_destroy", (DL_FUNC)&C_cgg_destroy, 1},        {"C_cgg_add_prior", (DL_FUNC)&C_cgg_add_prior, 5},
+    {"C_cgg_set_chain_w", (DL_FUNC)&C_cgg_set_chain_w, 2}, {NULL, NULL, 0}};
 
 void R_init_mcmcglmb200(DllInfo *dll) {
     R_registerRoutines(dll, NULL, call_methods, NULL, NULL);

@@ -64,3 +64,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_r_shim_compiles_against_stub_headers():
+    """r/src/rshim.c (the .Call layer a maintainer of the R package would ship) against include/cggibbs.h and minimal stand-ins
+    for R's headers (tests/r_stub): every C-ABI call in it has the right arity and types.  Syntax only: there is no R here."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "r_stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "rshim.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = open(os.path.join(ROOT, "r", "src", "rshim.c")).read()
+    rcode = "".join(open(os.path.join(ROOT, "r", "R", f)).read() for f in ("front.R", "engine.R"))
+    registered = set(re.findall(r'\{"(C_cgg_[a-z0-9_]+)"', shim))
+    called = set(re.findall(r"\.Call\((C_cgg_[a-z0-9_]+)", rcode))
+    assert called <= registered and len(registered) >= 11, called - registered

@@ -53,7 +53,8 @@ def test_row_terms_of_the_new_families(family):
         y = (rng.random(eta.size) < 0.5).astype(np.float64)
     got = debug_row_terms(family, y, eta)
     ref = oracle.log_density(family, oracle.linkinv(family, eta), y)
-    assert np.all(np.abs(got - ref) <= 8 * EPS * np.maximum(np.abs(ref), 1.0)), np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1))
+    tol = 8 if family == "negative_binomial" else 32      # CUDA normcdf (<= 5 ulp of p) against the oracle's erfc-based pnorm
+    assert np.all(np.abs(got - ref) <= tol * EPS * np.maximum(np.abs(ref), 1.0)), np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1))
     if family == "negative_binomial":
         assert debug_row_terms(family, np.array([2.0, 0.0]), np.array([800.0, 800.0])).tolist() == [-np.inf, -np.inf]
 
