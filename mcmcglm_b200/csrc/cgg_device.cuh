@@ -266,7 +266,7 @@ __device__ __forceinline__ void score_pairs(const RowPair<FAMILY> (&rp)[NP], int
                                             const double2 *tab, double *sacc, int lane, float &bE, float &bX, unsigned &nearmask, float &smax) {
     const unsigned all = (nc >= 32) ? 0xffffffffu : ((1u << nc) - 1u);
     unsigned fine = all & ~cmask;
-    if (FAMILY == CGG_BINOMIAL && cmask) {
+    if constexpr (FAMILY == CGG_BINOMIAL) if (cmask) {
         // pre-filter: candidates flagged in cmask are scored in fp32 (hardware ex2/lg2); the sums of
         // |eta| and |x| over the rows feed the rigorous error bound the decider applies
         float ef0[NP], ef1[NP], xf0[NP], xf1[NP];
@@ -288,9 +288,10 @@ __device__ __forceinline__ void score_pairs(const RowPair<FAMILY> (&rp)[NP], int
             for (int q = 0; q < NP; ++q) {
                 const float s00 = fmaf(xf0[q], d0, ef0[q]), s01 = fmaf(xf1[q], d0, ef1[q]);
                 const float s10 = fmaf(xf0[q], d1, ef0[q]), s11 = fmaf(xf1[q], d1, ef1[q]);
-                smax = fmaxf(smax, fmaxf(fmaxf(s00, s01), fmaxf(s10, s11)));      // for the bound on R's log(1 - p) rounding
-                v0 += softplus32(s00, n0) + softplus32(s01, n0);
-                v1 += softplus32(s10, n1) + softplus32(s11, n1);
+                // smax doubles as the accumulator of the bound on R's log(1 - p) rounding: sum of e^s over the (row, candidate)
+                // pairs in that regime (valid -- if generous -- for every pre-filtered candidate of the pass)
+                v0 += softplus32n(s00, rp[q].z0, n0, smax) + softplus32n(s01, rp[q].z1, n0, smax);
+                v1 += softplus32n(s10, rp[q].z0, n1, smax) + softplus32n(s11, rp[q].z1, n1, smax);
             }
             if (n0) nearmask |= 1u << k0;
             sacc[k0 * 32 + lane] -= (double)v0;
@@ -325,7 +326,7 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
     const int nc = cs.nc, cj = cs.cj;
     const int64_t n = cs.n;
     double *eta = cs.eta;
-    float smax = -INFINITY;     // largest s = +-eta' a pre-filtered candidate met on this lane's rows
+    float smax = 0.0f;          // pre-filter: sum of e^s over this lane's (row, candidate) pairs in R's log(1 - p) rounding regime
     unsigned nrows = 0;         // rows this lane scored
     if (!prefetched) cs.prologue(lane);
     for (int k = 0; k < nc; ++k) sacc[k * 32 + lane] = 0.0;
@@ -384,9 +385,7 @@ __device__ __forceinline__ void warp_pass_chain(const Dev &d, const ChainStream 
         // The pre-filter's bound is against the smooth -softplus; an exact evaluation follows R's log(1 - p) form, which
         // deviates by at most 2^-54 (1 + e^s) per row for s <= 30 (rform_log1p_rho; above the clamp it is a constant).
         // Folded into the sum the decider multiplies by (2^-22 + kappa) = 7.15e-7: 5.6e-17 / 7.15e-7, rounded up.
-        float ex;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fminf(smax, 30.01f) * 1.44269514f));
-        bE += (float)nrows * (1.0f + ex) * 8.2e-11f;
+        bE += ((float)nrows + smax) * 8.2e-11f;
     }
 }
 
@@ -1094,6 +1093,7 @@ __device__ __forceinline__ void build_candidates(const Dev &d, ChainState &s, Ct
     double l = s.L, r = s.R;
     const bool prefilter = d.coarse && !s.fine_next && shat > 0.0;
     const double far = d.coarse_theta * shat;
+    const bool after_undecided = s.fine_next != 0;     // the previous pass stopped at a candidate fp32 could not reject: it is probably inside
     for (int i = 0; n < d.K; ++i) {
         if (i >= nU) {
             if (i == 0 && s.phase == PH_SHRINK) s.status = CGG_E_STREAM;  // a needed draw is missing
@@ -1109,12 +1109,16 @@ __device__ __forceinline__ void build_candidates(const Dev &d, ChainState &s, Ct
         // about twice the slice width, and even a bracket as tight as the slice is hit with probability < 1
         double pacc = (shat > 0.0) ? 0.5 * shat / (r - l) : 0.35;   // first sweep: no estimate yet
         pacc = pacc < 0.85 ? pacc : 0.85;
+        if (after_undecided && i == 0) pacc = 0.85;
         pneed *= (1.0 - pacc);
         if (x < s.x0) l = x; else r = x;
     }
     if (s.phase == PH_STEPOUT && n == 0 && s.status == CGG_OK) s.status = CGG_E_STREAM;
     // pre-filter policy (cannot change results, only cost): a candidate further than coarse_theta slice widths
     // from x0 is almost surely outside the slice by a wide margin -> score it in fp32 and let the bound decide
+    // (Tried in round 2: sending EVERY candidate through the pre-filter while a chain is far from its stationary region.  It
+    // lost: from a prior draw at p = 1000 most rows sit beyond the logit clamp, the log-potential along a coordinate moves by
+    // tens, not thousands, per slice width, and the rigorous fp32 bound is ~35 there -- 3.8 undecided candidates per update.)
     unsigned cm = 0;
     if (d.coarse && !s.fine_next && shat > 0.0)
         for (int k = 0; k < n; ++k)
@@ -1604,8 +1608,14 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (lane < nc && ((cmask >> lane) & 1u)) {
             const double B = 1.01 * ((2.384185791015625e-07 + (double)kCoarseKappa) * (sE + fabs(s.cand[lane] - s.x0) * sX)
                                      + (double)kCoarseKappa * (double)d.n);
-            undecided = (aflags & 8u) || !(f + B < s.ylev);
-            if (!undecided) f = -INFINITY;
+            // certainly outside the slice: y >= f for any exact value within B.  A STEPPING-OUT test only needs the verdict
+            // (`while (y < f(L)) L <- L - w` never uses f itself), so it may also be certainly INSIDE; a shrink proposal that
+            // is inside is the accepted one and needs its exact f (the next update's f(x0)): it stays undecided.
+            const bool clean = !(aflags & 8u);
+            const bool out = clean && (f + B < s.ylev);
+            const bool in_ = clean && (s.ylev < f - B) && s.phase == PH_STEPOUT && lane < s.nL + s.nR;
+            undecided = !(out || in_);
+            if (out) f = -INFINITY; else if (in_) f = INFINITY;
         }
         const unsigned um = __ballot_sync(0xffffffffu, undecided);
         if (um) stop_at = __ffs(um) - 1;

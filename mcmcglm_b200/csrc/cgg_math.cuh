@@ -131,6 +131,19 @@ __device__ __forceinline__ float softplus32(float s, bool &near) {
     const float l = lg2_approx(1.0f + t) * 0.693147181f;
     return ((s > 0.0f) ? a : 0.0f) + l;
 }
+// The same, for a row with response y = 0 (z): an exact evaluation follows R's log(1 - p) form for 8 < s <= 30
+// (rform_log1p_rho), which deviates from the smooth -softplus by at most 2^-54 (1 + e^s); `noise` accumulates an upper
+// bound of e^s over those (row, candidate) pairs (margins for the fp32 rounding of s; e^s = 1 / exp(-s), rounded up).
+__device__ __forceinline__ float softplus32n(float s, bool z, bool &near, float &noise) {
+    float a = fabsf(s);
+    near = near || (fabsf(a - 30.0f) < 0.02f);
+    const bool rf = z && s > 7.9f && s <= 30.02f;
+    a = (a > 30.0f) ? 36.0436534f : a;
+    const float t = ex2_approx(-a * 1.44269504f);
+    if (rf) noise += __frcp_ru(t) * 1.001f;
+    const float l = lg2_approx(1.0f + t) * 0.693147181f;
+    return ((s > 0.0f) ? a : 0.0f) + l;
+}
 
 // The two rows (i, i+1) a lane owns in a tile, with everything that does not depend on the candidate
 // hoisted out of the candidate loop.  term(delta) returns the sum of the two rows' log-density terms up to
