@@ -68,8 +68,9 @@ def parse():
     ap.add_argument("--burnin-iters", type=int, default=30,
                     help="untimed Gibbs iterations before the warm-up steps, so that the timed steps measure the stationary "
                          "regime (chains start from a prior draw like the reference, whose own default burnin is 100)")
-    ap.add_argument("--e2e-iters", type=int, default=100,
-                    help="Gibbs iterations per end-to-end engine call (the reference's default call is n_samples = 500)")
+    ap.add_argument("--e2e-iters", type=int, default=500,
+                    help="Gibbs iterations per end-to-end engine call: the reference's own default, mcmcglm(n_samples = 500) "
+                         "(R/mcmcglm.R:156); the chains start from a prior draw like the reference's, transient included")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-jet", action="store_true", help="decide every candidate from exact passes (no jet passes)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -1,8 +1,12 @@
-# 2-GPU checks: the NCCL row-sharded test, chain-parallel weak scaling of the headline workload, the row-sharded workload
+# multi-GPU checks (gpurun --gpus N): the 2-process sharded tests, then the bench contract under torchrun with cfg5 riding along
+N=${N:-2}
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/multi_smi.txt
-( timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q 2>&1 | tail -3 ) > gpurun_out/multi_tests.log 2>&1
-cat gpurun_out/multi_tests.log
-python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/scale_n1.log 2>&1; tail -1 gpurun_out/scale_n1.log | cut -c1-160
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/scale_n2.log 2>&1; tail -1 gpurun_out/scale_n2.log | cut -c1-160
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload cfg5 --rows 12500000 --steps 2 --warmup 1 --burnin-iters 3 --no-cpu --no-e2e > gpurun_out/cfg5_n2.log 2>&1; tail -1 gpurun_out/cfg5_n2.log | cut -c1-700
+( timeout 900 python -m pytest tests/test_gpu_sharded.py -q -m gpu 2>&1 | tail -6 ) > gpurun_out/multi_tests_n$N.log 2>&1
+cat gpurun_out/multi_tests_n$N.log
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu > gpurun_out/multi_bench_n$N.log 2> gpurun_out/multi_bench_n$N.err
+tail -1 gpurun_out/multi_bench_n$N.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value', round(d['value']), 'n_gpus', d['n_gpus'], 'e2e', d['e2e'] and round(d['e2e']['value']))
+print('extra', json.dumps(d.get('extra_workloads'))[:1500])"
+tail -5 gpurun_out/multi_bench_n$N.err | cut -c1-300
