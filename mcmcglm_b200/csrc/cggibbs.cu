@@ -342,13 +342,16 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
     const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(sh.xs);
     double acc[NV];
+    const bool prof = d.prof != nullptr && blockIdx.x == 0 && lane == 0;      // CGG_PROFILE: phase timers of the first CTA
     for (unsigned long long pass = 0;; ++pass) {
         int nc = 0;
+        const long long tp0 = prof ? clock64() : 0;
         if (warp > 0) {
             int j;
             bool prefetched = false;
             NoLookAhead nola;
             nc = worker_pass<FAMILY>(d, c, sh.ctl, wid, W, lane, ring, s_l1p, sh.sacc + warp * KMAX * 32, acc, j, prefetched, 0, &nola);
+            if (prof && warp == 1) atomicAdd(d.prof + 22, (unsigned long long)(clock64() - tp0));
             if (nc > 0 && lane == 0) {
 #pragma unroll
                 for (int k = 0; k < NV; ++k) if (k < nc) sh.part[warp * NV + k] = acc[k];
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_
             const unsigned cmask = (unsigned)(w1 >> 32);
             nc = (j < 0) ? -1 : ((cmask & JET_BIT) ? jet_nvals(FAMILY, !(cmask & JET_FULL)) : ((ncand == 0 && cj < 0) ? 0 : ncand));
             if (nc >= 0 && sh.dc->valid) { decider_prefetch(d, c, sh.dc, lane); decider_prephase(d, c, sh.dc, lane); }
+            if (prof) { atomicAdd(d.prof + 20, (unsigned long long)(clock64() - tp0)); atomicAdd(d.prof + 24, 1ULL); }
         }
         if (nc < 0) break;                             // the chain has finished (every thread of the cluster sees the same block)
         __syncthreads();
@@ -371,8 +375,10 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_
             for (int w = 1; w < NWARPS; ++w) v += sh.part[w * NV + lane];
             for (int r = 0; r < S; ++r) st_cluster_f64(xs_addr + (uint32_t)(((par * CLUSTER_MAX + rank) * NV + lane) * 8), (unsigned)r, v);
         }
+        const long long tb0 = prof ? clock64() : 0;
         cluster_barrier();
         if (warp == 0) {
+            const long long td0 = prof ? clock64() : 0;
             if (lane < NV) {
                 double v = 0.0;
                 if (lane < nc) for (int r = 0; r < S; ++r) v += sh.xs[(par * CLUSTER_MAX + r) * NV + lane];       // rank order: identical in every CTA
@@ -382,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_
             decide_chain(&d, c, lane, -1, SRC_SLOTS, sh.dc, sh.vals);
             if (lane < CTL_WORDS) sh.ctl[lane] = reinterpret_cast<const double *>(&sh.dc->ct)[lane];
             __syncwarp();
+            if (prof) { atomicAdd(d.prof + 21, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 23, (unsigned long long)(td0 - tb0)); }
         }
         __syncthreads();
     }
@@ -1776,7 +1783,18 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
         for (double v : sh) if (v > 0) { m += v; ++cnt; mn = std::min(mn, v); mx = std::max(mx, v); }
         fprintf(stderr, "[cgg profile] slice-width estimate shat: mean %.4g min %.4g max %.4g (%d set)\n", cnt ? m / cnt : 0.0, mn, mx, cnt);
     }
-    if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT) {
+    if (want_prof && h->cluster_S > 0) {
+        unsigned long long pr[32];
+        CK(cudaMemcpy(pr, h->prof_dev, sizeof pr, cudaMemcpyDeviceToHost));
+        const double np_ = pr[24] ? (double)pr[24] : 1.0;
+        fprintf(stderr, "[cgg profile] cluster driver, %d CTAs per chain, %.3f ms, %llu passes; mean cycles per pass (CTA 0): decider's prefetch + pre-phase %.0f | "
+                        "a worker warp's pass %.0f | cluster barrier (decider) %.0f | sums + decision + control block %.0f\n",
+                h->cluster_S, ms, pr[24], pr[20] / np_, pr[22] / np_, pr[23] / np_, pr[21] / np_);
+        if (pr[12] | pr[14] | pr[15])      // (-DCGG_DECIDER_TICKS builds)
+            fprintf(stderr, "[cgg profile] decision phases, mean cycles: state + sums %.0f | draws / points at hand %.0f | round 1 judged %.0f | stepping out + proposals %.0f | accepted %.0f | next pass + store %.0f | fence %.0f\n",
+                    pr[12] / np_, pr[14] / np_, pr[15] / np_, pr[16] / np_, pr[17] / np_, pr[18] / np_, pr[19] / np_);
+    }
+    if (want_prof && h->cfg.driver == CGG_DRIVER_PERSISTENT && h->cluster_S == 0) {
         unsigned long long pr[24];
         CK(cudaMemcpy(pr, h->prof_dev, sizeof pr, cudaMemcpyDeviceToHost));
         const double nw = pr[6] ? (double)pr[6] : 1.0;
