@@ -394,7 +394,13 @@ def main():
     if multi:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    per_rank = None
     if multi:
+        # every rank's own numbers (event time of the timed region, device time inside the sweep kernels), for the record
+        mine = torch.tensor([ms, agg["sweep_ms"]], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"timed_region_ms": [round(float(v[0]), 3) for v in allr], "sweep_kernel_ms": [round(float(v[1]), 3) for v in allr]}
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -538,6 +544,8 @@ def main():
             extra = {"cfg5": {"error": repr(ex)[:300]}}
         dog.cancel()
     if rank == 0:
+        if per_rank:
+            line["per_rank"] = per_rank
         if extra:
             line["extra_workloads"] = extra
         print(json.dumps(line))

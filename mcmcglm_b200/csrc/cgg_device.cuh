@@ -1480,6 +1480,13 @@ __device__ __forceinline__ bool mbox_load(const MboxEntry *src, unsigned stamp, 
     v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
     return (unsigned)(w0 >> 32) == stamp && (unsigned)(w1 >> 32) == stamp;
 }
+__device__ __forceinline__ void mbox_load_raw(const MboxEntry *src, unsigned long long &w0, unsigned long long &w1) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+}
+__device__ __forceinline__ bool mbox_decode(unsigned long long w0, unsigned long long w1, unsigned stamp, double &v) {
+    v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+    return (unsigned)(w0 >> 32) == stamp && (unsigned)(w1 >> 32) == stamp;
+}
 // vals[0..nvals): in: this rank's sums (identical in every lane); out: the totals over the ranks.  false: timed out.
 __device__ __forceinline__ bool mbox_exchange(const Dev &d, int c, int nvals, unsigned stamp, int lane, double (&vals)[NV]) {
     const int nv = nvals < 1 ? 1 : nvals;
@@ -1490,17 +1497,29 @@ __device__ __forceinline__ bool mbox_exchange(const Dev &d, int c, int nvals, un
     if (lane < nv)
         for (int r = 0; r < d.world; ++r)
             mbox_store(reinterpret_cast<MboxEntry *>(d.mbox[r]) + ((size_t)c * d.world + d.rank) * NV + lane, mine, stamp);
-    // everybody's values from my mailbox, added in rank order by the lane of the value
+    // everybody's values from my mailbox: the world * nv entries are spread over the lanes (up to three per lane, requested
+    // back to back: one round trip per look), then lane k adds value k of the ranks in rank order
     const MboxEntry *my = reinterpret_cast<const MboxEntry *>(d.mbox[d.rank]) + (size_t)c * d.world * NV;
+    const int total = d.world * nv;                 // <= 8 * 10
     const unsigned long long t0 = globaltimer_ns();
-    double tot = 0.0;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
     for (unsigned spins = 0;; ++spins) {
-        bool ok = true;
-        tot = 0.0;
-        if (lane < nv)
-            for (int r = 0; r < d.world; ++r) { double v; ok = mbox_load(my + (size_t)r * NV + lane, stamp, v) && ok; tot += v; }
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+        // the three requests first, the checks after (a check right behind its load would serialise the round trips)
+        const unsigned long long sw = ((unsigned long long)stamp << 32);
+        unsigned long long a0 = sw, a1 = sw, b0 = sw, b1 = sw, c0 = sw, c1 = sw;
+        if (i0 < total) mbox_load_raw(my + (size_t)(i0 / nv) * NV + (i0 % nv), a0, a1);
+        if (i1 < total) mbox_load_raw(my + (size_t)(i1 / nv) * NV + (i1 % nv), b0, b1);
+        if (i2 < total) mbox_load_raw(my + (size_t)(i2 / nv) * NV + (i2 % nv), c0, c1);
+        const bool ok = mbox_decode(a0, a1, stamp, e0) & mbox_decode(b0, b1, stamp, e1) & mbox_decode(c0, c1, stamp, e2);
         if (__all_sync(0xffffffffu, ok)) break;
         if ((spins & 1023u) == 1023u && globaltimer_ns() - t0 > 4000000000ULL) return false;      // a peer never showed up
+    }
+    double tot = 0.0;
+    for (int r = 0; r < d.world; ++r) {
+        const int idx = r * nv + (lane < nv ? lane : 0);
+        const double a0 = __shfl_sync(0xffffffffu, e0, idx & 31), a1 = __shfl_sync(0xffffffffu, e1, idx & 31), a2 = __shfl_sync(0xffffffffu, e2, idx & 31);
+        tot += (idx < 32) ? a0 : ((idx < 64) ? a1 : a2);
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) vals[k] = __shfl_sync(0xffffffffu, tot, k);
