@@ -39,7 +39,7 @@ WORKLOADS = {
     "cfg5shard": dict(family="gaussian", n=6_250_000, p=200, prior="normal", chains=1, w=0.5, K=8, init_scale=1.0,
                       desc="gaussian n=6.25e6 (one of 8 row shards of n=5e7) p=200, 1 chain (BASELINE configs[4], local part)"),
     "cfg5": dict(family="gaussian", n=50_000_000, p=200, prior="normal", chains=1, w=0.5, K=8, init_scale=1.0, sharded=True,
-                 desc="gaussian n=5e7 p=200 normal(0,1) w=0.5, 1 chain, rows sharded over the GPUs, NCCL exchange per pass (BASELINE configs[4])"),
+                 desc="gaussian n=5e7 p=200 normal(0,1) w=0.5, 1 chain, rows sharded over the GPUs, per-pass exchange through peer mailboxes inside the persistent kernel (BASELINE configs[4])"),
     "tiny": dict(family="binomial", n=20_000, p=20, prior="laplace", chains=4, w=0.5, K=8, init_scale=1.0,
                  desc="tiny smoke workload"),
 }
