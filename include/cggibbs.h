@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CGG_ABI_VERSION 2
+#define CGG_ABI_VERSION 3
 #define CGG_KMAX 8 /* most candidates one chain can score in one pass over its rows */
 
 typedef enum cgg_status {
@@ -124,6 +124,7 @@ typedef struct cgg_stats {
     uint64_t jet_passes;     /* (chain, pass) pairs that were jet passes (subset of chain_passes) */
     uint64_t jet_fallbacks;  /* updates a jet pass could not finish: exact passes took over from that point */
     uint64_t jet_retries;    /* light jet passes (binomial) that were repeated as full jet passes */
+    uint64_t group_passes;   /* walks over the rows that served FOUR chains at once (persistent driver; counted by one worker warp; cgg_run only) */
 } cgg_stats;
 
 typedef struct cgg_handle cgg_handle;

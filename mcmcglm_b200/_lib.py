@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libcggibbs.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 KMAX = 8
 OK, E_ARG, E_UNSUPPORTED, E_CUDA, E_NAN, E_STREAM, E_NOTERM, E_STATE, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 GAUSSIAN, BINOMIAL, POISSON, NEGATIVE_BINOMIAL = 0, 1, 2, 3
@@ -46,7 +46,7 @@ class Stats(C.Structure):
                 ("stepouts", C.c_uint64), ("shrinks", C.c_uint64), ("launches", C.c_uint64),
                 ("sweep_ms", C.c_double), ("algorithmic_bytes", C.c_double), ("coarse_evals", C.c_uint64),
                 ("coarse_undecided", C.c_uint64), ("jet_passes", C.c_uint64), ("jet_fallbacks", C.c_uint64),
-                ("jet_retries", C.c_uint64)]
+                ("jet_retries", C.c_uint64), ("group_passes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

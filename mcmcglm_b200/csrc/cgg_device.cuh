@@ -102,7 +102,7 @@ struct Hdr {
     unsigned int ticket;        // stepwise driver: CTAs finished in this launch
     int32_t done;               // stepwise driver: every chain finished (or failed)
     int32_t abort;              // a wait timed out
-    int32_t pad;
+    int32_t group_passes;       // persistent driver: group passes (four chains per walk) walked by worker warp 0 in this cgg_run
 };
 
 struct LimbAcc;
@@ -127,7 +127,7 @@ struct Dev {
     int32_t rank;
     uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
     PriorSet prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache;   // pair: chains 2k, 2k+1 share a pass when they can;
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache, quad;   // pair: chains 2k, 2k+1 share a pass when they can; quad: chains 4k .. 4k+3 do (needs pair and the cache);
                                                                                                   // colcache: tiles per slot of the per-warp X-column cache (0: off)
 };
 
@@ -671,6 +671,184 @@ __device__ __forceinline__ void warp_pass_jet2(const Dev &d, int c0, const doubl
     for (int k = 0; k < NVD; ++k) { mA[k] = warp_sum(mA[k]); mB[k] = warp_sum(mB[k]); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// GROUP passes: NCH chains (c0 .. c0 + NCH - 1) at the same coordinate share one walk over the rows -- the pair pass
+// carried further.  What a walk costs per TILE (ring bookkeeping, branches, the reads of X_j and X_commit, the
+// look-ahead, the reductions' and the delivery's fixed part, the wait for the slowest CTA) is paid once for NCH chains
+// instead of once per pair: of the pair loop's 242 instructions per tile about 100 are such per-tile work.
+// A group pass is the specialisation for the steady state and ONLY for it: the X-column cache is on, X_commit is held
+// by the cache (or there is no pending update) and X_j is held or being filled by this very pass -- so the loop has
+// no operand-source branches, and a ring stage is [eta_0 .. eta_{NCH-1}, y] x 512 B.  Anything else runs as pair or
+// single passes.  Which kind of walk a WARP uses for a pass is its own business: every warp owns the same rows in
+// every kind of pass (with the cache on the tile -> warp map has no rotation) and delivers once per chain and pass.
+__device__ __forceinline__ bool group_cache_ok(const ColCache &cc, int cj) {
+    return cc.cap > 0 && (cj < 0 || cc.tag0 == cj || cc.tag1 == cj);
+}
+template <int NCH>
+struct GroupStream {
+    const double *pe;          // chain c0's eta at this lane's pair of the tile to be issued next
+    const double *pe_last, *pe_end;
+    double *eta0;              // chain c0's eta; chain k's is eta0 + k * lde
+    const double *y0, *xj0, *xc0;
+    int64_t lde, step;
+    long long vw;
+    int cj, j, sj, t_issue;
+    uint32_t sbase, xj_slot, xc_slot;
+    bool need_y, fillJ;
+#ifdef CGG_DEBUG_GROUP
+    int dbg_cap; int64_t dbg_n;
+#endif
+    __device__ __forceinline__ GroupStream(const Dev &d, int c0, const double *cw, long long wid, long long W, int lane, uint32_t ring,
+                                           ColCache &cc, bool with_y) {
+        const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
+        j = (int)(w0 & 0xffffffffLL);
+        cj = (int)(w1 & 0xffffffffLL);
+        lde = d.lde;
+        eta0 = d.eta + (int64_t)c0 * d.lde;
+        y0 = d.y; xj0 = d.X + (int64_t)j * d.ldx; xc0 = d.X + (int64_t)(cj < 0 ? 0 : cj) * d.ldx;
+        vw = wid;                                   // the cache is on: no rotation (== ChainStream's and PairStream's map)
+        sbase = ring + (uint32_t)lane * 16u;
+        step = W * TILE_ROWS;
+        const int64_t i0 = vw * TILE_ROWS + 2 * lane;
+        pe = eta0 + i0;
+        pe_last = eta0 + (d.n - 1);
+        pe_end = eta0 + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
+        need_y = with_y; t_issue = 0;
+#ifdef CGG_DEBUG_GROUP
+        dbg_cap = cc.cap; dbg_n = d.n;
+        if (j < 0 || j >= d.p || cj >= d.p || c0 < 0 || c0 + NCH > d.C || !group_cache_ok(cc, cj))
+            printf("[group dbg] ctor: c0 %d j %d cj %d p %lld tags %d %d fill %d/%d cap %d\n", c0, j, cj, (long long)d.p, cc.tag0, cc.tag1, cc.fill_col, cc.fill_slot, cc.cap);
+#endif
+        // ---- X_j: held, being filled (a prologue issued early began it), or a miss that this pass fills
+        fillJ = false;
+        if (cc.tag0 == j) sj = 0;
+        else if (cc.tag1 == j) sj = 1;
+        else if (cc.fill_col == j) { sj = cc.fill_slot; fillJ = true; }
+        else {
+            sj = (cj >= 0 && cc.tag0 == cj) ? 1 : 0;
+            if (sj == 0) cc.tag0 = -1; else cc.tag1 = -1;
+            cc.fill_col = j; cc.fill_slot = sj; fillJ = true;
+        }
+        xj_slot = cc.base + (uint32_t)(sj * cc.cap) * 512u;
+        xc_slot = cc.base + (uint32_t)(((cj >= 0 && cc.tag0 == cj) ? 0 : 1) * cc.cap) * 512u;    // (the caller checked group_cache_ok)
+    }
+    __device__ __forceinline__ void issue_next(unsigned st) {
+        if (pe < pe_last) {
+            const uint32_t sa = sbase + st * (RING_OPS * 512u);
+#ifdef CGG_DEBUG_GROUP
+            if (st >= RING_D || t_issue < 0 || (fillJ && t_issue >= dbg_cap) || (pe - eta0) < 0 || (pe - eta0) + 1 >= dbg_n || sj < 0 || sj > 1)
+                printf("[group dbg] issue: st %u t_issue %d cap %d off %lld n %lld sj %d fillJ %d j %d cj %d\n", st, t_issue, dbg_cap, (long long)(pe - eta0), (long long)dbg_n, sj, (int)fillJ, j, cj);
+#endif
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) cp_async16(sa + (uint32_t)k * 512u, pe + k * lde);
+            if (need_y) cp_async16(sa + (uint32_t)NCH * 512u, y0 + (pe - eta0));
+            if (fillJ) cp_async16(xj_slot + (uint32_t)t_issue * 512u, xj0 + (pe - eta0));
+        }
+        cp_async_commit();
+        pe += step;
+        ++t_issue;
+    }
+    __device__ __forceinline__ void prologue(bool skip) {
+        if (skip) { pe += (RING_D - 1) * step; t_issue += RING_D - 1; return; }
+#pragma unroll
+        for (int s = 0; s < RING_D - 1; ++s) issue_next((unsigned)s);
+    }
+    __device__ __forceinline__ void finish(ColCache &cc) const {
+        if (fillJ) { if (sj == 0) cc.tag0 = j; else cc.tag1 = j; cc.fill_col = -1; }
+    }
+};
+
+// cw0: the CTA's shared copies of the control blocks of chains c0 .. c0 + NCH - 1 (consecutive, CTL_WORDS apart), all
+// of them saying the same thing (pair_batchable).  m[k]: the sums of chain c0 + k, reduced over the warp.
+template <int FAMILY, bool FULL, int NCH, class EARLY, class AFTER>
+__device__ __forceinline__ void warp_pass_group(const Dev &d, int c0, const double *cw0, long long wid, long long W, int lane, uint32_t ring,
+                                                const double2 *tab, bool prefetched, ColCache &cc, EARLY &&after_prologue, AFTER &&after_tiles,
+                                                double (&m)[NCH][NV]) {
+    static_assert(NCH + 1 <= RING_OPS, "a group pass stages NCH eta tiles and y");
+    constexpr bool WITH_Y = FAMILY != CGG_BINOMIAL || FULL;        // a binomial light pass never looks at y (C1 carries it)
+    constexpr uint32_t STAGE = RING_OPS * 512u;
+    double cd[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cd[k] = cw0[k * CTL_WORDS + 2];
+    const double cscale = cw0[CTL_WORDS - 1];
+    const int64_t n = d.n;
+    GroupStream<NCH> gs(d, c0, cw0, wid, W, lane, ring, cc, WITH_Y);
+    const int cj = gs.cj;
+    double *eta0 = gs.eta0;
+    const int64_t lde = gs.lde;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) m[k][q] = 0.0;
+    }
+    unsigned risk[NCH], rows = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) risk[k] = 0;
+    gs.prologue(prefetched);
+    after_prologue();
+    unsigned stage = 0;
+    uint32_t t_off = 0;   // byte offset of the tile being scored inside a cache slot
+    // chain c0's eta at this lane's pair of the tile being scored (RING_D - 1 tiles behind the one being issued).  The pending
+    // update is applied unconditionally: without one, commit_delta is 0 and X_commit reads as 0, so eta + 0 * 0 is written back
+    // unchanged (the first pass of a launch only) -- no branch in the loop.
+    double *ps = const_cast<double *>(gs.pe) - (RING_D - 1) * gs.step;      // (the prologue, issued now or earlier, is RING_D - 1 tiles ahead)
+    const int64_t lde_b = lde;
+    for (; gs.pe < gs.pe_end; ) {
+        gs.issue_next((stage + RING_D - 1) & (RING_D - 1));
+        cp_async_wait<RING_D - 1>();
+        if (ps < gs.pe_last) {
+            const uint32_t s = gs.sbase + stage * STAGE;
+#ifdef CGG_DEBUG_GROUP
+            if ((int)(t_off / 512u) >= cc.cap || (ps - eta0) < 0 || (ps - eta0) + 1 >= n)
+                printf("[group dbg] score: t_off %u cap %d off %lld n %lld\n", t_off, cc.cap, (long long)(ps - eta0), (long long)n);
+#endif
+            double2 xs = lds2(gs.xj_slot + t_off);
+            xs.x *= cscale; xs.y *= cscale;
+            double2 cv = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
+            if (cj >= 0) cv = lds2(gs.xc_slot + t_off);
+            if (WITH_Y) yy = lds2(s + (uint32_t)NCH * 512u);
+            rows += 2;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                double2 e = lds2(s + (uint32_t)k * 512u);
+                e.x = eta_shift(e.x, cv.x, cd[k]); e.y = eta_shift(e.y, cv.y, cd[k]);
+                *reinterpret_cast<double2 *>(ps + k * lde_b) = e;
+                JetRow<FAMILY>::template add2<FULL>(yy, e, xs, d.inv_sd, tab, m[k], risk[k]);
+            }
+        }
+        ps += gs.step;
+        t_off += 512u;
+        stage = (stage + 1) & (RING_D - 1);
+    }
+    cp_async_wait<0>();
+    gs.finish(cc);
+    if (n & 1) {  // odd last row of the matrix: one lane of one worker, scalar
+        const int64_t t = n - 1;
+        const long long Tl = t / TILE_ROWS;
+        if (Tl % W == gs.vw && lane == (int)((t % TILE_ROWS) >> 1)) {
+            const double cv = (cj >= 0) ? __ldg(gs.xc0 + t) : 0.0;
+            const double yy = __ldg(d.y + t), xx = __ldg(gs.xj0 + t) * cscale;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                double e = __ldcg(eta0 + k * lde + t);
+                if (cj >= 0) { e = eta_shift(e, cv, cd[k]); eta0[k * lde + t] = e; }
+                JetRow<FAMILY>::template add1<FULL>(yy, e, xx, d.inv_sd, tab, m[k], risk[k]);
+            }
+            rows += 1;
+        }
+    }
+    after_tiles();     // the ring is free: the caller may already request the next group's first tiles
+    constexpr int NVD = (FAMILY == CGG_BINOMIAL && !FULL) ? JET_NVL : NV;      // values this pass delivers
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        if (FAMILY != CGG_GAUSSIAN) m[k][9] = (risk[k] >= JetRow<FAMILY>::RISK_KEY) ? 1.0 : 0.0;
+        if (FAMILY == CGG_BINOMIAL) m[k][8] = rform_noise_sum(risk[k], rows);
+        if (FAMILY == CGG_BINOMIAL && !FULL) jet_light_pack(m[k]);
+#pragma unroll
+        for (int q = 0; q < NVD; ++q) m[k][q] = warp_sum(m[k][q]);
+    }
+}
+
 // Two control blocks describe passes that can share one walk over the rows: both jet passes of the same kind on the
 // same column with the same pending column.
 __device__ __forceinline__ bool pair_batchable(const double *cwA, const double *cwB) {
@@ -790,6 +968,18 @@ struct CtaShared {                       // views into dynamic shared memory, si
 // only reads shared memory) so that its first tiles can be requested before this chain's sums are reduced and
 // delivered, and nobody has to fetch the block from global memory at the top of the next pass.  Decisions are
 // published roughly one pass before they are needed, so a look at the start of the pass would be too early.
+// The CTA's shared view of a chain's version, read ONCE for the warp (lane 0 reads, everybody gets that value) behind a
+// __syncwarp(): every branch of the hand-shake below is taken by all 32 lanes or by none.  A per-lane `volatile` read is
+// not good enough: the lanes of a warp are only guaranteed to be converged at *_sync primitives, another warp updates
+// the word at any time, and lanes that read it a few cycles apart took different branches -- one lane then met its
+// warp's next __shfl_sync at a different call site (seen on the GPU: a version "read" as the halves of two partial sums).
+__device__ __forceinline__ unsigned long long ver_bcast(const unsigned long long *p, int lane) {
+    __syncwarp();
+    unsigned long long v = 0;
+    if (lane == 0) v = *reinterpret_cast<const volatile unsigned long long *>(p);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
 struct LookAhead {
     CtaShared *sh; const ChainSync *sync; const Ctl *ctl;
     int nxt; unsigned long long nround;
@@ -797,7 +987,7 @@ struct LookAhead {
     __device__ __forceinline__ const double *poll(const Dev &d, int lane) {
         if (nxt < 0) return nullptr;
         volatile unsigned long long *sv = &sh->ver[nxt];
-        if (*sv < nround) {
+        if (ver_bcast(&sh->ver[nxt], lane) < nround) {
             int got = 0;
             if (lane == 0) got = (atomicCAS_block(&sh->lock[nxt], 0, 1) == 0);
             got = __shfl_sync(0xffffffffu, got, 0);
@@ -805,8 +995,12 @@ struct LookAhead {
                 unsigned long long v = 0;
                 if (lane == 0) v = ld_acquire_u64(&sync[nxt].version);
                 v = __shfl_sync(0xffffffffu, v, 0);
+#ifdef CGG_DEBUG_GROUP
+                if (lane == 0 && (nxt >= d.C || (v > nround + 2 && v != (1ULL << 62))))
+                    printf("[group dbg] LookAhead cta %d: nxt %d nround %llu v %llu\n", (int)blockIdx.x, nxt, nround, v);
+#endif
                 ++n_look; if (v >= nround) ++n_ok;
-                if (v >= nround && v > *sv) {
+                if (v >= nround && v > ver_bcast(&sh->ver[nxt], lane)) {
                     if (lane < CTL_WORDS) sh->ctl[nxt * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(ctl + nxt) + lane);
                     __syncwarp();
                     if (lane == 0) { __threadfence_block(); *sv = v; }
@@ -816,7 +1010,7 @@ struct LookAhead {
             }
         }
         // the shared control block of `nxt` belongs to version ver[nxt]: usable only if that is exactly the pass we will run
-        return (*sv == nround) ? sh->ctl + nxt * CTL_WORDS : nullptr;
+        return (ver_bcast(&sh->ver[nxt], lane) == nround) ? sh->ctl + nxt * CTL_WORDS : nullptr;
     }
 };
 
@@ -824,7 +1018,8 @@ struct LookAhead {
 // both control blocks).  True when both shared control blocks are exactly those of pass `nround`.
 __device__ __forceinline__ bool pair_lookahead(const Dev &d, CtaShared &sh, int c2, unsigned long long nround, int lane) {
     volatile unsigned long long *sv0 = &sh.ver[c2], *sv1 = &sh.ver[c2 + 1];
-    if (*sv0 < nround || *sv1 < nround) {
+    const unsigned long long s0 = ver_bcast(&sh.ver[c2], lane), s1 = ver_bcast(&sh.ver[c2 + 1], lane);
+    if (s0 < nround || s1 < nround) {
         int got = 0;
         if (lane == 0) got = (atomicCAS_block(&sh.lock[c2], 0, 1) == 0);
         got = __shfl_sync(0xffffffffu, got, 0);
@@ -832,7 +1027,12 @@ __device__ __forceinline__ bool pair_lookahead(const Dev &d, CtaShared &sh, int 
             unsigned long long v = 0;
             if (lane < 2) v = ld_acquire_u64(&d.sync[c2 + lane].version);
             const unsigned long long v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1);
-            const bool n0 = v0 >= nround && v0 > *sv0, n1 = v1 >= nround && v1 > *sv1;
+#ifdef CGG_DEBUG_GROUP
+            if (lane == 0 && (c2 < 0 || c2 + 1 >= d.C || (v0 > nround + 2 && v0 != (1ULL << 62)) || (v1 > nround + 2 && v1 != (1ULL << 62))))
+                printf("[group dbg] pair_lookahead cta %d: c2 %d C %d nround %llu v0 %llu v1 %llu sv0 %llu sv1 %llu\n", (int)blockIdx.x, c2, d.C, nround, v0, v1,
+                       (unsigned long long)*sv0, (unsigned long long)*sv1);
+#endif
+            const bool n0 = v0 >= nround && v0 > s0, n1 = v1 >= nround && v1 > s1;      // (s0, s1 only grow: a stale view repeats a fetch at worst)
             if (n0 || n1) {
                 const int which = lane / CTL_WORDS, word = lane % CTL_WORDS;       // lanes 0..11: chain c2, 12..23: chain c2 + 1
                 if (lane < 2 * CTL_WORDS && (which ? n1 : n0))
@@ -844,7 +1044,7 @@ __device__ __forceinline__ bool pair_lookahead(const Dev &d, CtaShared &sh, int 
             __syncwarp();
         }
     }
-    return *sv0 == nround && *sv1 == nround;
+    return ver_bcast(&sh.ver[c2], lane) == nround && ver_bcast(&sh.ver[c2 + 1], lane) == nround;
 }
 
 // Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
@@ -943,6 +1143,10 @@ __device__ __forceinline__ void cta_deliver_limbs(const Dev &d, CtaShared &sh, i
     // here is a MEMBAR.SC.CTA that also waits for the warp's outstanding global traffic -- the eta stores and the next
     // chain's prefetch just issued -- i.e. for a microsecond or two.)
     int last = 0;
+#ifdef CGG_DEBUG_GROUP
+    if (lane == 0 && (c < 0 || c >= d.C || nc < 0 || nc > NV || warp < 0 || warp >= NWARPS))
+        printf("[group dbg] cta_deliver_limbs cta %d warp %d: chain %d nc %d\n", (int)blockIdx.x, warp, c, nc);
+#endif
     if (lane == 0) {
         volatile double *pw = sh.part + ((size_t)c * NWARPS + warp) * NV;
 #pragma unroll

@@ -65,6 +65,12 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
             if (oc == DEC_ABORT) { if (lane == 0) { d.hdr->abort = 1; fence_gpu(); } return; }   // a peer rank never delivered
             const bool fin = oc == DEC_FINISHED;
+#ifdef CGG_DEBUG_GROUP
+            if (lane == 0) {
+                const unsigned long long cur = __ldcg(&d.sync[c].version);
+                if (cur != v) printf("[group dbg] DECIDER chain %d: version was %llu when the pass was taken up, now 0x%llx (arrive word 0x%llx)\n", c, v, cur, (unsigned long long)__ldcg(&d.sync[c].arrive));
+            }
+#endif
             if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
             if (!fin) {                                              // after publishing: off the chain's critical path
                 decider_prefetch(d, c, cache + c, lane);
@@ -80,7 +86,18 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
         if (progressed) { idle = 0; t0 = globaltimer_ns(); }
         else {
             __nanosleep(40);
-            if ((++idle & 255u) == 0 && wait_timed_out(d, t0, lane)) break;
+            if ((++idle & 255u) == 0 && wait_timed_out(d, t0, lane)) {
+#ifdef CGG_DEBUG_GROUP
+                for (int c = first_chain; c < d.C; c += stride)
+                    if (lane == 0) {
+                        const unsigned long long w0 = __ldcg(&d.lacc[(size_t)c * NV].w[0]), w1 = __ldcg(&d.lacc[(size_t)c * NV + 1].w[0]), w4 = __ldcg(&d.lacc[(size_t)c * NV + 4].w[0]);
+                        printf("[group dbg] decider chain %d version %llu | arrivals (mod 256) value 0: %d (prev %d), value 1: %d (prev %d), value 4: %d (prev %d) | ctl j %d cj %d mask %x\n", c,
+                               (unsigned long long)__ldcg(&d.sync[c].version), (int)(w0 >> 56), (int)(cache[c].prev[0] >> 56), (int)(w1 >> 56), (int)(cache[c].prev[4] >> 56),
+                               (int)(w4 >> 56), (int)(cache[c].prev[16] >> 56), cache[c].ct.j, cache[c].ct.commit_j, (unsigned)cache[c].ct.coarse_mask);
+                    }
+#endif
+                break;
+            }
         }
     }
 }
@@ -107,7 +124,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     const long long wid = (long long)blockIdx.x * NWARPS + warp;
     const long long W = (long long)d.G * NWARPS;
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
-    double acc[NV];
     bool prefetched = false;
     long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0, n_notready = 0, n_look = 0, n_look_ok = 0;
     const bool prof = d.prof != nullptr;
@@ -116,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     // into shared memory; the other warps only watch shared memory.  Returns false if the wait timed out.
     auto wait_decision = [&](int c, unsigned long long round) -> bool {
         volatile unsigned long long *sv = &sh.ver[c];
-        if (*sv < round) {
+        if (ver_bcast(&sh.ver[c], lane) < round) {
             ++n_slow;
             const unsigned long long t0 = globaltimer_ns();
             unsigned spins = 0;
@@ -128,28 +144,57 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     unsigned long long v = 0;
                     if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
                     v = __shfl_sync(0xffffffffu, v, 0);
+#ifdef CGG_DEBUG_GROUP
+                    if (lane == 0 && (c < 0 || c >= d.C || (v > round + 2 && v != (1ULL << 62))))
+                        printf("[group dbg] wait_decision cta %d warp %d: chain %d round %llu v %llu sv %llu\n", (int)blockIdx.x, warp, c, round, v, (unsigned long long)*sv);
+#endif
                     if (v < round) ++n_notready;
-                    if (v >= round && v > *sv) {
+                    if (v >= round && v > ver_bcast(&sh.ver[c], lane)) {
                         if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
                         __syncwarp();
                         if (lane == 0) { __threadfence_block(); *sv = v; }
                     }
                     if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
                 }
-                if (*sv >= round) break;
+                if (ver_bcast(&sh.ver[c], lane) >= round) break;
                 __nanosleep(spins < 8 ? 64 : 256);
-                if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) return false;
+                if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) {
+#ifdef CGG_DEBUG_GROUP
+                    if (lane == 0 && warp < 2 && blockIdx.x < 3)
+                        printf("[group dbg] worker cta %d warp %d waits for chain %d round %llu: shared ver %llu, global ver %llu | ctl j %d cj %d\n", (int)blockIdx.x, warp, c, round,
+                               (unsigned long long)*sv, (unsigned long long)__ldcg(&d.sync[c].version), __ldcg(&d.ctl[c].j), __ldcg(&d.ctl[c].commit_j));
+#endif
+                    return false;
+                }
             }
         }
         __syncwarp();
         return true;
     };
-    double acc2[NV];
+    double accg[4][NV];
+#ifdef CGG_DEBUG_GROUP
+    unsigned long long dbg_last[CMAX];
+    bool dbg_seen = false; int dbg_action = 0;
+    for (int i = 0; i < CMAX; ++i) dbg_last[i] = ~0ULL;
+    auto dbg_deliver = [&](int cc_, unsigned long long round_, int path, int nvals) {
+        const unsigned long long sv = *(volatile unsigned long long *)&sh.ver[cc_], gv = sv;
+        const unsigned long long want = dbg_last[cc_] + 1ULL;      // ~0 + 1 = 0: the first delivery is round 0
+        if (lane == 0 && (round_ != want || sv != round_ || (nvals < 2 && round_ >= 1 && round_ <= 4)))
+            printf("[group dbg] DELIVERY cta %d warp %d chain %d round %llu path %d nvals %d: last delivered %lld, global ver %llu, shared ver %llu\n",
+                   (int)blockIdx.x, warp, cc_, round_, path, nvals, (long long)dbg_last[cc_], gv, sv);
+        dbg_last[cc_] = round_;
+    };
+#endif
+    double (&acc)[NV] = accg[0];
+    double (&acc2)[NV] = accg[1];
     bool pair_prefetched = false;
-    int pf_j = -1, pf_cj = -1; bool pf_full = false;      // what the pair prologue issued ahead of time was issued for
-    ColCache cc;        // this warp's X-column cache (pair passes); lives for the launch
+    int pf_j = -1, pf_cj = -1, pf_g = 0; bool pf_full = false, pf_pred = false;      // what the pair / group prologue issued ahead of time was issued for
+    ColCache cc;        // this warp's X-column cache (pair and group passes); lives for the launch
     cc.cap = d.colcache; cc.base = sh.cache0 + (uint32_t)warp * (uint32_t)(2 * d.colcache) * 512u + (uint32_t)lane * 16u;
     cc.tag0 = cc.tag1 = -1; cc.fill_col = cc.fill_slot = -1;
+    // group passes (four chains per walk): the steady-state kinds of pass only (binomial light passes, gaussian)
+    constexpr bool GROUP_FAMILY = FAMILY == CGG_BINOMIAL || FAMILY == CGG_GAUSSIAN;
+    int n_group = 0;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
         for (int c = 0; c < d.C; ++c) {
@@ -157,6 +202,15 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             if (prof && lane == 0 && round >= 1 && round <= 128) {
                 if (blockIdx.x == 20 && warp == 0) d.prof[32 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
             }
+#ifdef CGG_DEBUG_GROUP
+            for (int q = 0; q < d.C; ++q) {
+                const unsigned long long vq = *(volatile unsigned long long *)&sh.ver[q];
+                if (lane == 0 && vq > round + 2 && vq != (1ULL << 62) && !dbg_seen) {
+                    dbg_seen = true;
+                    printf("[group dbg] CANARY cta %d warp %d at round %llu item %d: shared ver[%d] = %llu (0x%llx); last action %d\n", (int)blockIdx.x, warp, round, c, q, vq, vq, dbg_action);
+                }
+            }
+#endif
             if (!wait_decision(c, round)) return;
             // ---- chains 2k and 2k + 1 at the same coordinate share one walk over the rows (pair pass)
             bool pair = false;
@@ -164,15 +218,29 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 ((unsigned)(__double_as_longlong(sh.ctl[c * CTL_WORDS + 1]) >> 32) & JET_BIT)) {     // only a jet pass can be shared
                 if (!wait_decision(c + 1, round)) return;
                 // the shared control blocks must be exactly the ones of this round (a finished chain's never are)
-                pair = (*(volatile unsigned long long *)&sh.ver[c] == round) && (*(volatile unsigned long long *)&sh.ver[c + 1] == round) &&
+                pair = ver_bcast(&sh.ver[c], lane) == round && ver_bcast(&sh.ver[c + 1], lane) == round &&
                        pair_batchable(sh.ctl + c * CTL_WORDS, sh.ctl + (c + 1) * CTL_WORDS);
+            }
+            // ---- ... and chains 4k .. 4k + 3 (group pass) when all four say the same and the X-column cache serves the walk
+            int g = pair ? 2 : 1;
+            if (GROUP_FAMILY && pair && d.quad && !(c & 3) && c + 3 < d.C && cc.cap > 0) {
+                const double *cw = sh.ctl + c * CTL_WORDS;
+                const long long w1 = __double_as_longlong(cw[1]);
+                const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                if (FAMILY != CGG_BINOMIAL || !full) {
+                    if (!wait_decision(c + 2, round) || !wait_decision(c + 3, round)) return;
+                    if (ver_bcast(&sh.ver[c + 2], lane) == round && ver_bcast(&sh.ver[c + 3], lane) == round &&
+                        pair_batchable(cw, cw + 2 * CTL_WORDS) && pair_batchable(cw, cw + 3 * CTL_WORDS) &&
+                        group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) g = 4;
+                }
             }
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
             if (pair_prefetched) {
                 // the first tiles of this pass were requested ahead of time, possibly from a PREDICTED control block (same kind of
                 // pass, next column): they are only good if the real block says the same
-                bool good = pair;
+                bool good = g >= 2 && g == pf_g;
+                if (pf_g == 4 && pf_pred && (d.quad & 16)) good = false;       // (diagnostic: never use tiles requested from a prediction)
                 if (good) {
                     const double *cwA = sh.ctl + c * CTL_WORDS;
                     const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
@@ -182,6 +250,77 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 if (!good) { cp_async_wait<0>(); pair_prefetched = false; ++n_notready; }
             }
             if (pair && prefetched) { cp_async_wait<0>(); prefetched = false; }               // a single-pass prefetch of chain c: other ring layout
+            if constexpr (GROUP_FAMILY) if (g == 4) {
+                const double *cw0 = sh.ctl + c * CTL_WORDS;
+                constexpr bool GFULL = FAMILY != CGG_BINOMIAL;          // (binomial: light passes only, see above)
+                const bool was_pref = pair_prefetched;
+                pair_prefetched = false;
+                // which group comes next, and in which round
+                int c2 = -1; unsigned long long nround = round;
+                if (c + 4 >= d.C) { c2 = 0; nround = round + 1; }               // this is the last item of the round
+                else if (c + 7 < d.C) c2 = c + 4;                               // another group of four follows
+                if (c2 == c) c2 = -1;                                           // (the only group: its next decision cannot be there yet)
+                auto early = [&]() {      // with three or more groups the next group's decisions are published about a pass ahead
+                    if (c2 >= 0 && d.C >= 12 && warp == (int)((round + (unsigned long long)(c >> 2)) % NWARPS)) {
+                        pair_lookahead(d, sh, c2, nround, lane); pair_lookahead(d, sh, c2 + 2, nround, lane);
+                    }
+                };
+                auto after = [&]() {
+                    if (c2 < 0 || (d.quad & 2)) return;
+                    pf_pred = false;
+                    double pred[2];
+                    const double *nA = sh.ctl + c2 * CTL_WORDS;
+                    const bool l0 = pair_lookahead(d, sh, c2, nround, lane);
+                    const bool l1 = l0 && pair_lookahead(d, sh, c2 + 2, nround, lane);
+                    if (l1) {
+                        if (!(pair_batchable(nA, nA + CTL_WORDS) && pair_batchable(nA, nA + 2 * CTL_WORDS) && pair_batchable(nA, nA + 3 * CTL_WORDS))) return;
+                    } else if (!l0) {
+                        if (d.quad & 4) return;
+                        if ((d.quad & 32) && c2 == 0) return;       // (diagnostic: no prediction across rounds)
+                        if ((d.quad & 64) && c2 != 0) return;       // (diagnostic: no prediction inside a round)
+                        pf_pred = true;
+                        // not published yet: predict the pass (same kind, next column, committing the column just sampled), as the
+                        // pair passes do; the real blocks are compared with the prediction before the tiles are used
+                        // (the block may be rewritten by another warp of the CTA at any moment: one lane reads it for the warp)
+                        const long long w0 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[0]), 0), w1 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[1]), 0);
+                        const int jp = (int)(w0 & 0xffffffffLL);
+                        const unsigned mk = (unsigned)(w1 >> 32);
+                        if (!(mk & JET_BIT) || jp < 0 || (long long)jp >= (long long)d.p) return;
+                        const int jn = (jp + 1 == (int)d.p) ? 0 : jp + 1;
+                        pred[0] = __longlong_as_double((long long)(unsigned)jn);
+                        pred[1] = __longlong_as_double(((long long)mk << 32) | (long long)(unsigned)jp);
+                        nA = pred;
+                    } else if (d.quad & 8) return;                              // (l0 only: chain c2's real block stands for the group)
+                    const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
+                    const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                    if (!(((unsigned)(w1 >> 32)) & JET_BIT) || (int)(w0 & 0xffffffffLL) < 0 || full2 != GFULL) return;
+                    if (!group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) return;
+                    pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2; pf_g = 4;
+                    if (pf_pred && (d.quad & 256)) { pf_g = 99; pair_prefetched = true; return; }      // (diagnostic: bookkeeping only)
+                    GroupStream<4> ns(d, c2, nA, wid, W, lane, ring, cc, FAMILY != CGG_BINOMIAL || full2);
+                    if (pf_pred && (d.quad & 128)) { pf_g = 99; pair_prefetched = true; return; }      // (diagnostic: no loads)
+                    ns.prologue(false);
+                    pair_prefetched = true;
+                };
+                warp_pass_group<FAMILY, GFULL, 4>(d, c, cw0, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, accg);
+#ifdef CGG_DEBUG_GROUP
+                dbg_action = 400 + c * 10 + (was_pref ? 1 : 0) + (pair_prefetched ? 2 : 0) + (pf_pred ? 4 : 0);
+#endif
+                any = true;
+                ++n_group;
+                n_pref += pair_prefetched ? 1 : 0;
+                long long tC = prof ? clock64() : 0;
+                t_rows += tC - tB; t_tiles += tC - tB;
+                const int nvd = jet_nvals(FAMILY, !GFULL);
+#ifdef CGG_DEBUG_GROUP
+                for (int k = 0; k < 4; ++k) dbg_deliver(c + k, round, 4, nvd);
+#endif
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cta_deliver_limbs(d, sh, c + k, nvd, warp, lane, nworkers, accg[k]);
+                if (prof) t_arrive += clock64() - tC;
+                c += 3;
+                continue;
+            }
             if (pair) {
                 const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
                 const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(cwA[1]) >> 32)) & JET_FULL);
@@ -214,7 +353,8 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                         // tiles do not depend on the decision's VALUE, only on which pass comes: in the stationary regime
                         // that is a jet pass of the same kind on the next column, applying the update of the column just
                         // sampled.  Request them from that prediction; the real block is compared with it before use.
-                        const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
+                        // (the block may be rewritten by another warp of the CTA at any moment: one lane reads it for the warp)
+                        const long long w0 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[0]), 0), w1 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[1]), 0);
                         const int jp = (int)(w0 & 0xffffffffLL);
                         const unsigned mk = (unsigned)(w1 >> 32);
                         if (!(mk & JET_BIT) || jp < 0 || (long long)jp >= (long long)d.p) return;
@@ -225,11 +365,14 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     }
                     const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
                     const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
-                    pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2;
+                    pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2; pf_g = 2;
                     PairStream ns(d, c2, nA, wid, W, lane, ring, cc, full2);
                     ns.prologue(false);
                     pair_prefetched = true;
                 };
+#ifdef CGG_DEBUG_GROUP
+                dbg_action = 200 + c * 10 + (was_pref ? 1 : 0);
+#endif
                 if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
                 else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
                 any = true;
@@ -237,6 +380,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 long long tC = prof ? clock64() : 0;
                 t_rows += tC - tB; t_tiles += tC - tB;
                 const int nvd = jet_nvals(FAMILY, !full);
+#ifdef CGG_DEBUG_GROUP
+                dbg_deliver(c, round, 2, nvd); dbg_deliver(c + 1, round, 2, nvd);
+#endif
                 cta_deliver_limbs(d, sh, c, nvd, warp, lane, nworkers, acc);
                 cta_deliver_limbs(d, sh, c + 1, nvd, warp, lane, nworkers, acc2);
                 if (prof) t_arrive += clock64() - tC;
@@ -257,6 +403,9 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
+#ifdef CGG_DEBUG_GROUP
+            dbg_deliver(c, round, 1, nc);
+#endif
             cta_deliver_limbs(d, sh, c, nc, warp, lane, nworkers, acc);
             if (prof && lane == 0 && round == 60 && c == 0)
                 d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
@@ -269,6 +418,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         }
         if (!any) break;
     }
+    if (n_group && wid == 0 && lane == 0) atomicAdd(&d.hdr->group_passes, n_group);
     if (prof && lane == 0) {
         atomicAdd(d.prof + 0, (unsigned long long)t_wait); atomicAdd(d.prof + 1, (unsigned long long)t_rows);
         atomicAdd(d.prof + 2, (unsigned long long)t_arrive); atomicAdd(d.prof + 5, (unsigned long long)n_slow);
@@ -1027,6 +1177,11 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (G < 1) G = 1;
     d.G = (int)G;
     if (d.colcache && (int64_t)d.colcache * (int64_t)d.G * NWARPS < d.n_tiles) d.colcache = 0;    // (fewer CTAs than assumed: a warp's tiles would not fit)
+    {   // group passes (chains 4k .. 4k + 3 share a walk): from 8 chains on, so that a group's decisions still hide behind another
+        // group's pass; they need pair passes and the X-column cache.  CGG_QUAD=0/1 overrides (experiments, tests)
+        const char *e5 = getenv("CGG_QUAD");
+        d.quad = ((e5 ? atoi(e5) != 0 : C >= 8) && d.pair && d.colcache > 0) ? (e5 && atoi(e5) > 1 ? atoi(e5) : 1) : 0;      // (bit 1: no look-ahead prefetch between groups, a diagnostic)
+    }
     d.lde = (d.n + 31) / 32 * 32;
     {   // small n: one cluster per chain instead of the grid-wide protocol
         const char *e3 = getenv("CGG_SMALLN");
@@ -1059,7 +1214,7 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
                 if (cfg->driver == CGG_DRIVER_CLUSTER) { delete h; return fail(CGG_E_CUDA, "cgg_create: the device cannot run the cluster driver"); }
             } else {
                 h->cluster_S = S;
-                d.pair = 0; d.coarse = 0;       // one chain per cluster; the pre-filter's clamp flags live in global memory
+                d.pair = 0; d.quad = 0; d.coarse = 0;       // one chain per cluster; the pre-filter's clamp flags live in global memory
             }
         }
     }
@@ -1131,6 +1286,9 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
             if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
         }
     }
+    if (getenv("CGG_DEBUG_PTRS"))
+        fprintf(stderr, "[cgg ptrs] eta %p beta %p shat %p acc %p sync %p xbuf %p lacc %p ctl %p cs %p hdr %p colstat %p\n", (void *)d.eta, (void *)d.beta, (void *)d.shat,
+                (void *)d.acc, (void *)d.sync, (void *)d.xbuf, (void *)d.lacc, (void *)d.ctl, (void *)d.cs, (void *)d.hdr, (void *)h->colstat_dev);
     *out = h;
     return CGG_OK;
 }
@@ -1864,7 +2022,7 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     // be initialised again before it can run (cgg_init_chain / cgg_set_state)
     for (int c = 0; c < C; ++c)
         if (cs[c].status != CGG_OK || hdr.abort) { h->chain_init[c] = 0; h->fx_valid[c] = 0; h->fx_mag[c] = 0; }
-    st.launches = launches; st.sweep_ms = ms;
+    st.launches = launches; st.sweep_ms = ms; st.group_passes = (uint64_t)hdr.group_passes;
     st.algorithmic_bytes = 8.0 * (double)d.n * (3.0 * (double)st.chain_passes + 2.0 * (double)st.commit_passes);
     if (stats) *stats = st;
     if (hdr.abort) return fail(CGG_E_CUDA, "cgg_run: a chain wait timed out (a worker never arrived)");

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.Config) == 136
-    assert C.sizeof(_lib.Stats) == 128
+    assert C.sizeof(_lib.Stats) == 136
 
 
 def test_unsupported_inputs_are_rejected_before_touching_cuda():

@@ -157,3 +157,38 @@ def test_pair_single_handover_stress_keeps_eta_ownership(monkeypatch):
     for (b1, e1), (b0, e0) in zip(fin1, fin0):
         assert np.array_equal(e1, e0) and np.array_equal(b1, b0)
         assert np.max(np.abs(e1 - X @ b1)) < 1e-11
+
+
+@pytest.mark.parametrize("family,n", [("binomial", 150_001), ("gaussian", 150_001), ("binomial", 300_032)])
+def test_group_passes_change_nothing(monkeypatch, family, n):
+    """Group passes (four chains per walk over the rows, X-column cache required) are scheduling only: same samples, same
+    counts as pair passes and as one chain per pass; chain 0 also equals the oracle.  n odd (scalar tail row) and n a
+    multiple of the tile size; 12 chains = two groups of four that look ahead at each other + ... a third one; the chains
+    start at different points, so early iterations mix exact-pass hand-overs, pair passes and group passes."""
+    p, C, iters = 5, 12, 11
+    X, y, bt = synth(family, n, p, seed=29)
+    beta0 = bt + 0.05 * np.random.default_rng(5).standard_normal((C, p))
+    U = np.random.default_rng(6).random((C, 4000 + 60 * iters * p))
+
+    def run(pair, quad, chunk=8):
+        monkeypatch.setenv("CGG_PAIR", str(pair))
+        monkeypatch.setenv("CGG_QUAD", str(quad))
+        monkeypatch.setenv("CGG_CHUNK", str(chunk))
+        monkeypatch.setenv("CGG_SMALLN", "0")
+        return _chains(family, "laplace", X, y, beta0, iters, U, w=0.5, driver="grid")
+    S0, st0 = run(0, 0)
+    assert st0["group_passes"] == 0
+    for pair, quad, chunk in ((1, 0, 8), (1, 1, 8), (1, 1, 3)):
+        S, st = run(pair, quad, chunk)
+        assert np.array_equal(S, S0), (pair, quad, chunk)
+        for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
+            assert st[k] == st0[k], (pair, quad, chunk, k)
+        if quad:
+            assert st["group_passes"] > iters * p, st["group_passes"]      # most walks of worker warp 0 served four chains
+        else:
+            assert st["group_passes"] == 0
+    m = oracle.make_model(family, sd=1.0, **PRIOR_CASES["laplace"])
+    ref = oracle.run_chain(m, X, y, beta0[0], w=0.5, n_iter=iters, max_steps=-1, replay_u=U[0])
+    assert ref["rc"] == 0
+    assert np.max(np.abs(S0[0] - ref["samples"])) <= ATOL
+    assert st0["uniforms_used"][0] == ref["uniforms_used"]
