@@ -127,7 +127,7 @@ struct Dev {
     int32_t rank;
     uint64_t replay_origin[CMAX];   // replay mode: the chain's uniform cursor at the start of this cgg_run (replay_u is indexed from there)
     PriorSet prior;
-    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache, quad;   // pair: chains 2k, 2k+1 share a pass when they can; quad: chains 4k .. 4k+3 do (needs pair and the cache);
+    int32_t C, K, G, family, chain_offset, sharded, coarse, jet, jet_light, world, pair, colcache, quad, early;   // pair: chains 2k, 2k+1 share a pass when they can; quad: chains 4k .. 4k+3 do (needs pair and the cache);
                                                                                                   // colcache: tiles per slot of the per-warp X-column cache (0: off)
 };
 
@@ -695,9 +695,6 @@ struct GroupStream {
     int cj, j, sj, t_issue;
     uint32_t sbase, xj_slot, xc_slot;
     bool need_y, fillJ;
-#ifdef CGG_DEBUG_GROUP
-    int dbg_cap; int64_t dbg_n;
-#endif
     __device__ __forceinline__ GroupStream(const Dev &d, int c0, const double *cw, long long wid, long long W, int lane, uint32_t ring,
                                            ColCache &cc, bool with_y) {
         const long long w0 = __double_as_longlong(cw[0]), w1 = __double_as_longlong(cw[1]);
@@ -714,11 +711,6 @@ struct GroupStream {
         pe_last = eta0 + (d.n - 1);
         pe_end = eta0 + d.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
         need_y = with_y; t_issue = 0;
-#ifdef CGG_DEBUG_GROUP
-        dbg_cap = cc.cap; dbg_n = d.n;
-        if (j < 0 || j >= d.p || cj >= d.p || c0 < 0 || c0 + NCH > d.C || !group_cache_ok(cc, cj))
-            printf("[group dbg] ctor: c0 %d j %d cj %d p %lld tags %d %d fill %d/%d cap %d\n", c0, j, cj, (long long)d.p, cc.tag0, cc.tag1, cc.fill_col, cc.fill_slot, cc.cap);
-#endif
         // ---- X_j: held, being filled (a prologue issued early began it), or a miss that this pass fills
         fillJ = false;
         if (cc.tag0 == j) sj = 0;
@@ -735,10 +727,6 @@ struct GroupStream {
     __device__ __forceinline__ void issue_next(unsigned st) {
         if (pe < pe_last) {
             const uint32_t sa = sbase + st * (RING_OPS * 512u);
-#ifdef CGG_DEBUG_GROUP
-            if (st >= RING_D || t_issue < 0 || (fillJ && t_issue >= dbg_cap) || (pe - eta0) < 0 || (pe - eta0) + 1 >= dbg_n || sj < 0 || sj > 1)
-                printf("[group dbg] issue: st %u t_issue %d cap %d off %lld n %lld sj %d fillJ %d j %d cj %d\n", st, t_issue, dbg_cap, (long long)(pe - eta0), (long long)dbg_n, sj, (int)fillJ, j, cj);
-#endif
 #pragma unroll
             for (int k = 0; k < NCH; ++k) cp_async16(sa + (uint32_t)k * 512u, pe + k * lde);
             if (need_y) cp_async16(sa + (uint32_t)NCH * 512u, y0 + (pe - eta0));
@@ -798,10 +786,6 @@ __device__ __forceinline__ void warp_pass_group(const Dev &d, int c0, const doub
         cp_async_wait<RING_D - 1>();
         if (ps < gs.pe_last) {
             const uint32_t s = gs.sbase + stage * STAGE;
-#ifdef CGG_DEBUG_GROUP
-            if ((int)(t_off / 512u) >= cc.cap || (ps - eta0) < 0 || (ps - eta0) + 1 >= n)
-                printf("[group dbg] score: t_off %u cap %d off %lld n %lld\n", t_off, cc.cap, (long long)(ps - eta0), (long long)n);
-#endif
             double2 xs = lds2(gs.xj_slot + t_off);
             xs.x *= cscale; xs.y *= cscale;
             double2 cv = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
@@ -968,16 +952,17 @@ struct CtaShared {                       // views into dynamic shared memory, si
 // only reads shared memory) so that its first tiles can be requested before this chain's sums are reduced and
 // delivered, and nobody has to fetch the block from global memory at the top of the next pass.  Decisions are
 // published roughly one pass before they are needed, so a look at the start of the pass would be too early.
-// The CTA's shared view of a chain's version, read ONCE for the warp (lane 0 reads, everybody gets that value) behind a
-// __syncwarp(): every branch of the hand-shake below is taken by all 32 lanes or by none.  A per-lane `volatile` read is
-// not good enough: the lanes of a warp are only guaranteed to be converged at *_sync primitives, another warp updates
-// the word at any time, and lanes that read it a few cycles apart took different branches -- one lane then met its
-// warp's next __shfl_sync at a different call site (seen on the GPU: a version "read" as the halves of two partial sums).
-__device__ __forceinline__ unsigned long long ver_bcast(const unsigned long long *p, int lane) {
-    __syncwarp();
-    unsigned long long v = 0;
-    if (lane == 0) v = *reinterpret_cast<const volatile unsigned long long *>(p);
-    return __shfl_sync(0xffffffffu, v, 0);
+// The CTA's shared view of a chain's version is read by ONE lane and the verdict shared with a warp vote: every branch
+// of the hand-shake below is then taken by all 32 lanes or by none.  A per-lane `volatile` read is not good enough: the
+// lanes of a warp are only guaranteed to be converged at *_sync primitives, another warp updates the word at any time,
+// and lanes that read it a few cycles apart took different branches -- one lane then met its warp's next __shfl_sync at
+// a different call site (seen on the GPU: a version "read" as the halves of two partial sums).
+__device__ __forceinline__ unsigned long long ver_read(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
+__device__ __forceinline__ bool ver_below(const unsigned long long *p, unsigned long long round, int lane) {     // shared version < round ?
+    return __any_sync(0xffffffffu, lane == 0 && ver_read(p) < round);
+}
+__device__ __forceinline__ bool ver_is(const unsigned long long *p, unsigned long long round, int lane) {        // shared version == round ?
+    return __any_sync(0xffffffffu, lane == 0 && ver_read(p) == round);
 }
 
 struct LookAhead {
@@ -987,7 +972,7 @@ struct LookAhead {
     __device__ __forceinline__ const double *poll(const Dev &d, int lane) {
         if (nxt < 0) return nullptr;
         volatile unsigned long long *sv = &sh->ver[nxt];
-        if (ver_bcast(&sh->ver[nxt], lane) < nround) {
+        if (ver_below(&sh->ver[nxt], nround, lane)) {
             int got = 0;
             if (lane == 0) got = (atomicCAS_block(&sh->lock[nxt], 0, 1) == 0);
             got = __shfl_sync(0xffffffffu, got, 0);
@@ -995,12 +980,8 @@ struct LookAhead {
                 unsigned long long v = 0;
                 if (lane == 0) v = ld_acquire_u64(&sync[nxt].version);
                 v = __shfl_sync(0xffffffffu, v, 0);
-#ifdef CGG_DEBUG_GROUP
-                if (lane == 0 && (nxt >= d.C || (v > nround + 2 && v != (1ULL << 62))))
-                    printf("[group dbg] LookAhead cta %d: nxt %d nround %llu v %llu\n", (int)blockIdx.x, nxt, nround, v);
-#endif
                 ++n_look; if (v >= nround) ++n_ok;
-                if (v >= nround && v > ver_bcast(&sh->ver[nxt], lane)) {
+                if (__any_sync(0xffffffffu, lane == 0 && v >= nround && v > ver_read(&sh->ver[nxt]))) {
                     if (lane < CTL_WORDS) sh->ctl[nxt * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(ctl + nxt) + lane);
                     __syncwarp();
                     if (lane == 0) { __threadfence_block(); *sv = v; }
@@ -1010,41 +991,37 @@ struct LookAhead {
             }
         }
         // the shared control block of `nxt` belongs to version ver[nxt]: usable only if that is exactly the pass we will run
-        return (ver_bcast(&sh->ver[nxt], lane) == nround) ? sh->ctl + nxt * CTL_WORDS : nullptr;
+        return ver_is(&sh->ver[nxt], nround, lane) ? sh->ctl + nxt * CTL_WORDS : nullptr;
     }
 };
 
 // The same for a PAIR of chains (c2, c2 + 1) with one election and two concurrent round trips (both version flags, then
 // both control blocks).  True when both shared control blocks are exactly those of pass `nround`.
 __device__ __forceinline__ bool pair_lookahead(const Dev &d, CtaShared &sh, int c2, unsigned long long nround, int lane) {
-    volatile unsigned long long *sv0 = &sh.ver[c2], *sv1 = &sh.ver[c2 + 1];
-    const unsigned long long s0 = ver_bcast(&sh.ver[c2], lane), s1 = ver_bcast(&sh.ver[c2 + 1], lane);
-    if (s0 < nround || s1 < nround) {
+    // lane k < 2 looks after chain c2 + k: its shared version, its global version, and -- when that has moved on -- the
+    // publication of the fetched block; the other lanes learn what they have to know through votes
+    unsigned long long sv = (lane < 2) ? ver_read(&sh.ver[c2 + lane]) : ~0ULL;
+    if (__any_sync(0xffffffffu, sv < nround)) {
         int got = 0;
         if (lane == 0) got = (atomicCAS_block(&sh.lock[c2], 0, 1) == 0);
-        got = __shfl_sync(0xffffffffu, got, 0);
-        if (got) {
+        if (__any_sync(0xffffffffu, got != 0)) {
             unsigned long long v = 0;
-            if (lane < 2) v = ld_acquire_u64(&d.sync[c2 + lane].version);
-            const unsigned long long v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1);
-#ifdef CGG_DEBUG_GROUP
-            if (lane == 0 && (c2 < 0 || c2 + 1 >= d.C || (v0 > nround + 2 && v0 != (1ULL << 62)) || (v1 > nround + 2 && v1 != (1ULL << 62))))
-                printf("[group dbg] pair_lookahead cta %d: c2 %d C %d nround %llu v0 %llu v1 %llu sv0 %llu sv1 %llu\n", (int)blockIdx.x, c2, d.C, nround, v0, v1,
-                       (unsigned long long)*sv0, (unsigned long long)*sv1);
-#endif
-            const bool n0 = v0 >= nround && v0 > s0, n1 = v1 >= nround && v1 > s1;      // (s0, s1 only grow: a stale view repeats a fetch at worst)
-            if (n0 || n1) {
+            if (lane < 2) { v = ld_acquire_u64(&d.sync[c2 + lane].version); sv = ver_read(&sh.ver[c2 + lane]); }
+            const bool fresh = lane < 2 && v >= nround && v > sv;         // (a stale view repeats a fetch at worst: versions only grow)
+            const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+            if (fm) {
                 const int which = lane / CTL_WORDS, word = lane % CTL_WORDS;       // lanes 0..11: chain c2, 12..23: chain c2 + 1
-                if (lane < 2 * CTL_WORDS && (which ? n1 : n0))
+                if (lane < 2 * CTL_WORDS && ((fm >> which) & 1u))
                     sh.ctl[(c2 + which) * CTL_WORDS + word] = __ldcg(reinterpret_cast<const double *>(d.ctl + c2 + which) + word);
                 __syncwarp();
-                if (lane == 0) { __threadfence_block(); if (n0) *sv0 = v0; if (n1) *sv1 = v1; }
+                if (fresh) { __threadfence_block(); *reinterpret_cast<volatile unsigned long long *>(&sh.ver[c2 + lane]) = v; }
             }
-            if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c2], 0); }
             __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c2], 0); }
         }
     }
-    return ver_bcast(&sh.ver[c2], lane) == nround && ver_bcast(&sh.ver[c2 + 1], lane) == nround;
+    sv = (lane < 2) ? ver_read(&sh.ver[c2 + lane]) : nround;
+    return __all_sync(0xffffffffu, sv == nround);
 }
 
 // Deliver a warp's partial sums.  The last warp of the CTA to deliver (returns true in all its lanes)
@@ -1143,10 +1120,6 @@ __device__ __forceinline__ void cta_deliver_limbs(const Dev &d, CtaShared &sh, i
     // here is a MEMBAR.SC.CTA that also waits for the warp's outstanding global traffic -- the eta stores and the next
     // chain's prefetch just issued -- i.e. for a microsecond or two.)
     int last = 0;
-#ifdef CGG_DEBUG_GROUP
-    if (lane == 0 && (c < 0 || c >= d.C || nc < 0 || nc > NV || warp < 0 || warp >= NWARPS))
-        printf("[group dbg] cta_deliver_limbs cta %d warp %d: chain %d nc %d\n", (int)blockIdx.x, warp, c, nc);
-#endif
     if (lane == 0) {
         volatile double *pw = sh.part + ((size_t)c * NWARPS + warp) * NV;
 #pragma unroll
@@ -1519,6 +1492,34 @@ __device__ __forceinline__ void jet_pre_load(const JetPre *p, int lane, JetLane 
     sc = p->sc;
 }
 
+// The verdict on one candidate v (log-prior pv) from a jet pass's sums: certainly inside the slice, certainly outside, or
+// neither; fnew: the log-potential at v (full pass: enclosure midpoint; light pass: carried f(x0) + difference).  One
+// routine for jet_decide and for the early publication (jet_fast_publish): the two must agree bit for bit.
+struct JetJudge {
+    double x0, fx0, ylev, prior_rest, logu, prior_x0, fmag, llc;
+    bool light;
+};
+__device__ __forceinline__ void jet_verdict(const Dev &d, const double (&m)[NV], const double *cst, const JetJudge &q, double v, double pv,
+                                            bool &in, bool &out, double &fnew) {
+    double B;
+    const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -q.x0), q.fmag, B, q.light, d.jet_ce);
+    B = B * d.jet_bscale + 8.0 * JET_EPS * (q.fmag + fabs(dl));        // + the roundings of the sums formed below
+    if (q.light) {
+        const double t = dl + (pv - q.prior_x0);
+        fnew = q.fx0 + t;
+        in = q.logu + B < t;
+        out = t + B <= q.logu;
+    } else {
+        // same expression order as the exact path: (ll + ll_const) + (prior_rest + prior(v)), monotone in ll
+        const double ll = m[0] + dl;
+        const double pr = q.prior_rest + pv;
+        const double flo = ((ll - B) + q.llc) + pr, fhi = ((ll + B) + q.llc) + pr;
+        fnew = (ll + q.llc) + pr;
+        in = q.ylev < flo;
+        out = fhi <= q.ylev;
+    }
+}
+
 __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainState &s, Ctl &ct, const double (&m)[NV], bool light,
                                           double x0, double shat_j, const double *cst, const JetPre *pre,
                                           double &x1_out, double &shat_out, long long &tick) {
@@ -1551,27 +1552,8 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     s.openL = sc.openL; s.openR = sc.openR; s.Jb = sc.Jb; s.Kb = sc.Kb;
     s.phase = (s.openL || s.openR) ? PH_STEPOUT : PH_SHRINK;
     const double logu = sc.logu, prior_x0 = sc.prior_x0;
-    const double bscale = d.jet_bscale;
-    // verdict on candidate v with log-prior pv; fnew: the log-potential at v (full: enclosure midpoint; light: carried f(x0) + difference)
-    auto verdict = [&](double v, double pv, bool &in, bool &out, double &fnew) {
-        double B;
-        const double dl = jet_eval(d.family, m, cst, d.n_total, d.inv_sd, __dadd_rn(v, -s.x0), fmag, B, light, d.jet_ce);
-        B = B * bscale + 8.0 * JET_EPS * (fmag + fabs(dl));        // + the roundings of the sums formed below
-        if (light) {
-            const double t = dl + (pv - prior_x0);
-            fnew = s.fx0 + t;
-            in = logu + B < t;
-            out = t + B <= logu;
-        } else {
-            // same expression order as the exact path: (ll + ll_const) + (prior_rest + prior(v)), monotone in ll
-            const double ll = m[0] + dl;
-            const double pr = s.prior_rest + pv;
-            const double flo = ((ll - B) + llc) + pr, fhi = ((ll + B) + llc) + pr;
-            fnew = (ll + llc) + pr;
-            in = s.ylev < flo;
-            out = fhi <= s.ylev;
-        }
-    };
+    const JetJudge judge{s.x0, s.fx0, s.ylev, s.prior_rest, logu, prior_x0, fmag, llc, light};
+    auto verdict = [&](double v, double pv, bool &in, bool &out, double &fnew) { jet_verdict(d, m, cst, judge, v, pv, in, out, fnew); };
     // consume stepping-out verdicts of one side, in sequence; false: a test was not certain (the state is exact up to it)
     auto consume = [&](unsigned vin, unsigned vout, int ntests, bool left, bool &expanded) -> bool {
         for (int t = 0; t < ntests && (left ? s.openL : s.openR); ++t) {
@@ -1667,6 +1649,62 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     return JET_ACCEPTED;
 }
 
+// EARLY PUBLICATION (persistent driver).  What the workers need to start a chain's next pass is four words of its control
+// block -- next column, pending column, its delta, the column scale -- and in the steady state all of them follow from
+// the ROUND-1 verdicts alone: no stepping-out expansion, the first proposal that is not certainly rejected is certainly
+// accepted, and the update is neither the last of an iteration nor otherwise special.  The deciding warp therefore judges
+// round 1 straight from its shared-memory cache (the sums, the points prepared while the pass was streaming, five scalars
+// of the chain state), writes those four words and releases the chain's version -- ~2 us after the sums arrived -- and
+// only THEN runs the complete decision (decide_chain below: state machine, counters, beta / sample stores, next
+// prefetch), which used to sit on the chain's critical cycle with its ~10 us of dependent shared / local memory traffic.
+// The complete decision must arrive at the same block: it re-derives it independently and the caller compares (a mismatch
+// aborts the run).  Returns false -- nothing written -- whenever anything is not the plain case.
+__device__ __forceinline__ bool jet_fast_publish(const Dev &d, int c, int lane, const DeciderCache *dc, const double (&m)[NV], bool light,
+                                                 unsigned long long ver) {
+    const JetPre *pre = &dc->pre;
+    const int j = dc->s.j;
+    if (!(dc->pref_j == j && dc->ct.j == j && pre->valid && pre->sc.j == j && pre->sc.cursor == dc->s.cursor && pre->sc.x0 == dc->beta_j)) return false;
+    if (dc->s.status != CGG_OK || dc->s.jet_skip || !d.jet) return false;
+    if ((int64_t)j + 1 >= d.p) return false;                 // the iteration ends with this update (flush, prior re-sum, ...)
+    if (pre->sc.nAvail < 64) return false;                   // a replayed stream that is running out
+    JetJudge q;
+    q.light = light; q.x0 = dc->beta_j; q.logu = pre->sc.logu; q.prior_x0 = pre->sc.prior_x0;
+    q.llc = d.sharded ? 0.0 : d.ll_const;
+    if (light) { q.fx0 = dc->s.fx0; q.fmag = fabs(q.fx0) + 1.0; q.ylev = 0.0; q.prior_rest = 0.0; }
+    else {
+        if (!(fabs(m[0]) < INFINITY)) return false;
+        if (d.family != CGG_GAUSSIAN && m[9] != 0.0) return false;
+        q.fx0 = (m[0] + q.llc) + dc->s.prior_sum;            // exactly jet_decide's expressions
+        q.fmag = fabs(m[0]);
+        q.prior_rest = dc->s.prior_sum - pre->sc.prior_x0;
+        q.ylev = __dadd_rn(pre->sc.logu, q.fx0);
+    }
+    const bool openL = pre->sc.openL != 0, openR = pre->sc.openR != 0;
+    const double x = pre->x[lane];
+    bool in = false, out = false; double fm = 0.0;
+    if ((lane < JET_R1_SO) ? openL : ((lane < 2 * JET_R1_SO) ? openR : true)) jet_verdict(d, m, dc->cst, q, x, pre->pr[lane], in, out, fm);
+    const unsigned vin = __ballot_sync(0xffffffffu, in), vout = __ballot_sync(0xffffffffu, out);
+    if (openL && !(vout & 1u)) return false;                                 // f(L0) is not certainly below the level: expansion, or undecided
+    if (openR && !((vout >> JET_R1_SO) & 1u)) return false;
+    const unsigned pmask = (1u << JET_R1_PROP) - 1u;
+    const unsigned pout = (vout >> (2 * JET_R1_SO)) & pmask, pin = (vin >> (2 * JET_R1_SO)) & pmask;
+    if (pout == pmask) return false;
+    const int k = __ffs(~pout) - 1;
+    if (!((pin >> k) & 1u)) return false;
+    const double x1 = __shfl_sync(0xffffffffu, x, k + 2 * JET_R1_SO);
+    if (lane == 0) {
+        const bool full_next = !d.jet_light || d.family != CGG_BINOMIAL;
+        Ctl *g = d.ctl + c;
+        const int4 head = make_int4(j + 1, 0, j, (int)(JET_BIT | (full_next ? JET_FULL : 0u)));      // j, ncand, commit_j, coarse_mask
+        *reinterpret_cast<int4 *>(g) = head;
+        g->commit_delta = __dadd_rn(x1, -q.x0);
+        g->cscale = dc->cscale_n;
+        st_release_u64(&d.sync[c].version, ver + 1ULL);
+    }
+    __syncwarp();
+    return true;
+}
+
 // Row-sharded persistent driver: the ranks' totals of a pass, exchanged through peer-mapped mailboxes and added in RANK
 // ORDER, so that every rank decides from bit-identical sums.  Each value travels as two self-validating 64-bit words
 // {stamp32 : half32} (cf. LimbAcc: a 64-bit element of a vector access cannot be torn), written straight into every
@@ -1756,9 +1794,9 @@ __device__ __forceinline__ double xbuf_value(const Dev &d, int idx) {
     return v;
 }
 // vals_in (with SRC_SLOTS): the pass's sums are handed over by the caller (cluster driver) instead of read from the limbs.
-enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2, DEC_ABORT = 3 };
+enum DecideOutcome : int { DEC_CONTINUE = 0, DEC_FINISHED = 1, DEC_NOT_READY = 2, DEC_ABORT = 3, DEC_PUBLISHED = 4 /* continue; the version is already released */ };
 __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_hint, int src, DeciderCache *dc = nullptr,
-                                         const double *vals_in = nullptr, unsigned pass_no = 0) {
+                                         const double *vals_in = nullptr, unsigned pass_no = 0, unsigned long long ver = ~0ULL) {
     const bool from_xbuf = src == SRC_XBUF;
     const Dev &d = *dp;
     // ---- control block, state, beta/shat of j and j+1: from the deciding warp's shared-memory cache if it has them,
@@ -1804,6 +1842,10 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (jetpass && d.family == CGG_BINOMIAL && ((unsigned)ct.coarse_mask & JET_FULL) == 0u) jet_light_unpack(jm);
     if (s.x0 != s.x0) tick = 0;   // (keeps the state loads above the first timestamp)
     CGG_TICK(12);      // state loaded, sums read
+    // ---- the plain case: publish the next pass from the round-1 verdicts now, do the book-keeping afterwards
+    bool published = false;
+    if (jetpass && src == SRC_SLOTS && cached && !vals_in && ver != ~0ULL && d.early)
+        published = jet_fast_publish(d, c, lane, dc, jm, ((unsigned)ct.coarse_mask & JET_FULL) == 0u, ver);
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
     unsigned int aflags = 0;
@@ -1920,7 +1962,12 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         // the deciding warp of the persistent driver keeps the state in shared memory; global memory gets it when the
         // chain stops (the host reads it after the kernel) -- every decision otherwise
         if (!dc || fin) d.cs[c] = s;
-        d.ctl[c] = ct;
+        if (!published) d.ctl[c] = ct;
+        else if (fin || ct.j != s.j || ct.ncand != 0 || ct.commit_j != jq || ct.commit_delta != __ldcg(&d.ctl[c].commit_delta) ||
+                 ct.coarse_mask != __ldcg(&d.ctl[c].coarse_mask) || ct.j != __ldcg(&d.ctl[c].j) || ct.cscale != __ldcg(&d.ctl[c].cscale)) {
+            d.hdr->abort = 1;      // the early publication and the complete decision disagree: must never happen; fail loudly
+            fence_gpu();
+        }
         if (dc) { dc->s = s; dc->ct = ct; dc->valid = 1; }
     }
     fin = __shfl_sync(0xffffffffu, (int)fin, 0);
@@ -1930,7 +1977,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (!(src == SRC_SLOTS && cmask == 0u)) fence_gpu();
     __syncwarp();
     CGG_TICK(19);      // fence
-    return fin ? DEC_FINISHED : DEC_CONTINUE;
+    return fin ? DEC_FINISHED : (published ? DEC_PUBLISHED : DEC_CONTINUE);
 }
 
 }  // namespace cgg

@@ -61,17 +61,11 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             all_fin = false;
             const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
             const long long td0 = d.prof ? clock64() : 0;
-            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c, nullptr, (unsigned)v);     // reads the limb accumulators itself: one load per lane
+            const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c, nullptr, (unsigned)v, v);  // reads the limb accumulators itself: one load per lane
             if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
             if (oc == DEC_ABORT) { if (lane == 0) { d.hdr->abort = 1; fence_gpu(); } return; }   // a peer rank never delivered
             const bool fin = oc == DEC_FINISHED;
-#ifdef CGG_DEBUG_GROUP
-            if (lane == 0) {
-                const unsigned long long cur = __ldcg(&d.sync[c].version);
-                if (cur != v) printf("[group dbg] DECIDER chain %d: version was %llu when the pass was taken up, now 0x%llx (arrive word 0x%llx)\n", c, v, cur, (unsigned long long)__ldcg(&d.sync[c].arrive));
-            }
-#endif
-            if (lane == 0) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
+            if (lane == 0 && oc != DEC_PUBLISHED) st_release_u64(&d.sync[c].version, fin ? VERSION_FINISHED : v + 1);
             if (!fin) {                                              // after publishing: off the chain's critical path
                 decider_prefetch(d, c, cache + c, lane);
                 decider_prephase(d, c, cache + c, lane);
@@ -87,15 +81,6 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
         else {
             __nanosleep(40);
             if ((++idle & 255u) == 0 && wait_timed_out(d, t0, lane)) {
-#ifdef CGG_DEBUG_GROUP
-                for (int c = first_chain; c < d.C; c += stride)
-                    if (lane == 0) {
-                        const unsigned long long w0 = __ldcg(&d.lacc[(size_t)c * NV].w[0]), w1 = __ldcg(&d.lacc[(size_t)c * NV + 1].w[0]), w4 = __ldcg(&d.lacc[(size_t)c * NV + 4].w[0]);
-                        printf("[group dbg] decider chain %d version %llu | arrivals (mod 256) value 0: %d (prev %d), value 1: %d (prev %d), value 4: %d (prev %d) | ctl j %d cj %d mask %x\n", c,
-                               (unsigned long long)__ldcg(&d.sync[c].version), (int)(w0 >> 56), (int)(cache[c].prev[0] >> 56), (int)(w1 >> 56), (int)(cache[c].prev[4] >> 56),
-                               (int)(w4 >> 56), (int)(cache[c].prev[16] >> 56), cache[c].ct.j, cache[c].ct.commit_j, (unsigned)cache[c].ct.coarse_mask);
-                    }
-#endif
                 break;
             }
         }
@@ -132,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     // into shared memory; the other warps only watch shared memory.  Returns false if the wait timed out.
     auto wait_decision = [&](int c, unsigned long long round) -> bool {
         volatile unsigned long long *sv = &sh.ver[c];
-        if (ver_bcast(&sh.ver[c], lane) < round) {
+        if (ver_below(&sh.ver[c], round, lane)) {
             ++n_slow;
             const unsigned long long t0 = globaltimer_ns();
             unsigned spins = 0;
@@ -144,26 +129,17 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     unsigned long long v = 0;
                     if (lane == 0) v = ld_acquire_u64(&d.sync[c].version);
                     v = __shfl_sync(0xffffffffu, v, 0);
-#ifdef CGG_DEBUG_GROUP
-                    if (lane == 0 && (c < 0 || c >= d.C || (v > round + 2 && v != (1ULL << 62))))
-                        printf("[group dbg] wait_decision cta %d warp %d: chain %d round %llu v %llu sv %llu\n", (int)blockIdx.x, warp, c, round, v, (unsigned long long)*sv);
-#endif
                     if (v < round) ++n_notready;
-                    if (v >= round && v > ver_bcast(&sh.ver[c], lane)) {
+                    if (__any_sync(0xffffffffu, lane == 0 && v >= round && v > ver_read(&sh.ver[c]))) {
                         if (lane < CTL_WORDS) sh.ctl[c * CTL_WORDS + lane] = __ldcg(reinterpret_cast<const double *>(d.ctl + c) + lane);
                         __syncwarp();
                         if (lane == 0) { __threadfence_block(); *sv = v; }
                     }
                     if (lane == 0) { __threadfence_block(); atomicExch_block(&sh.lock[c], 0); }
                 }
-                if (ver_bcast(&sh.ver[c], lane) >= round) break;
+                if (!ver_below(&sh.ver[c], round, lane)) break;
                 __nanosleep(spins < 8 ? 64 : 256);
                 if ((++spins & 63u) == 0 && wait_timed_out(d, t0, lane)) {
-#ifdef CGG_DEBUG_GROUP
-                    if (lane == 0 && warp < 2 && blockIdx.x < 3)
-                        printf("[group dbg] worker cta %d warp %d waits for chain %d round %llu: shared ver %llu, global ver %llu | ctl j %d cj %d\n", (int)blockIdx.x, warp, c, round,
-                               (unsigned long long)*sv, (unsigned long long)__ldcg(&d.sync[c].version), __ldcg(&d.ctl[c].j), __ldcg(&d.ctl[c].commit_j));
-#endif
                     return false;
                 }
             }
@@ -171,29 +147,24 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
         __syncwarp();
         return true;
     };
+#ifdef CGG_GROUP_PASSES
     double accg[4][NV];
-#ifdef CGG_DEBUG_GROUP
-    unsigned long long dbg_last[CMAX];
-    bool dbg_seen = false; int dbg_action = 0;
-    for (int i = 0; i < CMAX; ++i) dbg_last[i] = ~0ULL;
-    auto dbg_deliver = [&](int cc_, unsigned long long round_, int path, int nvals) {
-        const unsigned long long sv = *(volatile unsigned long long *)&sh.ver[cc_], gv = sv;
-        const unsigned long long want = dbg_last[cc_] + 1ULL;      // ~0 + 1 = 0: the first delivery is round 0
-        if (lane == 0 && (round_ != want || sv != round_ || (nvals < 2 && round_ >= 1 && round_ <= 4)))
-            printf("[group dbg] DELIVERY cta %d warp %d chain %d round %llu path %d nvals %d: last delivered %lld, global ver %llu, shared ver %llu\n",
-                   (int)blockIdx.x, warp, cc_, round_, path, nvals, (long long)dbg_last[cc_], gv, sv);
-        dbg_last[cc_] = round_;
-    };
-#endif
     double (&acc)[NV] = accg[0];
     double (&acc2)[NV] = accg[1];
+#else
+    double acc[NV], acc2[NV];
+#endif
     bool pair_prefetched = false;
-    int pf_j = -1, pf_cj = -1, pf_g = 0; bool pf_full = false, pf_pred = false;      // what the pair / group prologue issued ahead of time was issued for
+    int pf_j = -1, pf_cj = -1, pf_g = 0; bool pf_full = false;      // what the pair / group prologue issued ahead of time was issued for
     ColCache cc;        // this warp's X-column cache (pair and group passes); lives for the launch
     cc.cap = d.colcache; cc.base = sh.cache0 + (uint32_t)warp * (uint32_t)(2 * d.colcache) * 512u + (uint32_t)lane * 16u;
     cc.tag0 = cc.tag1 = -1; cc.fill_col = cc.fill_slot = -1;
     // group passes (four chains per walk): the steady-state kinds of pass only (binomial light passes, gaussian)
+#ifdef CGG_GROUP_PASSES
     constexpr bool GROUP_FAMILY = FAMILY == CGG_BINOMIAL || FAMILY == CGG_GAUSSIAN;
+#else
+    constexpr bool GROUP_FAMILY = false;      // (group passes are an experiment: build with -DCGG_GROUP_PASSES)
+#endif
     int n_group = 0;
     for (unsigned long long round = 0;; ++round) {
         bool any = false;
@@ -202,15 +173,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             if (prof && lane == 0 && round >= 1 && round <= 128) {
                 if (blockIdx.x == 20 && warp == 0) d.prof[32 + 4096 + 32 * 128 * 4 + 2 * 1024 * 32 + (c * 128 + (round - 1))] = globaltimer_ns();
             }
-#ifdef CGG_DEBUG_GROUP
-            for (int q = 0; q < d.C; ++q) {
-                const unsigned long long vq = *(volatile unsigned long long *)&sh.ver[q];
-                if (lane == 0 && vq > round + 2 && vq != (1ULL << 62) && !dbg_seen) {
-                    dbg_seen = true;
-                    printf("[group dbg] CANARY cta %d warp %d at round %llu item %d: shared ver[%d] = %llu (0x%llx); last action %d\n", (int)blockIdx.x, warp, round, c, q, vq, vq, dbg_action);
-                }
-            }
-#endif
             if (!wait_decision(c, round)) return;
             // ---- chains 2k and 2k + 1 at the same coordinate share one walk over the rows (pair pass)
             bool pair = false;
@@ -218,18 +180,18 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 ((unsigned)(__double_as_longlong(sh.ctl[c * CTL_WORDS + 1]) >> 32) & JET_BIT)) {     // only a jet pass can be shared
                 if (!wait_decision(c + 1, round)) return;
                 // the shared control blocks must be exactly the ones of this round (a finished chain's never are)
-                pair = ver_bcast(&sh.ver[c], lane) == round && ver_bcast(&sh.ver[c + 1], lane) == round &&
+                pair = ver_is(&sh.ver[c], round, lane) && ver_is(&sh.ver[c + 1], round, lane) &&
                        pair_batchable(sh.ctl + c * CTL_WORDS, sh.ctl + (c + 1) * CTL_WORDS);
             }
             // ---- ... and chains 4k .. 4k + 3 (group pass) when all four say the same and the X-column cache serves the walk
             int g = pair ? 2 : 1;
-            if (GROUP_FAMILY && pair && d.quad && !(c & 3) && c + 3 < d.C && cc.cap > 0) {
+            if constexpr (GROUP_FAMILY) if (pair && d.quad && !(c & 3) && c + 3 < d.C && cc.cap > 0) {
                 const double *cw = sh.ctl + c * CTL_WORDS;
                 const long long w1 = __double_as_longlong(cw[1]);
                 const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
                 if (FAMILY != CGG_BINOMIAL || !full) {
                     if (!wait_decision(c + 2, round) || !wait_decision(c + 3, round)) return;
-                    if (ver_bcast(&sh.ver[c + 2], lane) == round && ver_bcast(&sh.ver[c + 3], lane) == round &&
+                    if (ver_is(&sh.ver[c + 2], round, lane) && ver_is(&sh.ver[c + 3], round, lane) &&
                         pair_batchable(cw, cw + 2 * CTL_WORDS) && pair_batchable(cw, cw + 3 * CTL_WORDS) &&
                         group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) g = 4;
                 }
@@ -240,7 +202,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 // the first tiles of this pass were requested ahead of time, possibly from a PREDICTED control block (same kind of
                 // pass, next column): they are only good if the real block says the same
                 bool good = g >= 2 && g == pf_g;
-                if (pf_g == 4 && pf_pred && (d.quad & 16)) good = false;       // (diagnostic: never use tiles requested from a prediction)
                 if (good) {
                     const double *cwA = sh.ctl + c * CTL_WORDS;
                     const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
@@ -250,6 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 if (!good) { cp_async_wait<0>(); pair_prefetched = false; ++n_notready; }
             }
             if (pair && prefetched) { cp_async_wait<0>(); prefetched = false; }               // a single-pass prefetch of chain c: other ring layout
+#ifdef CGG_GROUP_PASSES
             if constexpr (GROUP_FAMILY) if (g == 4) {
                 const double *cw0 = sh.ctl + c * CTL_WORDS;
                 constexpr bool GFULL = FAMILY != CGG_BINOMIAL;          // (binomial: light passes only, see above)
@@ -266,8 +228,7 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     }
                 };
                 auto after = [&]() {
-                    if (c2 < 0 || (d.quad & 2)) return;
-                    pf_pred = false;
+                    if (c2 < 0) return;
                     double pred[2];
                     const double *nA = sh.ctl + c2 * CTL_WORDS;
                     const bool l0 = pair_lookahead(d, sh, c2, nround, lane);
@@ -275,10 +236,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     if (l1) {
                         if (!(pair_batchable(nA, nA + CTL_WORDS) && pair_batchable(nA, nA + 2 * CTL_WORDS) && pair_batchable(nA, nA + 3 * CTL_WORDS))) return;
                     } else if (!l0) {
-                        if (d.quad & 4) return;
-                        if ((d.quad & 32) && c2 == 0) return;       // (diagnostic: no prediction across rounds)
-                        if ((d.quad & 64) && c2 != 0) return;       // (diagnostic: no prediction inside a round)
-                        pf_pred = true;
                         // not published yet: predict the pass (same kind, next column, committing the column just sampled), as the
                         // pair passes do; the real blocks are compared with the prediction before the tiles are used
                         // (the block may be rewritten by another warp of the CTA at any moment: one lane reads it for the warp)
@@ -290,37 +247,30 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                         pred[0] = __longlong_as_double((long long)(unsigned)jn);
                         pred[1] = __longlong_as_double(((long long)mk << 32) | (long long)(unsigned)jp);
                         nA = pred;
-                    } else if (d.quad & 8) return;                              // (l0 only: chain c2's real block stands for the group)
+                    }                                                           // (l0 only: chain c2's real block stands for the group)
                     const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
                     const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
                     if (!(((unsigned)(w1 >> 32)) & JET_BIT) || (int)(w0 & 0xffffffffLL) < 0 || full2 != GFULL) return;
                     if (!group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) return;
                     pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2; pf_g = 4;
-                    if (pf_pred && (d.quad & 256)) { pf_g = 99; pair_prefetched = true; return; }      // (diagnostic: bookkeeping only)
                     GroupStream<4> ns(d, c2, nA, wid, W, lane, ring, cc, FAMILY != CGG_BINOMIAL || full2);
-                    if (pf_pred && (d.quad & 128)) { pf_g = 99; pair_prefetched = true; return; }      // (diagnostic: no loads)
                     ns.prologue(false);
                     pair_prefetched = true;
                 };
                 warp_pass_group<FAMILY, GFULL, 4>(d, c, cw0, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, accg);
-#ifdef CGG_DEBUG_GROUP
-                dbg_action = 400 + c * 10 + (was_pref ? 1 : 0) + (pair_prefetched ? 2 : 0) + (pf_pred ? 4 : 0);
-#endif
                 any = true;
                 ++n_group;
                 n_pref += pair_prefetched ? 1 : 0;
                 long long tC = prof ? clock64() : 0;
                 t_rows += tC - tB; t_tiles += tC - tB;
                 const int nvd = jet_nvals(FAMILY, !GFULL);
-#ifdef CGG_DEBUG_GROUP
-                for (int k = 0; k < 4; ++k) dbg_deliver(c + k, round, 4, nvd);
-#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k) cta_deliver_limbs(d, sh, c + k, nvd, warp, lane, nworkers, accg[k]);
                 if (prof) t_arrive += clock64() - tC;
                 c += 3;
                 continue;
             }
+#endif
             if (pair) {
                 const double *cwA = sh.ctl + c * CTL_WORDS, *cwB = cwA + CTL_WORDS;
                 const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(__double_as_longlong(cwA[1]) >> 32)) & JET_FULL);
@@ -370,9 +320,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                     ns.prologue(false);
                     pair_prefetched = true;
                 };
-#ifdef CGG_DEBUG_GROUP
-                dbg_action = 200 + c * 10 + (was_pref ? 1 : 0);
-#endif
                 if (full) warp_pass_jet2<FAMILY, true>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
                 else warp_pass_jet2<FAMILY, false>(d, c, cwA, cwB, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, acc, acc2);
                 any = true;
@@ -380,9 +327,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 long long tC = prof ? clock64() : 0;
                 t_rows += tC - tB; t_tiles += tC - tB;
                 const int nvd = jet_nvals(FAMILY, !full);
-#ifdef CGG_DEBUG_GROUP
-                dbg_deliver(c, round, 2, nvd); dbg_deliver(c + 1, round, 2, nvd);
-#endif
                 cta_deliver_limbs(d, sh, c, nvd, warp, lane, nworkers, acc);
                 cta_deliver_limbs(d, sh, c + 1, nvd, warp, lane, nworkers, acc2);
                 if (prof) t_arrive += clock64() - tC;
@@ -403,9 +347,6 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
             long long tC = prof ? clock64() : 0;
             t_rows += tC - tB;
             // ---- CTA-level then grid-level arrival
-#ifdef CGG_DEBUG_GROUP
-            dbg_deliver(c, round, 1, nc);
-#endif
             cta_deliver_limbs(d, sh, c, nc, warp, lane, nworkers, acc);
             if (prof && lane == 0 && round == 60 && c == 0)
                 d.prof[32 + 4096 + 32 * 128 * 4 + (blockIdx.x * NWARPS + warp) * 2 + 1] = globaltimer_ns();
@@ -1177,10 +1118,18 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (G < 1) G = 1;
     d.G = (int)G;
     if (d.colcache && (int64_t)d.colcache * (int64_t)d.G * NWARPS < d.n_tiles) d.colcache = 0;    // (fewer CTAs than assumed: a warp's tiles would not fit)
-    {   // group passes (chains 4k .. 4k + 3 share a walk): from 8 chains on, so that a group's decisions still hide behind another
-        // group's pass; they need pair passes and the X-column cache.  CGG_QUAD=0/1 overrides (experiments, tests)
+    {   // early publication of the next pass by the deciding warps (cgg_device.cuh: jet_fast_publish): on by default where a
+        // chain's decision cannot hide behind other chains' passes -- one or two chains per device, i.e. the row-sharded runs
+        // (measured: one chain +8 %, cfg5's shard +11 %; 8 chains: no difference; 4 chains on the grid-wide kernel: -4 %, the
+        // deciding warp is busier).  CGG_EARLY=0/1 overrides.  Never changes results.
+        const char *e6 = getenv("CGG_EARLY");
+        d.early = (e6 ? atoi(e6) != 0 : C <= 2) ? 1 : 0;
+    }
+    {   // group passes (chains 4k .. 4k + 3 share a walk): an experiment, compiled in with -DCGG_GROUP_PASSES only;
+        // then on from 12 chains (three groups, so that a group's decisions still hide behind other groups' passes); they need
+        // pair passes and the X-column cache.  CGG_QUAD=0/1 overrides.
         const char *e5 = getenv("CGG_QUAD");
-        d.quad = ((e5 ? atoi(e5) != 0 : C >= 8) && d.pair && d.colcache > 0) ? (e5 && atoi(e5) > 1 ? atoi(e5) : 1) : 0;      // (bit 1: no look-ahead prefetch between groups, a diagnostic)
+        d.quad = ((e5 ? atoi(e5) != 0 : C >= 12) && d.pair && d.colcache > 0) ? 1 : 0;
     }
     d.lde = (d.n + 31) / 32 * 32;
     {   // small n: one cluster per chain instead of the grid-wide protocol

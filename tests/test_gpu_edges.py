@@ -1,6 +1,7 @@
 """Edge cases of the product path (jet passes + exact passes through the persistent driver) against the oracle:
 ragged and tiny row counts, a single column, more chains than deciding warps, degenerate and badly scaled columns,
 extreme slice widths.  Every case also has to equal the all-exact engine bit for bit."""
+import os
 import numpy as np
 import pytest
 import oracle
@@ -161,8 +162,9 @@ def test_pair_single_handover_stress_keeps_eta_ownership(monkeypatch):
 
 @pytest.mark.parametrize("family,n", [("binomial", 150_001), ("gaussian", 150_001), ("binomial", 300_032)])
 def test_group_passes_change_nothing(monkeypatch, family, n):
-    """Group passes (four chains per walk over the rows, X-column cache required) are scheduling only: same samples, same
-    counts as pair passes and as one chain per pass; chain 0 also equals the oracle.  n odd (scalar tail row) and n a
+    """Scheduling switches are scheduling only -- pair passes, the chunking of launches, the early publication of the next
+    pass (CGG_EARLY) and, in builds with -DCGG_GROUP_PASSES, group passes (four chains per walk, CGG_QUAD): same samples, same
+    counts as one chain per pass with none of them; chain 0 also equals the oracle.  n odd (scalar tail row) and n a
     multiple of the tile size; 12 chains = two groups of four that look ahead at each other + ... a third one; the chains
     start at different points, so early iterations mix exact-pass hand-overs, pair passes and group passes."""
     p, C, iters = 5, 12, 11
@@ -173,6 +175,7 @@ def test_group_passes_change_nothing(monkeypatch, family, n):
     def run(pair, quad, chunk=8):
         monkeypatch.setenv("CGG_PAIR", str(pair))
         monkeypatch.setenv("CGG_QUAD", str(quad))
+        monkeypatch.setenv("CGG_EARLY", str(quad))
         monkeypatch.setenv("CGG_CHUNK", str(chunk))
         monkeypatch.setenv("CGG_SMALLN", "0")
         return _chains(family, "laplace", X, y, beta0, iters, U, w=0.5, driver="grid")
@@ -183,9 +186,9 @@ def test_group_passes_change_nothing(monkeypatch, family, n):
         assert np.array_equal(S, S0), (pair, quad, chunk)
         for k in ("uniforms_used", "ref_evals", "stepouts", "shrinks", "updates"):
             assert st[k] == st0[k], (pair, quad, chunk, k)
-        if quad:
+        if quad and os.environ.get("CGG_TEST_GROUP"):        # (a library built with -DCGG_GROUP_PASSES: the experiment of DESIGN.md 5)
             assert st["group_passes"] > iters * p, st["group_passes"]      # most walks of worker warp 0 served four chains
-        else:
+        elif not quad:
             assert st["group_passes"] == 0
     m = oracle.make_model(family, sd=1.0, **PRIOR_CASES["laplace"])
     ref = oracle.run_chain(m, X, y, beta0[0], w=0.5, n_iter=iters, max_steps=-1, replay_u=U[0])
