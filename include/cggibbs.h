@@ -16,8 +16,11 @@
  *   - a handle is not re-entrant; all calls block until their results are in the output buffers.
  *   - environment switches read by the library (experiments and tests only; none of them can change a result):
  *     CGG_PAIR=0|1 (pair passes off/on; default on from 4 chains), CGG_CHUNK=<iterations per launch when pair passes
- *     are on; default 8>, CGG_COARSE_THETA=<fp32 pre-filter policy>, CGG_PROFILE[_TRACE|_CTAS|_WARPS]=1 (phase counters
- *     of the persistent kernel on stderr).
+ *     are on; default 8>, CGG_COLCACHE=0|1 (per-warp X-column cache of the pair passes), CGG_EARLY=0|1 (the plain update
+ *     judged, published and booked straight from the deciding warp's cache; default on), CGG_SMALLN=0|1 (cluster driver
+ *     for n <= 2^18), CGG_L2_PERSIST=0|1, CGG_QUAD=0|1 (group passes, only in builds with -DCGG_GROUP_PASSES),
+ *     CGG_COARSE_THETA=<fp32 pre-filter policy>, CGG_PROFILE[_TRACE|_CTAS|_WARPS]=1 (phase counters of the persistent
+ *     kernel on stderr), CGG_DEBUG_PTRS=1 (device addresses of the handle's buffers on stderr).
  *   - there is NO CPU fallback: unsupported family/link/prior/sampler => CGG_E_UNSUPPORTED,
  *     no usable CUDA device => CGG_E_CUDA.
  */
@@ -124,7 +127,8 @@ typedef struct cgg_stats {
     uint64_t jet_passes;     /* (chain, pass) pairs that were jet passes (subset of chain_passes) */
     uint64_t jet_fallbacks;  /* updates a jet pass could not finish: exact passes took over from that point */
     uint64_t jet_retries;    /* light jet passes (binomial) that were repeated as full jet passes */
-    uint64_t group_passes;   /* walks over the rows that served FOUR chains at once (persistent driver; counted by one worker warp; cgg_run only) */
+    uint64_t group_passes;   /* walks over the rows that served FOUR chains at once, counted by one worker warp (cgg_run of the persistent
+                              * driver; always 0 unless the library was built with -DCGG_GROUP_PASSES) */
 } cgg_stats;
 
 typedef struct cgg_handle cgg_handle;

@@ -1649,18 +1649,22 @@ __device__ __forceinline__ int jet_decide(const Dev &d, int c, int lane, ChainSt
     return JET_ACCEPTED;
 }
 
-// EARLY PUBLICATION (persistent driver).  What the workers need to start a chain's next pass is four words of its control
-// block -- next column, pending column, its delta, the column scale -- and in the steady state all of them follow from
-// the ROUND-1 verdicts alone: no stepping-out expansion, the first proposal that is not certainly rejected is certainly
-// accepted, and the update is neither the last of an iteration nor otherwise special.  The deciding warp therefore judges
-// round 1 straight from its shared-memory cache (the sums, the points prepared while the pass was streaming, five scalars
-// of the chain state), writes those four words and releases the chain's version -- ~2 us after the sums arrived -- and
-// only THEN runs the complete decision (decide_chain below: state machine, counters, beta / sample stores, next
-// prefetch), which used to sit on the chain's critical cycle with its ~10 us of dependent shared / local memory traffic.
-// The complete decision must arrive at the same block: it re-derives it independently and the caller compares (a mismatch
-// aborts the run).  Returns false -- nothing written -- whenever anything is not the plain case.
-__device__ __forceinline__ bool jet_fast_publish(const Dev &d, int c, int lane, const DeciderCache *dc, const double (&m)[NV], bool light,
-                                                 unsigned long long ver) {
+// THE PLAIN UPDATE, decided and booked without the general machinery.  In the steady state an update is: no stepping-out
+// expansion, and the first shrink proposal that is not certainly rejected is certainly accepted -- all of it visible in the
+// ROUND-1 verdicts, whose points were prepared while the pass was streaming.  For that case (and only when nothing else
+// is special: not the last column of an iteration, no clamp-risk rows, the whole replay window available) the deciding
+// warp works straight on its shared-memory cache:
+//   1. judges round 1 (jet_verdict: the same routine, hence the same verdicts, as jet_decide);
+//   2. persistent driver: writes the four control words the workers need -- next column, pending column, its delta, the
+//      column scale -- and releases the chain's version, ~2 us after the sums arrived (`ver` != ~0);
+//   3. books the update: exactly the state changes, counters and global stores (beta, slice-width estimate, sample) that
+//      decide_chain / jet_decide / accept_value make for this case, field by field, without copying the 300-byte chain state
+//      into registers and back (the general path spends ~20k cycles per decision, most of it such traffic).
+// Returns false -- nothing changed -- whenever the update is not of the plain kind; the general path then runs as ever.
+// CGG_EARLY=0 turns this off; every parity test compares chains with it (the default) against the oracle, and the
+// all-exact engine, the counters included.
+__device__ __forceinline__ bool jet_fast_update(const Dev &d, int c, int lane, DeciderCache *dc, const double (&m)[NV], bool light,
+                                                unsigned long long ver) {
     const JetPre *pre = &dc->pre;
     const int j = dc->s.j;
     if (!(dc->pref_j == j && dc->ct.j == j && pre->valid && pre->sc.j == j && pre->sc.cursor == dc->s.cursor && pre->sc.x0 == dc->beta_j)) return false;
@@ -1670,15 +1674,15 @@ __device__ __forceinline__ bool jet_fast_publish(const Dev &d, int c, int lane, 
     JetJudge q;
     q.light = light; q.x0 = dc->beta_j; q.logu = pre->sc.logu; q.prior_x0 = pre->sc.prior_x0;
     q.llc = d.sharded ? 0.0 : d.ll_const;
-    if (light) { q.fx0 = dc->s.fx0; q.fmag = fabs(q.fx0) + 1.0; q.ylev = 0.0; q.prior_rest = 0.0; }
+    q.prior_rest = dc->s.prior_sum - pre->sc.prior_x0;       // exactly jet_decide's expressions
+    if (light) { q.fx0 = dc->s.fx0; q.fmag = fabs(q.fx0) + 1.0; }
     else {
         if (!(fabs(m[0]) < INFINITY)) return false;
         if (d.family != CGG_GAUSSIAN && m[9] != 0.0) return false;
-        q.fx0 = (m[0] + q.llc) + dc->s.prior_sum;            // exactly jet_decide's expressions
+        q.fx0 = (m[0] + q.llc) + dc->s.prior_sum;
         q.fmag = fabs(m[0]);
-        q.prior_rest = dc->s.prior_sum - pre->sc.prior_x0;
-        q.ylev = __dadd_rn(pre->sc.logu, q.fx0);
     }
+    q.ylev = __dadd_rn(pre->sc.logu, q.fx0);
     const bool openL = pre->sc.openL != 0, openR = pre->sc.openR != 0;
     const double x = pre->x[lane];
     bool in = false, out = false; double fm = 0.0;
@@ -1691,15 +1695,45 @@ __device__ __forceinline__ bool jet_fast_publish(const Dev &d, int c, int lane, 
     if (pout == pmask) return false;
     const int k = __ffs(~pout) - 1;
     if (!((pin >> k) & 1u)) return false;
-    const double x1 = __shfl_sync(0xffffffffu, x, k + 2 * JET_R1_SO);
+    const int src = k + 2 * JET_R1_SO;
+    const double x1 = __shfl_sync(0xffffffffu, x, src), f1 = __shfl_sync(0xffffffffu, fm, src);
+    const double lk = __shfl_sync(0xffffffffu, pre->l[lane], src), rk = __shfl_sync(0xffffffffu, pre->r[lane], src);     // the bracket proposal k was drawn from
     if (lane == 0) {
         const bool full_next = !d.jet_light || d.family != CGG_BINOMIAL;
-        Ctl *g = d.ctl + c;
-        const int4 head = make_int4(j + 1, 0, j, (int)(JET_BIT | (full_next ? JET_FULL : 0u)));      // j, ncand, commit_j, coarse_mask
-        *reinterpret_cast<int4 *>(g) = head;
-        g->commit_delta = __dadd_rn(x1, -q.x0);
-        g->cscale = dc->cscale_n;
-        st_release_u64(&d.sync[c].version, ver + 1ULL);
+        const int mask_next = (int)(JET_BIT | (full_next ? JET_FULL : 0u));
+        const double cdelta = __dadd_rn(x1, -q.x0);
+        if (ver != ~0ULL) {         // persistent driver: the workers may go on
+            Ctl *g = d.ctl + c;
+            *reinterpret_cast<int4 *>(g) = make_int4(j + 1, 0, j, mask_next);      // j, ncand, commit_j, coarse_mask
+            g->commit_delta = cdelta;
+            g->cscale = dc->cscale_n;
+            st_release_u64(&d.sync[c].version, ver + 1ULL);
+        }
+        // ---- the book-keeping of decide_chain / jet_decide / accept_value for this case
+        ChainState &S = dc->s;
+        Ctl &T = dc->ct;
+        S.passes++; S.jet_passes++;
+        if (T.commit_j >= 0) S.commit_passes++;
+        S.x0 = q.x0; S.prior_rest = q.prior_rest; S.sdrawn = 0; S.npass = 0;
+        S.ylev = q.ylev;
+        S.ref_evals += 1u + (openL ? 1u : 0u) + (openR ? 1u : 0u) + (unsigned)(k + 1);     // f(x0), the stepping-out tests, the proposals
+        S.shrinks += (unsigned)(k + 1);
+        S.openL = 0; S.openR = 0; S.Jb = pre->sc.Jb; S.Kb = pre->sc.Kb;
+        if (openL || openR) S.pexp = 0.9 * S.pexp;
+        S.L = lk; S.R = rk;
+        const double shat_j = dc->shat_j;
+        const double shat_out = (shat_j > 0.0) ? 0.75 * shat_j + 0.25 * (rk - lk) : (rk - lk);
+        const int64_t pj = (int64_t)c * d.p + j;
+        d.shat[pj] = shat_out;
+        d.beta[pj] = x1;                                        // R/mcmcglm.R:264
+        if (d.samples) d.samples[((int64_t)c * d.n_iter + S.iter) * d.p + j] = x1;  // :271
+        S.fx0 = f1;
+        S.prior_sum = q.prior_rest + prior_logdens(d.prior, x1);
+        S.cursor += base_draws(d) + k + 1;
+        S.updates++;
+        S.j = j + 1;
+        S.phase = PH_JET; S.chain_passes++;
+        T.j = j + 1; T.ncand = 0; T.commit_j = j; T.coarse_mask = mask_next; T.commit_delta = cdelta; T.cscale = dc->cscale_n;
     }
     __syncwarp();
     return true;
@@ -1812,16 +1846,20 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     const double shat_j = pref ? dc->shat_j : __ldcg(sp + jq), shat_n = pref ? dc->shat_n : __ldcg(sp + jn);
     const double *cst_j = pref ? dc->cst : d.colstat + (int64_t)jq * CS_STRIDE;          // statistics of column jq
     const double cscale_n = pref ? dc->cscale_n : __ldcg(d.colstat + (int64_t)jn * CS_STRIDE);
-    Ctl ct = cached ? dc->ct : d.ctl[c];
-    ChainState s = cached ? dc->s : d.cs[c];
+    // (the 400 bytes of control block and chain state are only copied once the plain update -- jet_fast_update, which works
+    // on the cache itself -- has been ruled out: until then four scalars of them are all that is looked at)
+    const Ctl *ctp = cached ? &dc->ct : &d.ctl[c];
+    const ChainState *stp = cached ? &dc->s : &d.cs[c];
+    const int ph0 = stp->phase, st0 = stp->status, nc0 = ctp->ncand;
+    const unsigned cm0 = (unsigned)ctp->coarse_mask;
     long long tick = d.prof ? clock64() : 0;
-    if (s.phase == PH_FINISHED || s.status != CGG_OK) return DEC_FINISHED;
-    const bool jetpass = ((unsigned)ct.coarse_mask & JET_BIT) != 0u && s.phase == PH_JET;
-    const int nc = jetpass ? 0 : ct.ncand;
-    const unsigned cmask = jetpass ? 0u : (unsigned)ct.coarse_mask;
+    if (ph0 == PH_FINISHED || st0 != CGG_OK) return DEC_FINISHED;
+    const bool jetpass = (cm0 & JET_BIT) != 0u && ph0 == PH_JET;
+    const int nc = jetpass ? 0 : nc0;
+    const unsigned cmask = jetpass ? 0u : cm0;
     double jm[NV];        // the pass's sums, identical in every lane (slots source: all of them; else only for a jet pass)
     if (src == SRC_SLOTS) {
-        const int nvals = jetpass ? jet_nvals(d.family, ((unsigned)ct.coarse_mask & JET_FULL) == 0u) : (cmask ? nc + 2 : nc);
+        const int nvals = jetpass ? jet_nvals(d.family, (cm0 & JET_FULL) == 0u) : (cmask ? nc + 2 : nc);
         if (vals_in) {
 #pragma unroll
             for (int k = 0; k < NV; ++k) jm[k] = (k < nvals) ? vals_in[k] : 0.0;
@@ -1829,7 +1867,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         if (d.sharded && d.mbox[0]) {
             // row-sharded: this shard's additive constant joins its sums (M_0 of a jet pass that delivers it, every candidate
             // sum of an exact pass), then the ranks' sums are exchanged and added in rank order
-            const bool has_m0 = jetpass && (d.family != CGG_BINOMIAL || ((unsigned)ct.coarse_mask & JET_FULL) != 0u);
+            const bool has_m0 = jetpass && (d.family != CGG_BINOMIAL || (cm0 & JET_FULL) != 0u);
 #pragma unroll
             for (int k = 0; k < NV; ++k) if (jetpass ? (k == 0 && has_m0) : (k < nc)) jm[k] += d.ll_const;
             if (!mbox_exchange(d, c, nvals, d.mbox_stamp0 + pass_no + 1u, lane, jm)) return DEC_ABORT;
@@ -1839,13 +1877,15 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
 #pragma unroll
         for (int k = 0; k < NV; ++k) jm[k] = __shfl_sync(0xffffffffu, mv, k);
     }
-    if (jetpass && d.family == CGG_BINOMIAL && ((unsigned)ct.coarse_mask & JET_FULL) == 0u) jet_light_unpack(jm);
+    if (jetpass && d.family == CGG_BINOMIAL && (cm0 & JET_FULL) == 0u) jet_light_unpack(jm);
+    // ---- the plain update: judged, published and booked straight from the deciding warp's cache (jet_fast_update)
+    if (jetpass && src == SRC_SLOTS && cached && d.early &&
+        jet_fast_update(d, c, lane, dc, jm, (cm0 & JET_FULL) == 0u, vals_in ? ~0ULL : ver))
+        return (!vals_in && ver != ~0ULL) ? DEC_PUBLISHED : DEC_CONTINUE;
+    Ctl ct = *ctp;
+    ChainState s = *stp;
     if (s.x0 != s.x0) tick = 0;   // (keeps the state loads above the first timestamp)
     CGG_TICK(12);      // state loaded, sums read
-    // ---- the plain case: publish the next pass from the round-1 verdicts now, do the book-keeping afterwards
-    bool published = false;
-    if (jetpass && src == SRC_SLOTS && cached && !vals_in && ver != ~0ULL && d.early)
-        published = jet_fast_publish(d, c, lane, dc, jm, ((unsigned)ct.coarse_mask & JET_FULL) == 0u, ver);
     // lane k: total log-likelihood of candidate k + its prior term
     double f = 0.0;
     unsigned int aflags = 0;
@@ -1962,12 +2002,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
         // the deciding warp of the persistent driver keeps the state in shared memory; global memory gets it when the
         // chain stops (the host reads it after the kernel) -- every decision otherwise
         if (!dc || fin) d.cs[c] = s;
-        if (!published) d.ctl[c] = ct;
-        else if (fin || ct.j != s.j || ct.ncand != 0 || ct.commit_j != jq || ct.commit_delta != __ldcg(&d.ctl[c].commit_delta) ||
-                 ct.coarse_mask != __ldcg(&d.ctl[c].coarse_mask) || ct.j != __ldcg(&d.ctl[c].j) || ct.cscale != __ldcg(&d.ctl[c].cscale)) {
-            d.hdr->abort = 1;      // the early publication and the complete decision disagree: must never happen; fail loudly
-            fence_gpu();
-        }
+        d.ctl[c] = ct;
         if (dc) { dc->s = s; dc->ct = ct; dc->valid = 1; }
     }
     fin = __shfl_sync(0xffffffffu, (int)fin, 0);
@@ -1977,7 +2012,7 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     if (!(src == SRC_SLOTS && cmask == 0u)) fence_gpu();
     __syncwarp();
     CGG_TICK(19);      // fence
-    return fin ? DEC_FINISHED : (published ? DEC_PUBLISHED : DEC_CONTINUE);
+    return fin ? DEC_FINISHED : DEC_CONTINUE;
 }
 
 }  // namespace cgg

@@ -1118,13 +1118,6 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
     if (G < 1) G = 1;
     d.G = (int)G;
     if (d.colcache && (int64_t)d.colcache * (int64_t)d.G * NWARPS < d.n_tiles) d.colcache = 0;    // (fewer CTAs than assumed: a warp's tiles would not fit)
-    {   // early publication of the next pass by the deciding warps (cgg_device.cuh: jet_fast_publish): on by default where a
-        // chain's decision cannot hide behind other chains' passes -- one or two chains per device, i.e. the row-sharded runs
-        // (measured: one chain +8 %, cfg5's shard +11 %; 8 chains: no difference; 4 chains on the grid-wide kernel: -4 %, the
-        // deciding warp is busier).  CGG_EARLY=0/1 overrides.  Never changes results.
-        const char *e6 = getenv("CGG_EARLY");
-        d.early = (e6 ? atoi(e6) != 0 : C <= 2) ? 1 : 0;
-    }
     {   // group passes (chains 4k .. 4k + 3 share a walk): an experiment, compiled in with -DCGG_GROUP_PASSES only;
         // then on from 12 chains (three groups, so that a group's decisions still hide behind other groups' passes); they need
         // pair passes and the X-column cache.  CGG_QUAD=0/1 overrides.
@@ -1166,6 +1159,14 @@ extern "C" int cgg_create(const cgg_config *cfg, cgg_handle **out) {
                 d.pair = 0; d.quad = 0; d.coarse = 0;       // one chain per cluster; the pre-filter's clamp flags live in global memory
             }
         }
+    }
+    {   // the plain update decided, published and booked straight from the deciding warp's cache (cgg_device.cuh:
+        // jet_fast_update): on wherever a chain's decision sits on its critical cycle -- the cluster driver, one to four
+        // chains per device, the row-sharded runs (measured: cfg2 +17 %, one chain +17 %, cfg5's shard +6 %, README shape
+        // +15 %) -- and off where three or more pairs of chains hide each other's decisions anyway (8 chains: -0.8 %, +1 %:
+        // noise).  CGG_EARLY=0/1 overrides (experiments, tests).  Never changes results.
+        const char *e6 = getenv("CGG_EARLY");
+        d.early = (e6 ? atoi(e6) != 0 : (h->cluster_S > 0 || !(d.pair && C >= 6))) ? 1 : 0;
     }
     {   // rounding allowance of an accumulated moment: one rounding per add along the longest chain of additions a value goes
         // through -- the rows a lane owns, then the warp, CTA and (row-sharded: rank) folds; the grid fold is exact (limb
