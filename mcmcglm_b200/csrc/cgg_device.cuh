@@ -1852,7 +1852,11 @@ __device__ __noinline__ int decide_chain(const Dev *dp, int c, int lane, int j_h
     const ChainState *stp = cached ? &dc->s : &d.cs[c];
     const int ph0 = stp->phase, st0 = stp->status, nc0 = ctp->ncand;
     const unsigned cm0 = (unsigned)ctp->coarse_mask;
+#ifdef CGG_DECIDER_TICKS
     long long tick = d.prof ? clock64() : 0;
+#else
+    long long tick = 0;
+#endif
     if (ph0 == PH_FINISHED || st0 != CGG_OK) return DEC_FINISHED;
     const bool jetpass = (cm0 & JET_BIT) != 0u && ph0 == PH_JET;
     const int nc = jetpass ? 0 : nc0;

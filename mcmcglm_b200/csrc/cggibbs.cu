@@ -59,8 +59,13 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
             v = __shfl_sync(0xffffffffu, v, 0);
             if (v >= VERSION_FINISHED) continue;
             all_fin = false;
-            const unsigned long long tg0 = d.prof ? globaltimer_ns() : 0;
-            const long long td0 = d.prof ? clock64() : 0;
+#ifdef CGG_PROFILE_BUILD
+            const bool dprof = d.prof != nullptr;
+#else
+            constexpr bool dprof = false;
+#endif
+            const unsigned long long tg0 = dprof ? globaltimer_ns() : 0;
+            const long long td0 = dprof ? clock64() : 0;
             const int oc = decide_chain(dp, c, lane, -1, SRC_SLOTS, cache + c, nullptr, (unsigned)v, v);  // reads the limb accumulators itself: one load per lane
             if (oc == DEC_NOT_READY) continue;                                      // pass #v still has CTAs streaming
             if (oc == DEC_ABORT) { if (lane == 0) { d.hdr->abort = 1; fence_gpu(); } return; }   // a peer rank never delivered
@@ -70,7 +75,7 @@ __device__ __noinline__ void decider_loop(const Dev *dp, int first_chain, int st
                 decider_prefetch(d, c, cache + c, lane);
                 decider_prephase(d, c, cache + c, lane);
             }
-            if (d.prof && lane == 0) {
+            if (dprof && lane == 0) {
                 atomicAdd(d.prof + 7, (unsigned long long)(clock64() - td0)); atomicAdd(d.prof + 8, 1ULL);
                 if (v < 128) { d.prof[32 + 4096 + (c * 128 + v) * 4 + 0] = tg0; d.prof[32 + 4096 + (c * 128 + v) * 4 + 1] = globaltimer_ns(); }
             }
@@ -111,7 +116,13 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
     bool prefetched = false;
     long long t_wait = 0, t_rows = 0, t_arrive = 0, n_slow = 0, t_tiles = 0, n_pref = 0, n_notready = 0, n_look = 0, n_look_ok = 0;
+    // phase counters (CGG_PROFILE=1) exist only in builds with -DCGG_PROFILE_BUILD: even switched off at run time they held 18
+    // registers across the row loops of a kernel that sits at the 255-register limit
+#ifdef CGG_PROFILE_BUILD
     const bool prof = d.prof != nullptr;
+#else
+    constexpr bool prof = false;
+#endif
     // ---- wait until decision #round of chain c is published (usually it already is).  One warp at a time polls the
     // flag for the whole CTA and, when it has advanced, fetches the chain's control block with one coalesced request
     // into shared memory; the other warps only watch shared memory.  Returns false if the wait timed out.
@@ -433,7 +444,11 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_cluster_kernel(const __grid_
     const uint32_t ring = sh.ring0 + (uint32_t)warp * RING_BYTES_PER_WARP;
     const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(sh.xs);
     double acc[NV];
+#ifdef CGG_PROFILE_BUILD
     const bool prof = d.prof != nullptr && blockIdx.x == 0 && lane == 0;      // CGG_PROFILE: phase timers of the first CTA
+#else
+    constexpr bool prof = false;
+#endif
     for (unsigned long long pass = 0;; ++pass) {
         int nc = 0;
         const long long tp0 = prof ? clock64() : 0;
@@ -1796,7 +1811,16 @@ extern "C" int cgg_run(cgg_handle *h, int64_t n_iter, const double *replay_u, ui
     CK(cudaMemsetAsync(d.acc, 0, sizeof(Acc) * (size_t)C * NV, h->stream));
     CK(cudaMemsetAsync(d.sync, 0, sizeof(ChainSync) * (size_t)C, h->stream));
     CK(cudaMemsetAsync(d.lacc, 0, sizeof(LimbAcc) * (size_t)C * NV, h->stream));   // counts restart with the versions
+#ifdef CGG_PROFILE_BUILD
     const bool want_prof = getenv("CGG_PROFILE") != nullptr;
+#else
+    const bool want_prof = false;
+    if (getenv("CGG_PROFILE")) {
+        static bool told = false;
+        if (!told) fprintf(stderr, "[cgg profile] this libcggibbs.so has no phase counters: rebuild with CGG_NVCC_EXTRA=-DCGG_PROFILE_BUILD python -m mcmcglm_b200.build -f\n");
+        told = true;
+    }
+#endif
     if (want_prof) {
         if (!h->prof_dev) CK(cudaMalloc((void **)&h->prof_dev, 8 * (32 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128)));
         CK(cudaMemsetAsync(h->prof_dev, 0, 8 * (32 + 4 * 1024 + 32 * 128 * 4 + 2 * 1024 * 32 + 32 * 128), h->stream));
