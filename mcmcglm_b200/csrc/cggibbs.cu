@@ -207,12 +207,23 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                         group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) g = 4;
                 }
             }
+            // kind of walk: 1 single, 2 pair (general: any operand source), 3 lean pair (the steady state: X_commit held by the
+            // X-column cache, X_j held or filled by the pass itself -- GroupStream<2>, no operand-source branches), 4 group of four
+            int kind = g;
+#ifdef CGG_LEAN_PAIR
+            constexpr bool LFULL = FAMILY != CGG_BINOMIAL;           // the steady-state kind of jet pass of the family
+            if (g == 2 && cc.cap > 0) {
+                const long long w1 = __double_as_longlong(sh.ctl[c * CTL_WORDS + 1]);
+                const bool full = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                if (full == LFULL && group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) kind = 3;
+            }
+#endif
             long long tB = prof ? clock64() : 0;
             t_wait += tB - tA;
             if (pair_prefetched) {
                 // the first tiles of this pass were requested ahead of time, possibly from a PREDICTED control block (same kind of
                 // pass, next column): they are only good if the real block says the same
-                bool good = g >= 2 && g == pf_g;
+                bool good = kind >= 2 && kind == pf_g;
                 if (good) {
                     const double *cwA = sh.ctl + c * CTL_WORDS;
                     const long long w0 = __double_as_longlong(cwA[0]), w1 = __double_as_longlong(cwA[1]);
@@ -279,6 +290,59 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_persistent_kernel(const __gr
                 for (int k = 0; k < 4; ++k) cta_deliver_limbs(d, sh, c + k, nvd, warp, lane, nworkers, accg[k]);
                 if (prof) t_arrive += clock64() - tC;
                 c += 3;
+                continue;
+            }
+#endif
+#ifdef CGG_LEAN_PAIR
+            if (kind == 3) {
+                const double *cw0 = sh.ctl + c * CTL_WORDS;
+                const bool was_pref = pair_prefetched;
+                pair_prefetched = false;
+                int c2 = -1; unsigned long long nround = round;
+                if (d.C >= 6) {                   // (as for general pair passes: with one or two pairs the look would only cost)
+                    if (c + 2 >= d.C) { c2 = 0; nround = round + 1; }
+                    else if (c + 3 < d.C) { c2 = c + 2; }
+                    if (c2 == c) c2 = -1;
+                }
+                auto early = [&]() {
+                    if (c2 >= 0 && warp == (int)((round + (unsigned long long)(c >> 1)) % NWARPS)) pair_lookahead(d, sh, c2, nround, lane);
+                };
+                auto after = [&]() {
+                    if (c2 < 0) return;
+                    double pred[2];
+                    const double *nA = sh.ctl + c2 * CTL_WORDS;
+                    if (pair_lookahead(d, sh, c2, nround, lane)) {
+                        if (!pair_batchable(nA, nA + CTL_WORDS)) return;
+                    } else {
+                        const long long w0 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[0]), 0), w1 = __shfl_sync(0xffffffffu, __double_as_longlong(nA[1]), 0);
+                        const int jp = (int)(w0 & 0xffffffffLL);
+                        const unsigned mk = (unsigned)(w1 >> 32);
+                        if (!(mk & JET_BIT) || jp < 0 || (long long)jp >= (long long)d.p) return;
+                        const int jn = (jp + 1 == (int)d.p) ? 0 : jp + 1;
+                        pred[0] = __longlong_as_double((long long)(unsigned)jn);
+                        pred[1] = __longlong_as_double(((long long)mk << 32) | (long long)(unsigned)jp);
+                        nA = pred;
+                    }
+                    const long long w0 = __double_as_longlong(nA[0]), w1 = __double_as_longlong(nA[1]);
+                    const bool full2 = FAMILY != CGG_BINOMIAL || (((unsigned)(w1 >> 32)) & JET_FULL);
+                    if (!(((unsigned)(w1 >> 32)) & JET_BIT) || (int)(w0 & 0xffffffffLL) < 0 || full2 != LFULL) return;
+                    if (!group_cache_ok(cc, (int)(w1 & 0xffffffffLL))) return;
+                    pf_j = (int)(w0 & 0xffffffffLL); pf_cj = (int)(w1 & 0xffffffffLL); pf_full = full2; pf_g = 3;
+                    GroupStream<2> ns(d, c2, nA, wid, W, lane, ring, cc, FAMILY != CGG_BINOMIAL || full2);
+                    ns.prologue(false);
+                    pair_prefetched = true;
+                };
+                double accl[2][NV];
+                warp_pass_group<FAMILY, LFULL, 2>(d, c, cw0, wid, W, lane, ring, s_l1p, was_pref, cc, early, after, accl);
+                any = true;
+                n_pref += pair_prefetched ? 1 : 0;
+                long long tC = prof ? clock64() : 0;
+                t_rows += tC - tB; t_tiles += tC - tB;
+                const int nvd = jet_nvals(FAMILY, !LFULL);
+                cta_deliver_limbs(d, sh, c, nvd, warp, lane, nworkers, accl[0]);
+                cta_deliver_limbs(d, sh, c + 1, nvd, warp, lane, nworkers, accl[1]);
+                if (prof) t_arrive += clock64() - tC;
+                ++c;
                 continue;
             }
 #endif
