@@ -15,8 +15,3 @@ C2="python bench.py --workload cfg2 --steps 3 --warmup 3 --no-e2e --no-cpu"
 $C2 > gpurun_out/${R}_plain_cfg2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sweep_cluster -s 4 -c 1 -f -o gpurun_out/${R}_cluster_cfg2 $C2 > gpurun_out/${R}_ncu_full_c2.log 2>&1
 ls -la gpurun_out/${R}_*.ncu-rep gpurun_out/${R}_launches_cfg3.csv
-B="python bench.py --no-e2e --no-cpu --steps 3 --warmup 3"
-( for e in 0 1 0 1; do echo "== cfg3 p=100 early=$e"; CGG_EARLY=$e timeout 300 $B --workload cfg3 --cols 100 2>&1 | cut -c1-100 | tail -1; done
-echo "== README shape (gaussian n=1000 p=3, 1 chain)"; timeout 300 $B --rows 1000 --cols 3 --chains 1 --family gaussian --prior normal --workload cfg2 2>&1 | cut -c1-100 | tail -1
-) > gpurun_out/${R}_ab.log 2>&1
-cat gpurun_out/${R}_ab.log
