@@ -161,6 +161,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
+// the same under a predicate, in ONE instruction stream: no branch around the copy, and consecutive predicated copies stay
+// one LDGSTS group for ptxas (which puts three filler instructions in front of every group)
+__device__ __forceinline__ void cp_async16_if(bool p, uint32_t smem_addr, const void *gptr) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(smem_addr), "l"(gptr), "r"((int)p) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -729,13 +734,12 @@ struct GroupStream {
         xc_slot = cc.base + (uint32_t)(((cj >= 0 && cc.tag0 == cj) ? 0 : 1) * cc.cap) * 512u;    // (the caller checked group_cache_ok)
     }
     __device__ __forceinline__ void issue_next(unsigned st) {
-        if (pe < pe_last) {
-            const uint32_t sa = sbase + st * (RING_OPS * 512u);
+        const bool ok = pe < pe_last;
+        const uint32_t sa = sbase + st * (RING_OPS * 512u);
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) cp_async16(sa + (uint32_t)k * 512u, pe + k * lde);
-            if (need_y) cp_async16(sa + (uint32_t)NCH * 512u, y0 + (pe - eta0));
-            if (fillJ) cp_async16(xj_slot + (uint32_t)t_issue * 512u, xj0 + (pe - eta0));
-        }
+        for (int k = 0; k < NCH; ++k) cp_async16_if(ok, sa + (uint32_t)k * 512u, pe + k * lde);
+        if (need_y) cp_async16_if(ok, sa + (uint32_t)NCH * 512u, y0 + (pe - eta0));           // (need_y is a compile-time constant of the pass)
+        cp_async16_if(ok && fillJ, xj_slot + (uint32_t)t_issue * 512u, xj0 + (pe - eta0));
         cp_async_commit();
         pe += step;
         ++t_issue;
