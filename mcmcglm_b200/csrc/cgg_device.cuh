@@ -441,12 +441,11 @@ __device__ __forceinline__ void warp_pass_jet(const Dev &d, const ChainStream &c
         const double *const pe_end = eta + cs.n_tiles * TILE_ROWS + 2 * lane + (RING_D - 1) * step;
         const uint32_t sbase = cs.slot0;
         auto issue_next = [&](unsigned st) {       // the tile at the running pointers goes to ring stage st
-            if (pe < pe_last) {
-                const uint32_t sa = sbase + st * (RING_OPS * 512u);
-                cp_async16(sa, pe);
-                cp_async16(sa + 512u, py); cp_async16(sa + 1024u, px);
-                if (cj >= 0) cp_async16(sa + 1536u, pc);
-            }
+            const bool ok = pe < pe_last;          // (predicated copies, no branch: see cp_async16_if)
+            const uint32_t sa = sbase + st * (RING_OPS * 512u);
+            cp_async16_if(ok, sa, pe);
+            cp_async16_if(ok, sa + 512u, py); cp_async16_if(ok, sa + 1024u, px);
+            cp_async16_if(ok && cj >= 0, sa + 1536u, pc);
             cp_async_commit();
             pe += step; py += step; px += step; pc += step;
         };
