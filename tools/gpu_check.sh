@@ -1,3 +1,4 @@
+# (the CGG_PROFILE lines below need a library built with CGG_NVCC_EXTRA=-DCGG_PROFILE_BUILD python -m mcmcglm_b200.build -f)
 # quick GPU regression: parity/jet/api tests, then short benches with the phase counters
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_jet.py tests/test_gpu_parity.py tests/test_gpu_api.py tests/test_gpu_coarse.py -x -q 2>&1 | tail -4 ) > gpurun_out/gpu_tests.log 2>&1

@@ -1,3 +1,5 @@
+# group passes need a library built with -DCGG_GROUP_PASSES (CGG_NVCC_EXTRA=-DCGG_GROUP_PASSES python -m mcmcglm_b200.build -f);
+# CGG_PROFILE lines need -DCGG_PROFILE_BUILD as well.
 # early publication + group passes: tests, then A/B benches
 mkdir -p gpurun_out
 ( timeout 1200 python -m pytest tests/test_gpu_edges.py tests/test_gpu_jet.py tests/test_gpu_parity.py -x -q 2>&1 | tail -5 ) > gpurun_out/r2n_tests.log 2>&1

@@ -1,3 +1,5 @@
+# same-box A/B of the plain-update path (CGG_EARLY) on the latency-bound workloads.  tools/_old/libcggibbs_old.so was a build of the
+# round's first commit (git show 8b5f41b:... into a scratch tree, ABI constant patched to 3), loaded through CGG_LIB; not kept.
 mkdir -p gpurun_out
 ( timeout 1500 python -m pytest tests/test_gpu_jet.py tests/test_gpu_parity.py tests/test_gpu_edges.py tests/test_gpu_api.py tests/test_gpu_wider.py -x -q 2>&1 | tail -12 ) > gpurun_out/r2s_tests.log 2>&1
 cat gpurun_out/r2s_tests.log

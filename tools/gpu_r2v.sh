@@ -1,3 +1,5 @@
+# (the variant libraries under tools/ and tools/_old/ were scratch builds -- an older commit, or the working tree with one -D
+# flag / one edit -- loaded through CGG_LIB for a same-box A/B; they are not kept: rebuild them the same way to re-run this)
 # lean pair passes (-DCGG_LEAN_PAIR, tools/libcggibbs_lean.so): same-box A/B and parity
 mkdir -p gpurun_out
 B="python bench.py --no-e2e --no-cpu --steps 3 --warmup 3"

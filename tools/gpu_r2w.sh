@@ -1,3 +1,5 @@
+# (the variant libraries under tools/ and tools/_old/ were scratch builds -- an older commit, or the working tree with one -D
+# flag / one edit -- loaded through CGG_LIB for a same-box A/B; they are not kept: rebuild them the same way to re-run this)
 # predicated copies in the lean pair loop: same-box A/B (tools/libcggibbs_pred.so vs the built library)
 mkdir -p gpurun_out
 B="python bench.py --no-e2e --no-cpu --steps 3 --warmup 3"

@@ -1,3 +1,5 @@
+# (the variant libraries under tools/ and tools/_old/ were scratch builds -- an older commit, or the working tree with one -D
+# flag / one edit -- loaded through CGG_LIB for a same-box A/B; they are not kept: rebuild them the same way to re-run this)
 # 32-bit tile counters in the lean loop (tools/libcggibbs_cnt.so) vs the built library, parity tests on the variant, and a
 # --set full capture of the built library's steady launch
 mkdir -p gpurun_out
