@@ -18,17 +18,21 @@ using namespace cgg;
 // Kernels
 // ============================================================================================
 
-// K3 (persistent driver).  Launched cooperatively, one 16-warp CTA per SM, so that every warp of the grid
-// is resident.  Warps are specialised:
-//   worker warps  own a fixed set of 64-row tiles for the whole run and walk the chains round-robin.  A
-//                 chain's pass #r may start as soon as its decision #r is published (version >= r).  Workers
-//                 deliver their partial sums to their CTA without blocking; the last worker of a CTA folds
-//                 them into the chain's exact accumulators and arrives for the CTA.
-//   decider warps (the last warp of CTA c, one per chain) watch their chain's arrival counter and run the
-//                 chain's slice state machine the moment a pass is complete, then publish the next version.
-// There is no grid-wide barrier and no worker ever runs a decision: decisions of different chains proceed
-// concurrently on different SMs, and with >= 2 chains per device their latency is hidden behind the
-// streaming of the other chains.
+// K3 (persistent driver).  Launched cooperatively, one 8-warp CTA per SM, so that every warp of the grid is resident:
+// d.G worker CTAs and, behind them, ONE decider CTA.
+//   worker warps  own a fixed set of 64-row tiles for the whole run and walk the chains round-robin.  A chain's pass #r
+//                 may start as soon as its decision #r is published (version >= r).  Kinds of walk: a single chain
+//                 (worker_pass: jet or exact pass), a pair of chains at the same coordinate through the general loop
+//                 (warp_pass_jet2: any operand source), a pair through the lean loop (warp_pass_group<.., 2>: the steady
+//                 state, everything but eta from the X-column cache), and -- builds with -DCGG_GROUP_PASSES -- four chains.
+//                 A warp's sums go to its CTA without blocking; the last warp of the CTA to arrive folds them in warp order
+//                 and adds the CTA's sums to the chain's limb accumulators (cta_deliver_limbs): no fence, no flag.
+//   decider warps (warp w of the decider CTA decides chains w, w + 8, ...) watch their chains' accumulators and the moment
+//                 a pass is complete either take the plain-update path (jet_fast_update: judge round 1, publish, book) or
+//                 run the general state machine (decide_chain), publish the next version, and then prepare the chain's next
+//                 decision while its pass streams (decider_prefetch, decider_prephase).
+// There is no grid-wide barrier and no worker ever runs a decision: decisions of different chains proceed concurrently,
+// and with >= 3 pairs of chains per device their latency hides behind the streaming of the other pairs.
 constexpr unsigned long long VERSION_FINISHED = 1ULL << 62;
 
 __device__ __forceinline__ bool wait_timed_out(const Dev &d, unsigned long long t0, int lane) {
